@@ -1,0 +1,20 @@
+"""dewi_b200 -- B200-native backend for DEWI's retrieval hot path.
+
+Public names mirror the reference package (`dewi`, src/dewi/__init__.py:5-15 plus the modules its
+README imports from): `DewiIndex`, `Payload`, `Weights`, `Signals`, `DewiScorer`, `RobustStats`.
+Importing the package never touches the GPU; constructing an index or scoring does, and raises
+ImportError when libdewi_b200.so or a B200 is missing (no CPU fallback).
+"""
+
+__version__ = "0.1.0"
+
+from .types import Payload, Signals, Weights  # noqa: F401
+from .backends import BaseIndex, CudaIndex, IndexBackend  # noqa: F401
+from .index import DewiIndex  # noqa: F401
+from .scorer import DewiScorer, RobustStats  # noqa: F401
+from .redundancy import cross_modal_similarity, redundancy_join  # noqa: F401
+
+__all__ = [
+    "__version__", "DewiIndex", "BaseIndex", "CudaIndex", "IndexBackend", "Payload", "Signals", "Weights",
+    "DewiScorer", "RobustStats", "cross_modal_similarity", "redundancy_join",
+]

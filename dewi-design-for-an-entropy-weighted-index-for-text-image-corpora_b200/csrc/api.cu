@@ -1,0 +1,440 @@
+// C ABI of libdewi_b200.so: index handle, search orchestration, error plumbing.
+// Entry points are documented in include/dewi_b200.h next to the reference code they replace.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+
+namespace dewi {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    const size_t want = need + need / 4;
+    DEWI_CUDA(cudaMalloc(&p, want));
+    bytes = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+// Minimum corpus size for which the tensor-core sweep is selected automatically.
+constexpr int64_t kTcMinRows = 2048;
+
+}  // namespace
+}  // namespace dewi
+
+using namespace dewi;
+
+struct dewi_index {
+  int dim = 0, space = 0, dtype = 0, device = 0, sm_count = 0;
+  int64_t n = 0, cap = 0, id_base = 0;
+  float* rows_f32 = nullptr;          // [cap, dim]  (fp32 mode)
+  __nv_bfloat16* plane0 = nullptr;    // [cap, dim]  bf16 rows / hi plane
+  __nv_bfloat16* plane1 = nullptr;    // [cap, dim]  lo plane (fp32 mode)
+  float* dewi_col = nullptr;          // [cap]
+  float* ent_col = nullptr;           // [cap]
+  int* bad_flag = nullptr;
+  // cached tensor maps of the corpus planes
+  CUtensorMap map_e0, map_e1;
+  int64_t map_rows = -1;
+  int map_box = 0;
+  // workspaces
+  DevBuf stage, qraw, qn, q0, q1, part_s, part_i, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
+      out_score;
+  int last_launches = 0;
+};
+
+namespace {
+
+int set_device(const dewi_index* h) {
+  DEWI_CUDA(cudaSetDevice(h->device));
+  return 0;
+}
+
+int grow(dewi_index* h, int64_t need_rows, cudaStream_t stream) {
+  if (need_rows <= h->cap) return 0;
+  const int64_t newcap = std::max<int64_t>(need_rows, h->cap + h->cap / 2);
+  const size_t d = static_cast<size_t>(h->dim);
+  auto regrow = [&](void** p, size_t elem_bytes_per_row) -> int {
+    void* np = nullptr;
+    DEWI_CUDA(cudaMalloc(&np, static_cast<size_t>(newcap) * elem_bytes_per_row));
+    if (*p && h->n > 0)
+      DEWI_CUDA(cudaMemcpyAsync(np, *p, static_cast<size_t>(h->n) * elem_bytes_per_row, cudaMemcpyDeviceToDevice, stream));
+    if (*p) {
+      DEWI_CUDA(cudaStreamSynchronize(stream));
+      DEWI_CUDA(cudaFree(*p));
+    }
+    *p = np;
+    return 0;
+  };
+  if (h->dtype == DEWI_DTYPE_FP32) {
+    DEWI_TRY(regrow(reinterpret_cast<void**>(&h->rows_f32), d * 4));
+    if (h->space == DEWI_SPACE_COSINE) DEWI_TRY(regrow(reinterpret_cast<void**>(&h->plane1), d * 2));
+  }
+  if (h->dtype == DEWI_DTYPE_BF16 || h->space == DEWI_SPACE_COSINE)
+    DEWI_TRY(regrow(reinterpret_cast<void**>(&h->plane0), d * 2));
+  {
+    // payload columns default to zero (Payload() defaults, types.py:11-18)
+    float* nd = nullptr;
+    float* ne = nullptr;
+    DEWI_CUDA(cudaMalloc(&nd, static_cast<size_t>(newcap) * 4));
+    DEWI_CUDA(cudaMalloc(&ne, static_cast<size_t>(newcap) * 4));
+    DEWI_CUDA(cudaMemsetAsync(nd, 0, static_cast<size_t>(newcap) * 4, stream));
+    DEWI_CUDA(cudaMemsetAsync(ne, 0, static_cast<size_t>(newcap) * 4, stream));
+    if (h->dewi_col && h->n > 0) {
+      DEWI_CUDA(cudaMemcpyAsync(nd, h->dewi_col, static_cast<size_t>(h->n) * 4, cudaMemcpyDeviceToDevice, stream));
+      DEWI_CUDA(cudaMemcpyAsync(ne, h->ent_col, static_cast<size_t>(h->n) * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+    if (h->dewi_col) cudaFree(h->dewi_col);
+    if (h->ent_col) cudaFree(h->ent_col);
+    h->dewi_col = nd;
+    h->ent_col = ne;
+  }
+  h->cap = newcap;
+  h->map_rows = -1;
+  return 0;
+}
+
+int ensure_corpus_maps(dewi_index* h, int box_rows) {
+  if (h->map_rows == h->n && h->map_box == box_rows) return 0;
+  DEWI_TRY(tc_encode_rows_map(&h->map_e0, h->plane0, h->n, h->dim, box_rows));
+  if (h->plane1)
+    DEWI_TRY(tc_encode_rows_map(&h->map_e1, h->plane1, h->n, h->dim, box_rows));
+  else
+    h->map_e1 = h->map_e0;
+  h->map_rows = h->n;
+  h->map_box = box_rows;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dewi_abi_version(void) { return DEWI_B200_ABI_VERSION; }
+
+const char* dewi_last_error(void) { return g_last_error.c_str(); }
+
+int dewi_device_check(int device, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0)
+    return fail(std::string("no CUDA device available: ") + cudaGetErrorString(e) + " -- this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail("device ordinal out of range");
+  cudaDeviceProp prop;
+  DEWI_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(std::string("device '") + prop.name + "' is compute capability " + std::to_string(prop.major) + "." +
+                std::to_string(prop.minor) + "; libdewi_b200 is built for sm_100a (B200) only");
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (free_bytes || total_bytes) {
+    size_t f = 0, t = 0;
+    DEWI_CUDA(cudaSetDevice(device));
+    DEWI_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+  }
+  return 0;
+}
+
+int dewi_index_create(int dim, int space, int dtype, int device, dewi_index_t** out) {
+  if (!out) return fail("out is NULL");
+  if (dim <= 0) return fail("dim must be positive");
+  if (space != DEWI_SPACE_COSINE && space != DEWI_SPACE_L2) return fail("unknown space");
+  if (dtype != DEWI_DTYPE_FP32 && dtype != DEWI_DTYPE_BF16) return fail("unknown dtype");
+  int sms = 0;
+  DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
+  DEWI_CUDA(cudaSetDevice(device));
+  dewi_index* h = new dewi_index();
+  h->dim = dim;
+  h->space = space;
+  h->dtype = dtype;
+  h->device = device;
+  h->sm_count = sms;
+  if (cudaMalloc(&h->bad_flag, sizeof(int)) != cudaSuccess) {
+    delete h;
+    return fail("cudaMalloc failed");
+  }
+  cudaMemset(h->bad_flag, 0, sizeof(int));
+  *out = h;
+  return 0;
+}
+
+int dewi_index_destroy(dewi_index_t* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaFree(h->rows_f32);
+  cudaFree(h->plane0);
+  cudaFree(h->plane1);
+  cudaFree(h->dewi_col);
+  cudaFree(h->ent_col);
+  cudaFree(h->bad_flag);
+  for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->cand_idx, &h->cand_sim,
+                    &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score})
+    b->release();
+  delete h;
+  return 0;
+}
+
+int dewi_index_reserve(dewi_index_t* h, int64_t rows) {
+  if (!h) return fail("null handle");
+  DEWI_TRY(set_device(h));
+  return grow(h, rows, nullptr);
+}
+
+int dewi_index_set_id_base(dewi_index_t* h, int64_t id_base) {
+  if (!h) return fail("null handle");
+  h->id_base = id_base;
+  return 0;
+}
+
+int dewi_index_append(dewi_index_t* h, const float* rows, int64_t n, int normalized, int src_is_host, void* stream_) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("negative row count");
+  if (n == 0) return 0;
+  if (!rows) return fail("rows is NULL");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  if (h->n + n >= (int64_t(1) << 31)) return fail("a shard holds at most 2^31-1 rows");
+  DEWI_TRY(grow(h, h->n + n, stream));
+  const int do_norm = (h->space == DEWI_SPACE_COSINE && !normalized) ? 1 : 0;
+  const size_t d = static_cast<size_t>(h->dim);
+  const int64_t chunk = src_is_host ? std::max<int64_t>(1, (int64_t(256) << 20) / static_cast<int64_t>(d * 4)) : n;
+  for (int64_t done = 0; done < n; done += chunk) {
+    const int64_t m = std::min(chunk, n - done);
+    const float* src = rows + static_cast<size_t>(done) * d;
+    if (src_is_host) {
+      DEWI_TRY(h->stage.ensure(static_cast<size_t>(m) * d * 4));
+      DEWI_CUDA(cudaMemcpyAsync(h->stage.p, src, static_cast<size_t>(m) * d * 4, cudaMemcpyHostToDevice, stream));
+      src = h->stage.as<float>();
+    }
+    const size_t off = static_cast<size_t>(h->n + done) * d;
+    DEWI_TRY(launch_prep_corpus(src, m, h->dim, do_norm, h->rows_f32 ? h->rows_f32 + off : nullptr,
+                                h->plane0 ? h->plane0 + off : nullptr, h->plane1 ? h->plane1 + off : nullptr,
+                                h->bad_flag, stream));
+    if (src_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));  // staging buffer is reused
+  }
+  if (do_norm) {
+    int bad = 0;
+    DEWI_CUDA(cudaMemcpyAsync(&bad, h->bad_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+    if (bad) {
+      DEWI_CUDA(cudaMemsetAsync(h->bad_flag, 0, sizeof(int), stream));
+      return fail("zero-norm embedding in cosine space (the reference would store a NaN row, backends.py:405)");
+    }
+  }
+  h->n += n;
+  h->map_rows = -1;
+  return 0;
+}
+
+int dewi_index_set_payload(dewi_index_t* h, const float* dewi_v, const float* ent_v, int64_t offset, int64_t n,
+                           int src_is_host, void* stream_) {
+  if (!h) return fail("null handle");
+  if (offset < 0 || n < 0 || offset + n > h->n) return fail("payload range outside the corpus");
+  if (n == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  const cudaMemcpyKind kind = src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  DEWI_CUDA(cudaMemcpyAsync(h->dewi_col + offset, dewi_v, static_cast<size_t>(n) * 4, kind, stream));
+  DEWI_CUDA(cudaMemcpyAsync(h->ent_col + offset, ent_v, static_cast<size_t>(n) * 4, kind, stream));
+  if (src_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int dewi_index_size(const dewi_index_t* h, int64_t* rows) {
+  if (!h || !rows) return fail("null argument");
+  *rows = h->n;
+  return 0;
+}
+
+int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host) {
+  if (!h || !out_host) return fail("null argument");
+  if (row < 0 || row >= h->n) return fail("row out of range");
+  DEWI_TRY(set_device(h));
+  const size_t d = static_cast<size_t>(h->dim);
+  if (h->rows_f32) {
+    DEWI_CUDA(cudaMemcpy(out_host, h->rows_f32 + static_cast<size_t>(row) * d, d * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint16_t> tmp(d);
+    DEWI_CUDA(cudaMemcpy(tmp.data(), h->plane0 + static_cast<size_t>(row) * d, d * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < d; ++i) {
+      const uint32_t u = static_cast<uint32_t>(tmp[i]) << 16;
+      std::memcpy(&out_host[i], &u, 4);
+    }
+  }
+  return 0;
+}
+
+int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
+                            int64_t* out_id, float* out_dewi, float* out_ent, void* stream_) {
+  if (!h) return fail("null handle");
+  if (B <= 0 || kcand <= 0) return fail("B and kcand must be positive");
+  if (h->n <= 0) return fail("index is empty");
+  if (flags & DEWI_FLAG_SCOPE_FULL) return fail("full-corpus blend scope is not implemented (not the reference's semantics)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  h->last_launches = 0;
+  const int dim = h->dim;
+  const int b_pad = static_cast<int>(round_up(B, kQueryBlock));
+  const int n_qb = b_pad / kQueryBlock;
+  const int kc_valid = static_cast<int>(std::min<int64_t>(kcand, h->n));
+
+  bool use_tc = h->space == DEWI_SPACE_COSINE && h->plane0 && tc_supported(dim, h->n) && !(flags & DEWI_FLAG_FORCE_SIMT) &&
+                (h->n >= kTcMinRows || (flags & DEWI_FLAG_FORCE_TC));
+  int mode = (h->dtype == DEWI_DTYPE_FP32) ? 2 : ((flags & DEWI_FLAG_PRECISE_QUERY) ? 1 : 0);
+  // list capacity: over-fetch so that rounding in the bf16-plane sweep cannot push a true top-2k row out
+  int kc = (mode == 0) ? std::max(32, kc_valid + 16) : kc_valid + 8;
+  TcPlan plan;
+  if (use_tc) {
+    if (tc_make_plan(mode, dim, h->n, n_qb, kc, h->sm_count, &plan) != 0) {
+      if (flags & DEWI_FLAG_FORCE_TC) return 1;
+      use_tc = false;
+    }
+  } else if (flags & DEWI_FLAG_FORCE_TC) {
+    return fail("tcgen05 sweep not applicable (needs cosine space and dim % 64 == 0)");
+  }
+
+  // queries -> normalised fp32 + bf16 planes
+  DEWI_TRY(h->qn.ensure(static_cast<size_t>(b_pad) * dim * 4));
+  DEWI_TRY(h->q0.ensure(static_cast<size_t>(b_pad) * dim * 2));
+  DEWI_TRY(h->q1.ensure(static_cast<size_t>(b_pad) * dim * 2));
+  const int qnorm = (h->space == DEWI_SPACE_COSINE && !(flags & DEWI_FLAG_QUERY_NORMALIZED)) ? 1 : 0;
+  DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
+                               h->q1.as<__nv_bfloat16>(), stream));
+  h->last_launches++;
+
+  const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
+  const int exact_is_bf16 = h->rows_f32 ? 0 : 1;
+  Partials parts;
+  if (use_tc) {
+    DEWI_TRY(ensure_corpus_maps(h, plan.n_tile));
+    CUtensorMap mq0, mq1;
+    DEWI_TRY(tc_encode_rows_map(&mq0, h->q0.p, b_pad, dim, kQueryBlock));
+    DEWI_TRY(tc_encode_rows_map(&mq1, h->q1.p, b_pad, dim, kQueryBlock));
+    const size_t items = static_cast<size_t>(plan.n_chunks) * n_qb;
+    DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
+    DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
+    DEWI_TRY(tc_launch(plan, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
+                       h->part_i.as<int>(), stream));
+    h->last_launches++;
+    parts.n_chunks = plan.n_chunks;
+  } else {
+    kc = kc_valid;
+    int n_chunks = 1;
+    DEWI_TRY(simt_plan(h->n, B, h->sm_count, &n_chunks));
+    const size_t items = static_cast<size_t>(n_chunks) * n_qb;
+    DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
+    DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
+    DEWI_TRY(simt_launch(exact_rows, exact_is_bf16, h->n, dim, h->space, h->qn.as<float>(), B, kc, n_chunks,
+                         h->part_s.as<float>(), h->part_i.as<int>(), stream));
+    h->last_launches++;
+    parts.n_chunks = n_chunks;
+  }
+  parts.s = h->part_s.as<float>();
+  parts.i = h->part_i.as<int>();
+  parts.n_qb = n_qb;
+  parts.kc = kc;
+
+  DEWI_TRY(h->cand_idx.ensure(static_cast<size_t>(B) * kc * 4));
+  DEWI_TRY(h->cand_sim.ensure(static_cast<size_t>(B) * kc * 4));
+  DEWI_TRY(launch_merge_select(parts, B, kc, h->cand_idx.as<int>(), h->cand_sim.as<float>(), stream));
+  h->last_launches++;
+  if (use_tc) {
+    DEWI_TRY(launch_rescore(exact_rows, exact_is_bf16, dim, h->qn.as<float>(), h->cand_idx.as<int>(), B, kc,
+                            h->cand_sim.as<float>(), stream));
+    h->last_launches++;
+  }
+  DEWI_TRY(launch_finalize_local(h->cand_idx.as<int>(), h->cand_sim.as<float>(), B, kc, kcand, h->id_base, h->dewi_col,
+                                 h->ent_col, out_sim, out_id, out_dewi, out_ent, stream));
+  h->last_launches++;
+  return 0;
+}
+
+int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int ncand,
+                int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
+                float* out_score, int device, void* stream_) {
+  if (B <= 0 || ncand <= 0 || k <= 0) return fail("B, ncand and k must be positive");
+  if (cand_count > ncand) cand_count = ncand;
+  if (k > cand_count) return fail("k exceeds the number of candidates (k > N)");
+  DEWI_CUDA(cudaSetDevice(device));
+  return launch_rerank(sim, id, dewi_v, ent_v, B, ncand, cand_count, k, w_sim, w_dewi, pref, use_pref, out_id, out_score,
+                       static_cast<cudaStream_t>(stream_));
+}
+
+int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref, int flags,
+                      int64_t* out_id, float* out_score, void* stream_) {
+  if (!h) return fail("null handle");
+  if (B <= 0 || k <= 0) return fail("B and k must be positive");
+  if (k > h->n) return fail("k exceeds the number of indexed rows (ExactIndex raises ValueError, backends.py:468)");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  const int kcand = static_cast<int>(std::min<int64_t>(2 * static_cast<int64_t>(k), h->n));  // backends.py:440
+  const bool host_io = (flags & DEWI_FLAG_HOST_IO) != 0;
+  const float* q_dev = queries;
+  if (host_io) {
+    DEWI_TRY(h->qraw.ensure(static_cast<size_t>(B) * h->dim * 4));
+    DEWI_CUDA(cudaMemcpyAsync(h->qraw.p, queries, static_cast<size_t>(B) * h->dim * 4, cudaMemcpyHostToDevice, stream));
+    q_dev = h->qraw.as<float>();
+  }
+  const size_t nc = static_cast<size_t>(B) * kcand;
+  DEWI_TRY(h->loc_sim.ensure(nc * 4));
+  DEWI_TRY(h->loc_id.ensure(nc * 8));
+  DEWI_TRY(h->loc_dewi.ensure(nc * 4));
+  DEWI_TRY(h->loc_ent.ensure(nc * 4));
+  DEWI_TRY(dewi_index_search_local(h, q_dev, B, kcand, flags, h->loc_sim.as<float>(), h->loc_id.as<int64_t>(),
+                                   h->loc_dewi.as<float>(), h->loc_ent.as<float>(), stream_));
+  int64_t* d_id = out_id;
+  float* d_sc = out_score;
+  if (host_io) {
+    DEWI_TRY(h->out_id.ensure(static_cast<size_t>(B) * k * 8));
+    DEWI_TRY(h->out_score.ensure(static_cast<size_t>(B) * k * 4));
+    d_id = h->out_id.as<int64_t>();
+    d_sc = h->out_score.as<float>();
+  }
+  // numpy evaluates (1 - eta) in float64 and rounds the weak scalar to float32 (backends.py:461)
+  const float w_sim = static_cast<float>(1.0 - eta);
+  const float w_dewi = static_cast<float>(eta);
+  const float pref = static_cast<float>(entropy_pref);
+  DEWI_TRY(launch_rerank(h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(), h->loc_ent.as<float>(),
+                         B, kcand, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
+  h->last_launches++;
+  if (host_io) {
+    DEWI_CUDA(cudaMemcpyAsync(out_id, d_id, static_cast<size_t>(B) * k * 8, cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaMemcpyAsync(out_score, d_sc, static_cast<size_t>(B) * k * 4, cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+int dewi_index_last_launches(const dewi_index_t* h, int* launches) {
+  if (!h || !launches) return fail("null argument");
+  *launches = h->last_launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Internal declarations shared by the translation units of libdewi_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/dewi_b200.h"
+
+namespace dewi {
+
+// ---- error plumbing (thread-local message behind dewi_last_error) -----------------------------
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+#define DEWI_CUDA(expr)                                                                              \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::dewi::fail(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + ":" + \
+                          std::to_string(__LINE__) + ")");                                           \
+  } while (0)
+#define DEWI_TRY(expr)     \
+  do {                     \
+    int _r = (expr);       \
+    if (_r != 0) return _r; \
+  } while (0)
+
+constexpr int kQueryBlock = 128;  // queries per MMA M-tile == TMEM lanes
+constexpr int kKBlock = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int kMaxStages = 8;
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Partial candidate lists: [n_items][kc][128] (score) / (row index); item = chunk * n_qb + qb.
+struct Partials {
+  float* s = nullptr;
+  int* i = nullptr;
+  int n_chunks = 0;
+  int n_qb = 0;
+  int kc = 0;
+};
+
+// ---- tcgen05 sweep (search_tc.cu) ------------------------------------------------------------
+// mode 0: S = Q0.E0 ; mode 1: S = (Q0+Q1).E0 ; mode 2: S = Q0.E0 + Q1.E0 + Q0.E1
+struct TcPlan {
+  int mode;
+  int n_tile;    // corpus rows per MMA (N): 128 or 256
+  int n_stages;  // smem ring depth
+  int n_chunks;  // corpus chunks (work items per query block)
+  int grid;
+  size_t smem_bytes;
+};
+int tc_supported(int dim, int64_t n_rows);
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan);
+int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
+int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+              const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
+              cudaStream_t stream);
+
+// ---- CUDA-core exact sweep (search_simt.cu) --------------------------------------------------
+int simt_plan(int64_t n_rows, int B, int sm_count, int* n_chunks);
+int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, int space, const float* qn, int B, int kc,
+                int n_chunks, float* part_s, int* part_i, cudaStream_t stream);
+
+// ---- selection / re-rank (select.cu) ---------------------------------------------------------
+int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
+int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
+                   float* cand_sim, cudaStream_t stream);
+int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
+                          const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
+                          float* out_ent, cudaStream_t stream);
+int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
+                  int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
+                  float* out_score, cudaStream_t stream);
+
+// ---- operand preparation (prep.cu) -----------------------------------------------------------
+// rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.
+int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream);
+// queries fp32 [B, dim] -> qn fp32 [b_pad, dim], q hi/lo bf16 [b_pad, dim] (rows >= B zeroed).
+int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
+                        __nv_bfloat16* lo, cudaStream_t stream);
+
+}  // namespace dewi

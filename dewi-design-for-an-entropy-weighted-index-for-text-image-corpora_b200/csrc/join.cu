@@ -1,0 +1,223 @@
+// K5 -- redundancy similarity pass.
+//
+// dewi_similarity_dense: `F.normalize(t) @ F.normalize(i).T` exactly as
+//   RedundancyEstimator.compute_cross_modal_similarity does after the CLIP forward
+//   (reference src/dewi/signals/redundancy.py:36-38), dense fp32 output for small inputs.
+// dewi_join: the same product with the [M, N] matrix never materialised: a fused epilogue keeps
+//   per-row max / argmax / count(sim >= tau) and appends (i, j, sim) pairs.  The reference defines
+//   no such reduction; the definition lives in include/dewi_b200.h.
+//
+// This translation unit is the fp32 CUDA-core implementation (64x64 tiles, 4x4 register blocking,
+// shared-memory staged).  It is exact to fp32 rounding and serves as the small-size path.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace dewi {
+namespace {
+
+__global__ void normalize_rows_kernel(const float* __restrict__ src, long long n, int d, float eps,
+                                      float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n; row += warps) {
+    const float* s = src + static_cast<size_t>(row) * d;
+    float ss = 0.f;
+    for (int k = lane; k < d; k += 32) ss = fmaf(s[k], s[k], ss);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float den = fmaxf(sqrtf(ss), eps);  // torch F.normalize: x / max(||x||, eps)
+    for (int k = lane; k < d; k += 32) dst[static_cast<size_t>(row) * d + k] = __fdiv_rn(s[k], den);
+  }
+}
+
+constexpr int TM = 64, TN = 64, TK = 16;
+
+__device__ __forceinline__ unsigned int orderable(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// MODE 0: dense store.  MODE 1: thresholded join epilogue.
+template <int MODE>
+__global__ void __launch_bounds__(256)
+sim_tile_kernel(const float* __restrict__ a, long long m, const float* __restrict__ b, long long n, int d,
+                float* __restrict__ out, float tau, int self_join, unsigned long long* __restrict__ row_best,
+                int* __restrict__ row_count, long long* __restrict__ pair_i, long long* __restrict__ pair_j,
+                float* __restrict__ pair_sim, long long pair_cap, unsigned long long* __restrict__ pair_count) {
+  __shared__ float sa[TK][TM + 1];
+  __shared__ float sb[TK][TN + 1];
+  const long long i0 = static_cast<long long>(blockIdx.y) * TM;
+  const long long j0 = static_cast<long long>(blockIdx.x) * TN;
+  if (MODE == 1 && self_join && j0 + TN <= i0) return;  // strictly-lower tiles: covered by symmetry
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, k = e % TK;
+      sa[k][r] = (i0 + r < m && k0 + k < d) ? a[static_cast<size_t>(i0 + r) * d + k0 + k] : 0.f;
+      sb[k][r] = (j0 + r < n && k0 + k < d) ? b[static_cast<size_t>(j0 + r) * d + k0 + k] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) av[r] = sa[k][ty * 4 + r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) bv[c] = sb[k][tx * 4 + c];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long i = i0 + ty * 4 + r;
+    if (i >= m) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const long long j = j0 + tx * 4 + c;
+      if (j >= n) continue;
+      const float s = acc[r][c];
+      if (MODE == 0) {
+        out[static_cast<size_t>(i) * n + j] = s;
+      } else {
+        if (self_join && i == j) continue;
+        const unsigned long long key =
+            (static_cast<unsigned long long>(orderable(s)) << 32) | static_cast<unsigned int>(~static_cast<unsigned int>(j));
+        if (!self_join) {
+          atomicMax(&row_best[i], key);
+          if (s >= tau) {
+            atomicAdd(&row_count[i], 1);
+            const unsigned long long slot = atomicAdd(pair_count, 1ull);
+            if (static_cast<long long>(slot) < pair_cap) { pair_i[slot] = i; pair_j[slot] = j; pair_sim[slot] = s; }
+          }
+        } else {
+          // upper-triangle tiles update both rows; diagonal tiles hold (i, j) and (j, i) themselves
+          const bool diag_tile = (j0 < i0 + TM) && (i0 < j0 + TN);
+          atomicMax(&row_best[i], key);
+          if (s >= tau) atomicAdd(&row_count[i], 1);
+          if (!diag_tile) {
+            const unsigned long long key_t =
+                (static_cast<unsigned long long>(orderable(s)) << 32) | static_cast<unsigned int>(~static_cast<unsigned int>(i));
+            atomicMax(&row_best[j], key_t);
+            if (s >= tau) atomicAdd(&row_count[j], 1);
+          }
+          if (s >= tau && j > i) {
+            const unsigned long long slot = atomicAdd(pair_count, 1ull);
+            if (static_cast<long long>(slot) < pair_cap) { pair_i[slot] = i; pair_j[slot] = j; pair_sim[slot] = s; }
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void join_finish_kernel(const unsigned long long* __restrict__ row_best, long long m,
+                                   float* __restrict__ row_max, long long* __restrict__ row_argmax) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long key = row_best[i];
+  if (key == 0ull) {
+    row_max[i] = -INFINITY;
+    row_argmax[i] = -1;
+    return;
+  }
+  const unsigned int o = static_cast<unsigned int>(key >> 32);
+  row_max[i] = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+  row_argmax[i] = static_cast<long long>(~static_cast<unsigned int>(key & 0xffffffffull));
+}
+
+int normalize_into(const float* src, int64_t n, int d, float* dst, cudaStream_t stream) {
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n * 32, threads), 148 * 16);
+  normalize_rows_kernel<<<static_cast<int>(std::max<int64_t>(blocks, 1)), threads, 0, stream>>>(src, n, d, 1e-12f, dst);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+}  // namespace dewi
+
+using namespace dewi;
+
+extern "C" int dewi_similarity_dense(const float* a, int64_t m, const float* b, int64_t n, int d, float* out,
+                                     int device, void* stream_) {
+  if (!a || !b || !out) return fail("null argument");
+  if (m <= 0 || n <= 0 || d <= 0) return fail("similarity needs positive sizes");
+  DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
+  DEWI_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float *an = nullptr, *bn = nullptr;
+  DEWI_CUDA(cudaMalloc(&an, static_cast<size_t>(m) * d * 4));
+  if (cudaMalloc(&bn, static_cast<size_t>(n) * d * 4) != cudaSuccess) {
+    cudaFree(an);
+    return fail("cudaMalloc failed");
+  }
+  int rc = normalize_into(a, m, d, an, stream);
+  if (!rc) rc = normalize_into(b, n, d, bn, stream);
+  if (!rc) {
+    dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
+    sim_tile_kernel<0><<<grid, 256, 0, stream>>>(an, m, bn, n, d, out, 0.f, 0, nullptr, nullptr, nullptr, nullptr,
+                                                 nullptr, 0, nullptr);
+    if (cudaGetLastError() != cudaSuccess) rc = fail("similarity kernel launch failed");
+  }
+  cudaStreamSynchronize(stream);
+  cudaFree(an);
+  cudaFree(bn);
+  return rc;
+}
+
+extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
+                         float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
+                         float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
+  if (!a || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
+  if (self_join) { b = a; n = m; }
+  if (!b) return fail("null argument");
+  if (m <= 0 || n <= 0 || d <= 0) return fail("join needs positive sizes");
+  if (n >= (int64_t(1) << 32)) return fail("join supports fewer than 2^32 columns");
+  if (pair_cap > 0 && (!pair_i || !pair_j || !pair_sim)) return fail("pair buffers missing");
+  DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
+  DEWI_CUDA(cudaSetDevice(device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float *an = nullptr, *bn = nullptr;
+  unsigned long long *best = nullptr, *count = nullptr;
+  int rc = 0;
+  do {
+    if (cudaMalloc(&an, static_cast<size_t>(m) * d * 4) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
+    if (!self_join && cudaMalloc(&bn, static_cast<size_t>(n) * d * 4) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
+    if (cudaMalloc(&best, static_cast<size_t>(m) * 8) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
+    if (cudaMalloc(&count, 8) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
+    cudaMemsetAsync(best, 0, static_cast<size_t>(m) * 8, stream);
+    cudaMemsetAsync(count, 0, 8, stream);
+    cudaMemsetAsync(row_count, 0, static_cast<size_t>(m) * 4, stream);
+    if ((rc = normalize_into(a, m, d, an, stream))) break;
+    if (!self_join && (rc = normalize_into(b, n, d, bn, stream))) break;
+    dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
+    sim_tile_kernel<1><<<grid, 256, 0, stream>>>(an, m, self_join ? an : bn, n, d, nullptr, tau, self_join, best,
+                                                 row_count, reinterpret_cast<long long*>(pair_i),
+                                                 reinterpret_cast<long long*>(pair_j), pair_sim, pair_cap, count);
+    join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
+                                                                               reinterpret_cast<long long*>(row_argmax));
+    if (cudaGetLastError() != cudaSuccess) { rc = fail("join kernel launch failed"); break; }
+    unsigned long long cnt = 0;
+    if (cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+        cudaStreamSynchronize(stream) != cudaSuccess) {
+      rc = fail(std::string("join: ") + cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    *pair_count_host = static_cast<int64_t>(cnt);
+  } while (0);
+  cudaFree(an);
+  cudaFree(bn);
+  cudaFree(best);
+  cudaFree(count);
+  return rc;
+}

@@ -1,0 +1,94 @@
+// Operand preparation: row normalisation (ExactIndex.add, reference src/dewi/backends.py:403-405;
+// query normalisation, :420-424) fused with the split of fp32 values into bf16 planes that the
+// tensor-core sweep streams.  One warp per row, coalesced, fp32 arithmetic with IEEE division.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace dewi {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// hi = bf16(x); lo = bf16(x - hi): hi + lo carries 16 significand bits of x.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
+}
+
+__global__ void prep_rows_kernel(const float* __restrict__ src, long long n, long long n_out, int dim, int normalize,
+                                 int guard_zero, float* __restrict__ dst_f32, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int* __restrict__ bad_flag) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n_out; row += warps) {
+    const size_t off = static_cast<size_t>(row) * dim;
+    if (row >= n) {  // zero padding rows (query block padding)
+      for (int d = lane; d < dim; d += 32) {
+        if (dst_f32) dst_f32[off + d] = 0.f;
+        if (hi) hi[off + d] = __float2bfloat16_rn(0.f);
+        if (lo) lo[off + d] = __float2bfloat16_rn(0.f);
+      }
+      continue;
+    }
+    const float* s = src + off;
+    float scale_div = 1.f;
+    bool do_div = false;
+    if (normalize) {
+      float ss = 0.f;
+      for (int d = lane; d < dim; d += 32) {
+        const float x = s[d];
+        ss = fmaf(x, x, ss);
+      }
+      ss = warp_sum(ss);
+      const float nrm = sqrtf(ss);
+      if (nrm > 0.f) {
+        scale_div = nrm;
+        do_div = true;
+      } else if (guard_zero && lane == 0 && bad_flag) {
+        atomicExch(bad_flag, 1);  // zero-norm corpus row: the reference would store NaNs
+      }
+    }
+    for (int d = lane; d < dim; d += 32) {
+      float x = s[d];
+      if (do_div) x = __fdiv_rn(x, scale_div);
+      if (dst_f32) dst_f32[off + d] = x;
+      if (hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(x, h, l);
+        hi[off + d] = h;
+        if (lo) lo[off + d] = l;
+      }
+    }
+  }
+}
+
+int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, int guard_zero, float* dst_f32,
+           __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
+  if (n_out <= 0) return 0;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), 148 * 16);
+  prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero, dst_f32,
+                                                                    hi, lo, bad_flag);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
+  return launch(src, n, n, dim, normalize, 1, dst_f32, hi, lo, bad_flag, stream);
+}
+
+int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
+                        __nv_bfloat16* lo, cudaStream_t stream) {
+  // a zero query stays zero (backends.py:422-424: divide only when the norm is positive)
+  return launch(q, B, b_pad, dim, normalize, 0, qn, hi, lo, nullptr, stream);
+}
+
+}  // namespace dewi

@@ -1,0 +1,367 @@
+// K1 -- similarity sweep on the 5th-gen tensor cores with the candidate selection fused in.
+//
+// Replaces the hot statement of ExactIndex.search, `scores = np.dot(self._embeddings, query.T)`
+// (reference src/dewi/backends.py:431-433) and the first half of `np.argpartition(scores,
+// -candidate_count)` (:444): the [queries x corpus] score matrix is produced tile by tile in TMEM
+// and reduced to per-query candidate lists on chip; it never reaches HBM.
+//
+// Shape of the contraction (per CTA, per corpus tile):
+//     D[128 queries, N_TILE corpus rows] (fp32, TMEM) = sum_k  Q[128, k] (bf16, smem) . E[N_TILE, k]^T (bf16, smem)
+// Queries sit on the MMA M dimension so that TMEM lane == query: an epilogue thread owns one query
+// and scans its lane's columns against that query's running threshold -- no cross-thread traffic.
+//
+// Warp roles (192 threads, one CTA per SM, persistent over work items):
+//   warp 0      TMA producer   : E tile k-blocks (+ the matching Q k-blocks) into a smem ring
+//   warp 1      MMA issuer     : tcgen05.mma.kind::f16 into one of two TMEM accumulators; owns TMEM alloc
+//   warps 2..5  epilogue       : tcgen05.ld -> threshold test -> rare insertion into smem top-kc lists
+//
+// Precision modes (operand planes are bf16, products are exact, accumulation fp32):
+//   mode 0  Q0.E0                      bf16 corpus, single query plane (over-fetch + exact re-score follow)
+//   mode 1  Q0.E0 + Q1.E0              bf16 corpus, query split hi+lo
+//   mode 2  Q0.E0 + Q1.E0 + Q0.E1      fp32 corpus as hi+lo planes (drops only the lo.lo term, ~2^-18)
+#include <algorithm>
+#include <mutex>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace dewi {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+struct TcArgs {
+  int n_rows;
+  int n_tiles;
+  int n_kb;
+  int n_qb;
+  int n_chunks;
+  int n_items;
+  int kc;
+  int n_stages;
+  float* part_s;
+  int* part_i;
+};
+
+template <int MODE>
+struct ModeTraits {
+  static constexpr int PE = (MODE == 2) ? 2 : 1;  // corpus planes streamed
+  static constexpr int PQ = (MODE == 0) ? 1 : 2;  // query planes streamed
+};
+
+__device__ __forceinline__ void tile_range(int chunk, int n_chunks, int n_tiles, int& t0, int& t1) {
+  t0 = static_cast<int>((static_cast<long long>(chunk) * n_tiles) / n_chunks);
+  t1 = static_cast<int>((static_cast<long long>(chunk + 1) * n_tiles) / n_chunks);
+}
+
+template <int MODE, int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1)
+search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
+                 const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
+                 const TcArgs a) {
+  using T = ModeTraits<MODE>;
+  constexpr uint32_t kEPlaneBytes = N_TILE * 128;
+  constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
+  constexpr uint32_t kStageBytes = T::PE * kEPlaneBytes + T::PQ * kQPlaneBytes;
+  constexpr uint32_t kTmemCols = 2 * N_TILE;
+  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kQueryBlock, N_TILE);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B operand tiles.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  float* list_s = reinterpret_cast<float*>(ring + static_cast<size_t>(a.n_stages) * kStageBytes);
+  int* list_i = reinterpret_cast<int*>(list_s + a.kc * kQueryBlock);
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(list_i + a.kc * kQueryBlock);
+  uint64_t* bar_empty = bar_full + kMaxStages;
+  uint64_t* bar_acc_full = bar_empty + kMaxStages;
+  uint64_t* bar_acc_empty = bar_acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&map_e0);
+    ptx::prefetch_tmap(&map_q0);
+    if (T::PE > 1) ptx::prefetch_tmap(&map_e1);
+    if (T::PQ > 1) ptx::prefetch_tmap(&map_q1);
+    for (int s = 0; s < a.n_stages; ++s) {
+      ptx::mbar_init(&bar_full[s], 1);
+      ptx::mbar_init(&bar_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar_acc_full[b], 1);
+      ptx::mbar_init(&bar_acc_empty[b], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        const int qb = item % a.n_qb;
+        int t0, t1;
+        tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_empty[stage], phase ^ 1);
+            uint8_t* st = ring + static_cast<size_t>(stage) * kStageBytes;
+            ptx::mbar_arrive_expect_tx(&bar_full[stage], kStageBytes);
+            ptx::tma_load_2d(st, &map_e0, &bar_full[stage], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
+            if (T::PE > 1)
+              ptx::tma_load_2d(st + kEPlaneBytes, &map_e1, &bar_full[stage], kb * kKBlock, t * N_TILE,
+                               ptx::kEvictFirst);
+            uint8_t* sq = st + T::PE * kEPlaneBytes;
+            ptx::tma_load_2d(sq, &map_q0, &bar_full[stage], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+            if (T::PQ > 1)
+              ptx::tma_load_2d(sq + kQPlaneBytes, &map_q1, &bar_full[stage], kb * kKBlock, qb * kQueryBlock,
+                               ptx::kEvictLast);
+            if (++stage == a.n_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int t0, t1;
+        tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * N_TILE);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_full[stage], phase);  // TMA bytes have landed
+            ptx::tc_fence_after();
+            const uint32_t st = ptx::smem_u32(ring + static_cast<size_t>(stage) * kStageBytes);
+            const uint64_t de0 = ptx::make_desc_sw128(st);
+            const uint64_t de1 = ptx::make_desc_sw128(st + kEPlaneBytes);
+            const uint64_t dq0 = ptx::make_desc_sw128(st + T::PE * kEPlaneBytes);
+            const uint64_t dq1 = ptx::make_desc_sw128(st + T::PE * kEPlaneBytes + kQPlaneBytes);
+#pragma unroll
+            for (int k = 0; k < kKBlock / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
+              ptx::mma_bf16_ss(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              if (MODE >= 1) ptx::mma_bf16_ss(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
+              if (MODE == 2) ptx::mma_bf16_ss(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+            }
+            ptx::mma_commit(&bar_empty[stage]);  // smem slot reusable once these MMAs retire
+            if (kb == a.n_kb - 1) ptx::mma_commit(&bar_acc_full[acc]);
+            if (++stage == a.n_stages) { stage = 0; phase ^= 1; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> per-query candidate lists =====================
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may read
+    const int qlane = quarter * 32 + lane;    // query within the 128-query block == TMEM lane
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int kc = a.kc;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      int t0, t1;
+      tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
+      for (int k = 0; k < kc; ++k) {
+        list_s[k * kQueryBlock + qlane] = -INFINITY;
+        list_i[k * kQueryBlock + qlane] = -1;
+      }
+      float thr = -INFINITY;  // smallest score in the list == admission threshold
+      int minpos = 0;
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * N_TILE);
+        const int row_base = t * N_TILE;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / 32; ++c) {
+          float v[32];
+          ptx::tmem_ld_32x32(tcol + c * 32, v);
+          const int r0 = row_base + c * 32;
+          if (r0 + 32 > a.n_rows) {  // ragged corpus tail: TMA zero-filled those rows
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (r0 + j >= a.n_rows) v[j] = -INFINITY;
+          }
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          if (mx > thr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (v[j] > thr) {
+                list_s[minpos * kQueryBlock + qlane] = v[j];
+                list_i[minpos * kQueryBlock + qlane] = r0 + j;
+                float m = list_s[qlane];
+                int p = 0;
+                for (int k = 1; k < kc; ++k) {
+                  const float x = list_s[k * kQueryBlock + qlane];
+                  if (x < m) { m = x; p = k; }
+                }
+                thr = m;
+                minpos = p;
+              }
+            }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      // flush this item's lists: [item][k][query]
+      float* ps = a.part_s + static_cast<size_t>(item) * kc * kQueryBlock;
+      int* pi = a.part_i + static_cast<size_t>(item) * kc * kQueryBlock;
+      for (int k = 0; k < kc; ++k) {
+        ps[k * kQueryBlock + qlane] = list_s[k * kQueryBlock + qlane];
+        pi[k * kQueryBlock + qlane] = list_i[k * kQueryBlock + qlane];
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+size_t stage_bytes(int mode, int n_tile) {
+  const int pe = (mode == 2) ? 2 : 1, pq = (mode == 0) ? 1 : 2;
+  return static_cast<size_t>(pe) * n_tile * 128 + static_cast<size_t>(pq) * kQueryBlock * 128;
+}
+size_t fixed_bytes(int kc) {
+  return static_cast<size_t>(kc) * kQueryBlock * 8 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+}
+
+template <int MODE, int N_TILE>
+int launch_one(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+               const CUtensorMap& q1, const TcArgs& args, cudaStream_t stream) {
+  auto kern = search_tc_kernel<MODE, N_TILE>;
+  DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
+  kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int tc_supported(int dim, int64_t n_rows) {
+  return dim % kKBlock == 0 && dim >= kKBlock && dim <= 8192 && n_rows >= 1 && n_rows < (int64_t(1) << 31);
+}
+
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan) {
+  if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
+  const size_t smem_max = 227 * 1024;
+  int n_tile = (mode == 2) ? 128 : 256;
+  size_t fixed = fixed_bytes(kc);
+  int stages = 0;
+  for (;;) {
+    if (fixed < smem_max) stages = static_cast<int>((smem_max - fixed) / stage_bytes(mode, n_tile));
+    if (stages >= 2 || n_tile == 128) break;
+    n_tile = 128;
+  }
+  if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
+  stages = std::min(stages, kMaxStages);
+  const int64_t n_tiles = ceil_div(n_rows, n_tile);
+  // Work items = chunks x query blocks, dealt round-robin to `grid` persistent CTAs.  Choose the
+  // number of chunks so the item count is a multiple of the grid (equal work per CTA).
+  int grid = static_cast<int>(std::min<int64_t>(sm_count, n_tiles * n_qb));
+  int64_t want = ceil_div(static_cast<int64_t>(grid), n_qb);  // >= one item per CTA
+  // make chunks * n_qb a multiple of grid when the corpus is long enough
+  int64_t chunks = want;
+  for (int64_t c = want; c <= want + grid && c <= n_tiles; ++c) {
+    if ((c * n_qb) % grid == 0) { chunks = c; break; }
+  }
+  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
+  plan->mode = mode;
+  plan->n_tile = n_tile;
+  plan->n_stages = stages;
+  plan->n_chunks = static_cast<int>(chunks);
+  plan->grid = static_cast<int>(std::min<int64_t>(grid, chunks * n_qb));
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * stage_bytes(mode, n_tile);
+  return 0;
+}
+
+int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail("cuTensorMapEncodeTiled is unavailable (no CUDA driver?)");
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(dim), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dim) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKBlock), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+  return 0;
+}
+
+int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+              const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
+              cudaStream_t stream) {
+  TcArgs a;
+  a.n_rows = static_cast<int>(n_rows);
+  a.n_tiles = static_cast<int>(ceil_div(n_rows, plan.n_tile));
+  a.n_kb = dim / kKBlock;
+  a.n_qb = n_qb;
+  a.n_chunks = plan.n_chunks;
+  a.n_items = plan.n_chunks * n_qb;
+  a.kc = kc;
+  a.n_stages = plan.n_stages;
+  a.part_s = part_s;
+  a.part_i = part_i;
+  if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 0 && plan.n_tile == 128) return launch_one<0, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1 && plan.n_tile == 128) return launch_one<1, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 2 && plan.n_tile == 128) return launch_one<2, 128>(plan, e0, e1, q0, q1, a, stream);
+  return fail("unsupported tcgen05 sweep configuration");
+}
+
+}  // namespace dewi

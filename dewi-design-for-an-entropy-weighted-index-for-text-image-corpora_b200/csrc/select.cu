@@ -1,0 +1,289 @@
+// K2 -- candidate merge, exact re-score, DEWI blend and final selection.
+//
+// Everything after the sweep in ExactIndex.search (reference src/dewi/backends.py:439-481):
+//   merge_select   : per-CTA partial lists -> the query's best `kc` rows by (approximate) similarity
+//   rescore        : exact fp32 similarity of those rows against the fp32 query (tensor path only)
+//   finalize_local : sort, keep the shard's top min(2k, n) (:439-447), attach global id + payload columns
+//   rerank         : top-2k of the gathered shards' candidates, `adj = (1-eta)*sim + eta*dewi
+//                    (+ entropy_pref*entropy)` in fp32 with numpy's rounding (:461-465), top-k, sort (:468-471)
+// One thread block per query; candidate counts are tiny next to the sweep, so these are latency-, not
+// bandwidth-bound kernels.
+#include <algorithm>
+
+#include "internal.h"
+
+namespace dewi {
+namespace {
+
+constexpr int kSelThreads = 128;
+
+__device__ __forceinline__ uint32_t orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// Descending sort key: score first, then lower id first.
+__device__ __forceinline__ unsigned long long make_key(float score, uint32_t id_lo) {
+  return (static_cast<unsigned long long>(orderable(score)) << 32) | static_cast<unsigned long long>(~id_lo);
+}
+
+// In-place descending bitonic sort of p (power of two) (key, val) pairs in shared memory.
+__device__ void bitonic_sort_desc(unsigned long long* key, int* val, int p) {
+  for (int size = 2; size <= p; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (p >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = key[lo], b = key[hi];
+        if ((a < b) == desc) {
+          key[lo] = b; key[hi] = a;
+          const int va = val[lo]; val[lo] = val[hi]; val[hi] = va;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__host__ __device__ inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ---- merge_select -------------------------------------------------------------------------------
+// Streams the query's n_chunks*kc partial candidates through a shared-memory window, keeping the
+// running best kc_out (sorted).  Window = best list + a batch of new candidates, bitonic-sorted.
+constexpr int kWindow = 2048;
+
+__global__ void __launch_bounds__(kSelThreads)
+merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ part_i, int n_chunks, int n_qb, int kc,
+                    int kc_out, int* __restrict__ cand_idx, float* __restrict__ cand_sim) {
+  __shared__ unsigned long long key[kWindow];
+  __shared__ int val[kWindow];
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = b % kQueryBlock;
+  const int total = n_chunks * kc;
+  const int batch = kWindow - kc_out;
+  for (int t = threadIdx.x; t < kc_out; t += blockDim.x) { key[t] = 0ull; val[t] = -1; }
+  for (int base = 0; base < total; base += batch) {
+    const int m = min(batch, total - base);
+    const int p = next_pow2(kc_out + m);
+    for (int t = threadIdx.x; t < p - kc_out; t += blockDim.x) {
+      unsigned long long kk = 0ull;
+      int vv = -1;
+      if (t < m) {
+        const int e = base + t;
+        const int chunk = e / kc, k = e - chunk * kc;
+        const size_t off = ((static_cast<size_t>(chunk) * n_qb + qb) * kc + k) * kQueryBlock + ql;
+        const int idx = part_i[off];
+        if (idx >= 0) { kk = make_key(part_s[off], static_cast<uint32_t>(idx)); vv = idx; }
+      }
+      key[kc_out + t] = kk;
+      val[kc_out + t] = vv;
+    }
+    bitonic_sort_desc(key, val, p);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kc_out; t += blockDim.x) {
+    const int idx = val[t];
+    cand_idx[static_cast<size_t>(b) * kc_out + t] = idx;
+    float s = -INFINITY;
+    if (idx >= 0) {
+      const uint32_t o = static_cast<uint32_t>(key[t] >> 32);
+      s = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+    }
+    cand_sim[static_cast<size_t>(b) * kc_out + t] = s;
+  }
+}
+
+// ---- rescore ------------------------------------------------------------------------------------
+template <typename RowT>
+__global__ void rescore_kernel(const RowT* __restrict__ rows, int dim, const float* __restrict__ qn,
+                               const int* __restrict__ cand_idx, int total, int kc, float* __restrict__ cand_sim) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const int idx = cand_idx[w];
+  if (idx < 0) {
+    if (lane == 0) cand_sim[w] = -INFINITY;
+    return;
+  }
+  const int b = w / kc;
+  const RowT* r = rows + static_cast<size_t>(idx) * dim;
+  const float* q = qn + static_cast<size_t>(b) * dim;
+  float acc = 0.f;
+  for (int d = lane * 8; d < dim; d += 256) {
+    float x[8];
+    if (sizeof(RowT) == 2) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + d));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[2 * i] = __uint_as_float(u[i] << 16);
+        x[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+      }
+    } else {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(r + d));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(r + d) + 1);
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+      x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+    }
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(q + d));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(q + d) + 1);
+    acc = fmaf(x[0], q0.x, acc); acc = fmaf(x[1], q0.y, acc); acc = fmaf(x[2], q0.z, acc); acc = fmaf(x[3], q0.w, acc);
+    acc = fmaf(x[4], q1.x, acc); acc = fmaf(x[5], q1.y, acc); acc = fmaf(x[6], q1.z, acc); acc = fmaf(x[7], q1.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) cand_sim[w] = acc;
+}
+
+// ---- finalize_local -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads)
+finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict__ cand_sim, int kc_in, int kcand,
+                      long long id_base, const float* __restrict__ dewi, const float* __restrict__ ent,
+                      float* __restrict__ out_sim, long long* __restrict__ out_id, float* __restrict__ out_dewi,
+                      float* __restrict__ out_ent) {
+  extern __shared__ unsigned long long sh[];
+  const int p = next_pow2(kc_in);
+  unsigned long long* key = sh;
+  int* val = reinterpret_cast<int*>(sh + p);
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < p; t += blockDim.x) {
+    unsigned long long kk = 0ull;
+    int vv = -1;
+    if (t < kc_in) {
+      const int idx = cand_idx[static_cast<size_t>(b) * kc_in + t];
+      if (idx >= 0) { kk = make_key(cand_sim[static_cast<size_t>(b) * kc_in + t], static_cast<uint32_t>(idx)); vv = t; }
+    }
+    key[t] = kk;
+    val[t] = vv;
+  }
+  bitonic_sort_desc(key, val, p);
+  for (int t = threadIdx.x; t < kcand; t += blockDim.x) {
+    const size_t o = static_cast<size_t>(b) * kcand + t;
+    const int slot = (t < p) ? val[t] : -1;
+    if (slot >= 0) {
+      const int idx = cand_idx[static_cast<size_t>(b) * kc_in + slot];
+      out_sim[o] = cand_sim[static_cast<size_t>(b) * kc_in + slot];
+      out_id[o] = id_base + idx;
+      out_dewi[o] = dewi[idx];
+      out_ent[o] = ent[idx];
+    } else {
+      out_sim[o] = -INFINITY;
+      out_id[o] = -1;
+      out_dewi[o] = 0.f;
+      out_ent[o] = 0.f;
+    }
+  }
+}
+
+// ---- rerank -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSelThreads)
+rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, const float* __restrict__ dewi,
+              const float* __restrict__ ent, int ncand, int cand_count, int k, float w_sim, float w_dewi, float pref,
+              int use_pref, long long* __restrict__ out_id, float* __restrict__ out_score) {
+  extern __shared__ unsigned long long sh[];
+  const int p = next_pow2(ncand);
+  unsigned long long* key = sh;
+  int* val = reinterpret_cast<int*>(sh + p);
+  float* adj = reinterpret_cast<float*>(val + p);
+  const int b = blockIdx.x;
+  const size_t base = static_cast<size_t>(b) * ncand;
+  // 1. candidate set: the cand_count best by similarity (backends.py:439-447)
+  for (int t = threadIdx.x; t < p; t += blockDim.x) {
+    unsigned long long kk = 0ull;
+    int vv = -1;
+    if (t < ncand) {
+      const long long g = id[base + t];
+      if (g >= 0) { kk = make_key(sim[base + t], static_cast<uint32_t>(g)); vv = t; }
+    }
+    key[t] = kk;
+    val[t] = vv;
+  }
+  bitonic_sort_desc(key, val, p);
+  // 2. blend in fp32, one rounding per operation as numpy does (backends.py:461-465)
+  for (int t = threadIdx.x; t < p; t += blockDim.x) {
+    const int slot = (t < cand_count) ? val[t] : -1;
+    unsigned long long kk = 0ull;
+    float a = 0.f;
+    if (slot >= 0) {
+      a = __fadd_rn(__fmul_rn(w_sim, sim[base + slot]), __fmul_rn(w_dewi, dewi[base + slot]));
+      if (use_pref) a = __fadd_rn(a, __fmul_rn(pref, ent[base + slot]));
+      kk = make_key(a, static_cast<uint32_t>(id[base + slot]));
+    }
+    // entry t is read and rewritten by the same thread only: no cross-thread hazard
+    key[t] = kk;
+    val[t] = slot;
+    if (slot >= 0) adj[slot] = a;
+  }
+  // 3. top-k by adjusted score, descending (backends.py:468-471)
+  bitonic_sort_desc(key, val, p);
+  for (int t = threadIdx.x; t < k; t += blockDim.x) {
+    const int slot = (t < p) ? val[t] : -1;
+    const size_t o = static_cast<size_t>(b) * k + t;
+    if (slot >= 0) {
+      out_id[o] = id[base + slot];
+      out_score[o] = adj[slot];
+    } else {
+      out_id[o] = -1;
+      out_score[o] = -INFINITY;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream) {
+  if (kc_out > kWindow / 2) return fail("candidate count too large for merge window");
+  merge_select_kernel<<<B, kSelThreads, 0, stream>>>(p.s, p.i, p.n_chunks, p.n_qb, p.kc, kc_out, cand_idx, cand_sim);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
+                   float* cand_sim, cudaStream_t stream) {
+  if (dim % 8 != 0) return fail("rescore needs dim % 8 == 0");
+  const int total = B * kc;
+  const int threads = 256;
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(total) * 32, threads));
+  if (rows_are_bf16)
+    rescore_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(rows), dim, qn,
+                                                                   cand_idx, total, kc, cand_sim);
+  else
+    rescore_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(rows), dim, qn, cand_idx, total, kc,
+                                                           cand_sim);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
+                          const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
+                          float* out_ent, cudaStream_t stream) {
+  const int p = next_pow2(kc_in);
+  if (p > 4096) return fail("too many candidates per query");
+  const size_t smem = static_cast<size_t>(p) * 12;
+  finalize_local_kernel<<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, out_sim,
+                                                          reinterpret_cast<long long*>(out_id), out_dewi, out_ent);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
+                  int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
+                  float* out_score, cudaStream_t stream) {
+  const int p = next_pow2(ncand);
+  if (p > 8192) return fail("too many gathered candidates per query");
+  const size_t smem = static_cast<size_t>(p) * 16;
+  auto kern = rerank_kernel;
+  if (smem > 48 * 1024)
+    DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<B, kSelThreads, smem, stream>>>(sim, reinterpret_cast<const long long*>(id), dewi, ent, ncand, cand_count, k,
+                                         w_sim, w_dewi, pref, use_pref, reinterpret_cast<long long*>(out_id), out_score);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dewi

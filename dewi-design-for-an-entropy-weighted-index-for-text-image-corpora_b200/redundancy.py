@@ -1,0 +1,80 @@
+"""Redundancy similarity pass on a B200.
+
+`cross_modal_similarity(tfeat, ifeat)` is the arithmetic of
+`RedundancyEstimator.compute_cross_modal_similarity` after the CLIP forward
+(src/dewi/signals/redundancy.py:36-38): L2-normalise both feature matrices, `T @ I.T`, float32.
+`redundancy_join` is the thresholded form that never materialises `[M, N]` (this repository's
+definition -- the reference has none).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import _native
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def _as_cuda(x, dev):
+    torch = _torch()
+    return torch.as_tensor(x, dtype=torch.float32).to(torch.device("cuda", dev)).contiguous()
+
+
+def cross_modal_similarity(tfeat, ifeat, device: Optional[int] = None):
+    """`normalize(tfeat) @ normalize(ifeat).T` -> numpy `[T, I]` float32 (redundancy.py:36-38)."""
+    torch = _torch()
+    dev = int(device) if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    _native.require_device(dev)
+    a, b = _as_cuda(tfeat, dev), _as_cuda(ifeat, dev)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("feature matrices must be [T, D] and [I, D]")
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    lib = _native.load_library()
+    with torch.cuda.device(dev):
+        rc = lib.dewi_similarity_dense(ctypes.c_void_p(a.data_ptr()), a.shape[0], ctypes.c_void_p(b.data_ptr()),
+                                       b.shape[0], a.shape[1], ctypes.c_void_p(out.data_ptr()), dev, _native.stream_ptr())
+    _native.check(rc)
+    return out.cpu().numpy()  # the reference returns `.cpu().numpy()` (redundancy.py:38)
+
+
+def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device: Optional[int] = None):
+    """Thresholded similarity join.  `b=None` is the self-join (diagonal excluded, pairs j > i).
+
+    Returns dict(max_sim [M] f32, argmax [M] i64, count [M] i32, pairs_i, pairs_j, pairs_sim, n_pairs)
+    of CUDA tensors; `n_pairs` may exceed `pair_cap`, in which case only `pair_cap` pairs were kept."""
+    torch = _torch()
+    dev = int(device) if device is not None else (torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    _native.require_device(dev)
+    self_join = b is None
+    ta = _as_cuda(a, dev)
+    tb = ta if self_join else _as_cuda(b, dev)
+    if ta.ndim != 2 or tb.ndim != 2 or ta.shape[1] != tb.shape[1]:
+        raise ValueError("feature matrices must be [M, D] and [N, D]")
+    m = ta.shape[0]
+    tdev = ta.device
+    row_max = torch.empty(m, dtype=torch.float32, device=tdev)
+    row_arg = torch.empty(m, dtype=torch.int64, device=tdev)
+    row_cnt = torch.empty(m, dtype=torch.int32, device=tdev)
+    pi = torch.empty(pair_cap, dtype=torch.int64, device=tdev)
+    pj = torch.empty(pair_cap, dtype=torch.int64, device=tdev)
+    ps = torch.empty(pair_cap, dtype=torch.float32, device=tdev)
+    cnt = ctypes.c_int64(0)
+    lib = _native.load_library()
+    with torch.cuda.device(dev):
+        rc = lib.dewi_join(ctypes.c_void_p(ta.data_ptr()), m, ctypes.c_void_p(tb.data_ptr()), tb.shape[0], ta.shape[1],
+                           float(tau), int(self_join), ctypes.c_void_p(row_max.data_ptr()),
+                           ctypes.c_void_p(row_arg.data_ptr()), ctypes.c_void_p(row_cnt.data_ptr()),
+                           ctypes.c_void_p(pi.data_ptr()), ctypes.c_void_p(pj.data_ptr()), ctypes.c_void_p(ps.data_ptr()),
+                           int(pair_cap), ctypes.byref(cnt), dev, _native.stream_ptr())
+    _native.check(rc)
+    kept = min(int(cnt.value), pair_cap)
+    return {"max_sim": row_max, "argmax": row_arg, "count": row_cnt, "pairs_i": pi[:kept], "pairs_j": pj[:kept],
+            "pairs_sim": ps[:kept], "n_pairs": int(cnt.value)}

@@ -1,0 +1,134 @@
+/*
+ * dewi_b200.h -- C ABI of the B200-native DEWI retrieval hot path (libdewi_b200.so).
+ *
+ * The reference (lexsightllc/DEWI) is pure Python: it has no FFI boundary of its own.  Its plugin
+ * boundary is the Python class `BaseIndex` (src/dewi/backends.py:54-163) selected by `DewiIndex`
+ * (src/dewi/index.py:44-60).  This header is the native layer a `BaseIndex` subclass binds through
+ * ctypes; every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; `dewi_last_error()` then returns a
+ *     thread-local message.  No C++ exception crosses this boundary.
+ *   - plain pointers and sizes only.  Unless a parameter says "host", pointers are DEVICE pointers
+ *     on the handle's device; the caller owns them.  The library owns only the handle, its corpus
+ *     planes and its workspace.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls on one
+ *     handle must be issued from one thread at a time.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every compute entry point
+ *     fails with an error.
+ */
+#ifndef DEWI_B200_H
+#define DEWI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEWI_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DEWI_API __attribute__((visibility("default")))
+#else
+#define DEWI_API
+#endif
+
+typedef struct dewi_index dewi_index_t;
+
+/* space: how ExactIndex scores (backends.py:392,431-436) */
+enum { DEWI_SPACE_COSINE = 0, DEWI_SPACE_L2 = 1 };
+/* corpus storage */
+enum {
+  DEWI_DTYPE_FP32 = 0, /* rows kept in fp32 + a bf16 hi/lo plane pair for the tensor-core sweep  */
+  DEWI_DTYPE_BF16 = 1  /* rows rounded to bf16 after normalisation (2 B / element)               */
+};
+/* search flags */
+enum {
+  DEWI_FLAG_QUERY_NORMALIZED = 1 << 0, /* queries were already normalised as backends.py:420-424  */
+  DEWI_FLAG_FORCE_SIMT = 1 << 1,       /* use the CUDA-core exact sweep even when tcgen05 applies  */
+  DEWI_FLAG_FORCE_TC = 1 << 2,         /* fail instead of falling back to the CUDA-core sweep      */
+  DEWI_FLAG_HOST_IO = 1 << 3,          /* queries / outputs are HOST pointers (copies inside call) */
+  DEWI_FLAG_PRECISE_QUERY = 1 << 4,    /* bf16 corpus: hi+lo query planes (2 MMAs) not 1 + rescore */
+  DEWI_FLAG_SCOPE_FULL = 1 << 5        /* (non-reference) blend over the whole corpus; unsupported */
+};
+
+/* ---- library ------------------------------------------------------------------------------ */
+DEWI_API int dewi_abi_version(void);
+DEWI_API const char* dewi_last_error(void);
+/* Fails unless `device` is compute capability 10.x (B200); reports SM count and memory. */
+DEWI_API int dewi_device_check(int device, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+
+/* ---- index lifetime: replaces ExactIndex.__init__ / add / build (backends.py:389-412) ------ */
+DEWI_API int dewi_index_create(int dim, int space, int dtype, int device, dewi_index_t** out);
+DEWI_API int dewi_index_destroy(dewi_index_t* h);
+/* Pre-size the corpus planes for `rows` rows (avoids regrowth while appending). */
+DEWI_API int dewi_index_reserve(dewi_index_t* h, int64_t rows);
+/* Global id of this shard's row 0 (row-sharded corpus). */
+DEWI_API int dewi_index_set_id_base(dewi_index_t* h, int64_t id_base);
+/* Append `n` fp32 rows [n, dim] (device pointer, or host pointer when src_is_host).  When
+ * `normalized` is 0 and space is cosine each row is divided by its L2 norm in fp32 as
+ * backends.py:403-405 does; a zero-norm row is an error (the reference stores a NaN row).  */
+DEWI_API int dewi_index_append(dewi_index_t* h, const float* rows, int64_t n, int normalized, int src_is_host, void* stream);
+/* Per-row payload columns read by the re-rank: dewi[i] = payload.dewi and ent[i] =
+ * float32((ht_mean + hi_mean) * 0.5) (backends.py:457-458).  Writes rows [offset, offset+n). */
+DEWI_API int dewi_index_set_payload(dewi_index_t* h, const float* dewi, const float* ent, int64_t offset, int64_t n,
+                           int src_is_host, void* stream);
+DEWI_API int dewi_index_size(const dewi_index_t* h, int64_t* rows);
+/* Copy the stored (normalised) row back as fp32 -- DewiIndex.get_embedding (index.py:101-116). */
+DEWI_API int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host);
+
+/* ---- search: replaces ExactIndex.search (backends.py:414-481) ------------------------------ */
+/* Stage 1+2 on one shard: similarity sweep (backends.py:431-436) and candidate selection
+ * (backends.py:439-447).  For each of the B queries emits the shard's `kcand` best rows by exact
+ * similarity, sorted descending: similarity, GLOBAL id (id_base + row, -1 = empty slot) and the
+ * two payload columns of that row.  All outputs are [B, kcand] device arrays.               */
+DEWI_API int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
+                            int64_t* out_id, float* out_dewi, float* out_ent, void* stream);
+/* Stage 3: DEWI blend and final select (backends.py:461-481) over `ncand` gathered candidates per
+ * query (the concatenation of every shard's stage-1 output).  Keeps the `cand_count`
+ * (= min(2k, N_total), backends.py:440) best by similarity, computes in fp32
+ *     adj = w_sim * sim + w_dewi * dewi  [+ pref * ent   when use_pref]
+ * with w_sim = float32(1 - eta), w_dewi = float32(eta) rounded exactly as numpy does, and writes
+ * the k best by adj, sorted descending.  Does not need an index handle.                        */
+DEWI_API int dewi_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
+                int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
+                float* out_score, int device, void* stream);
+/* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
+ * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
+DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,
+                      int flags, int64_t* out_id, float* out_score, void* stream);
+/* Kernel launches issued by the last search on this handle (bench.py's `gpu_launches`). */
+DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
+
+/* ---- scorer: replaces RobustStats.fit and DewiScorer.score (scorer.py:18-31,49-89) ---------- */
+/* Median and MAD of `f` fp32 columns of `n` values each (column c starts at cols + c*ld).
+ * Exact order statistics: even n averages the two middle values in fp32 like np.median; MAD is
+ * the fp32 median of |v - med|; a zero MAD is returned as 1e-8 (scorer.py:22-25).
+ * med_host / mad_host: host arrays of `f` doubles; the call synchronises the stream.           */
+DEWI_API int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, double* med_host, double* mad_host, int device,
+                   void* stream);
+/* Seven signal columns in the order ht_mean, ht_q90, hi_mean, hi_q90, I_hat, redundancy, noise
+ * (column c at cols + c*ld).  med7/mad7 (host) as fitted; w6 (host) = alpha_t, alpha_i, alpha_m,
+ * alpha_r, alpha_n, delta.  float64 arithmetic of scorer.py:28-31,49-89; `out` is n floats, or n
+ * doubles when out_f64.                                                                        */
+DEWI_API int dewi_score(const float* cols, int64_t n, int64_t ld, const double* med7, const double* mad7, const double* w6,
+               int conditional, void* out, int out_f64, int device, void* stream);
+
+/* ---- redundancy: replaces RedundancyEstimator's normalise + matmul (redundancy.py:36-38) ---- */
+/* out[m, n] = normalize(a)[m, d] @ normalize(b)[n, d]^T, fp32, eps 1e-12 as torch F.normalize. */
+DEWI_API int dewi_similarity_dense(const float* a, int64_t m, const float* b, int64_t n, int d, float* out, int device,
+                          void* stream);
+/* Thresholded join (this repository's definition): per row of `a` the
+ * best similarity against rows of `b`, its index, and the number of rows with sim >= tau; plus up
+ * to `pair_cap` (i, j, sim) pairs with sim >= tau appended to pair_i/pair_j/pair_sim, the total
+ * number found in *pair_count_host.  self_join: b == a, diagonal excluded, pairs only j > i.   */
+DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, float* row_max,
+              int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+              int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEWI_B200_H */
