@@ -166,9 +166,9 @@ struct ScoreParams {
   int conditional;
 };
 
-template <typename OutT>
+template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-score_kernel(const float* __restrict__ cols, long long n, long long ld, const ScoreParams p, OutT* __restrict__ out) {
+score_kernel(const InT* __restrict__ cols, long long n, long long ld, const ScoreParams p, OutT* __restrict__ out) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     double z[7];
@@ -266,7 +266,7 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   return rc;
 }
 
-extern "C" int dewi_score(const float* cols, int64_t n, int64_t ld, const double* med7, const double* mad7,
+extern "C" int dewi_score(const void* cols, int in_f64, int64_t n, int64_t ld, const double* med7, const double* mad7,
                           const double* w6, int conditional, void* out, int out_f64, int device, void* stream_) {
   if (!cols || !med7 || !mad7 || !w6 || !out) return fail("null argument");
   if (n <= 0) return fail("score needs at least one row");
@@ -283,10 +283,16 @@ extern "C" int dewi_score(const float* cols, int64_t n, int64_t ld, const double
   p.conditional = conditional ? 1 : 0;
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n, threads), 148 * 16));
-  if (out_f64)
-    score_kernel<double><<<blocks, threads, 0, stream>>>(cols, n, ld, p, static_cast<double*>(out));
+  const float* c32 = static_cast<const float*>(cols);
+  const double* c64 = static_cast<const double*>(cols);
+  if (in_f64 && out_f64)
+    score_kernel<double, double><<<blocks, threads, 0, stream>>>(c64, n, ld, p, static_cast<double*>(out));
+  else if (in_f64)
+    score_kernel<double, float><<<blocks, threads, 0, stream>>>(c64, n, ld, p, static_cast<float*>(out));
+  else if (out_f64)
+    score_kernel<float, double><<<blocks, threads, 0, stream>>>(c32, n, ld, p, static_cast<double*>(out));
   else
-    score_kernel<float><<<blocks, threads, 0, stream>>>(cols, n, ld, p, static_cast<float*>(out));
+    score_kernel<float, float><<<blocks, threads, 0, stream>>>(c32, n, ld, p, static_cast<float*>(out));
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

@@ -77,13 +77,14 @@ class DewiIndex(BaseIndex):
             raise ValueError(f"Expected query shape ({self.dim},), got {q.shape}")
         return self._backend.search(q, k, eta, entropy_pref)
 
-    def search_batch(self, queries, k: int = 10, eta: Optional[float] = None, entropy_pref: Optional[float] = None):
+    def search_batch(self, queries, k: int = 10, eta: Optional[float] = None, entropy_pref: Optional[float] = None,
+                     flags: int = 0):
         """`[B, dim]` queries -> `(row_ids [B, k], scores [B, k])` (extension, see CudaIndex.search_batch)."""
         if not self._built:
             self.build()
         eta = self.rerank_eta if eta is None else eta
         entropy_pref = self.entropy_pref if entropy_pref is None else entropy_pref
-        return self._backend.search_batch(queries, k, eta, entropy_pref)
+        return self._backend.search_batch(queries, k, eta, entropy_pref, flags)
 
     def refresh_payloads(self) -> None:
         self._backend.refresh_payloads()

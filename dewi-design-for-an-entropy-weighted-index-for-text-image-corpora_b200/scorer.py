@@ -111,9 +111,13 @@ class DewiScorer:
         _native.require_device(dev)
         tdev = torch.device("cuda", dev)
         if isinstance(columns, Mapping):
-            cols = torch.stack([torch.as_tensor(columns[k], dtype=torch.float32).to(tdev) for k in SIGNAL_FIELDS])
+            parts = [torch.as_tensor(columns[k]) for k in SIGNAL_FIELDS]
+            in_f64 = all(p.dtype == torch.float64 for p in parts)
+            cols = torch.stack([p.to(tdev, torch.float64 if in_f64 else torch.float32) for p in parts])
         else:
-            cols = torch.as_tensor(columns, dtype=torch.float32).to(tdev)
+            cols = torch.as_tensor(columns)
+            in_f64 = cols.dtype == torch.float64  # float64 rows are scored un-rounded, as the reference does
+            cols = cols.to(tdev, torch.float64 if in_f64 else torch.float32)
         cols = cols.contiguous()
         if cols.ndim != 2 or cols.shape[0] != 7:
             raise ValueError("expected seven signal columns")
@@ -124,7 +128,7 @@ class DewiScorer:
         mad = (ctypes.c_double * 7)(*[self.stats.mads[k] for k in SIGNAL_FIELDS])
         lib = _native.load_library()
         with torch.cuda.device(dev):
-            rc = lib.dewi_score(ctypes.c_void_p(cols.data_ptr()), n, cols.stride(0), med, mad, self._w6(),
+            rc = lib.dewi_score(ctypes.c_void_p(cols.data_ptr()), int(in_f64), n, cols.stride(0), med, mad, self._w6(),
                                 int(bool(conditional)), ctypes.c_void_p(out.data_ptr()), int(f64), dev,
                                 _native.stream_ptr())
         _native.check(rc)
@@ -132,8 +136,8 @@ class DewiScorer:
 
     def _score_one(self, sig: Mapping[str, float], conditional: bool) -> float:
         assert self.stats is not None, "Call fit_stats() before scoring."
-        # float64 inputs are rounded to float32 on upload; signals are float32 in every batch path
-        cols = np.asarray([[sig[k]] for k in SIGNAL_FIELDS], dtype=np.float32)
+        # the reference scores the caller's un-rounded Python floats (scorer.py:28-31): float64 in
+        cols = np.asarray([[sig[k]] for k in SIGNAL_FIELDS], dtype=np.float64)
         return float(self.score_batch(cols, conditional, "float64")[0].item())
 
     def score(self, sig: Mapping[str, float]) -> float:

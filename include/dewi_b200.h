@@ -110,11 +110,12 @@ DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
 DEWI_API int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, double* med_host, double* mad_host, int device,
                    void* stream);
 /* Seven signal columns in the order ht_mean, ht_q90, hi_mean, hi_q90, I_hat, redundancy, noise
- * (column c at cols + c*ld).  med7/mad7 (host) as fitted; w6 (host) = alpha_t, alpha_i, alpha_m,
- * alpha_r, alpha_n, delta.  float64 arithmetic of scorer.py:28-31,49-89; `out` is n floats, or n
- * doubles when out_f64.                                                                        */
-DEWI_API int dewi_score(const float* cols, int64_t n, int64_t ld, const double* med7, const double* mad7, const double* w6,
-               int conditional, void* out, int out_f64, int device, void* stream);
+ * (column c at cols + c*ld elements; floats, or doubles when in_f64 -- the reference scores
+ * un-rounded Python floats, which matters when a MAD is tiny).  med7/mad7 (host) as fitted; w6
+ * (host) = alpha_t, alpha_i, alpha_m, alpha_r, alpha_n, delta.  float64 arithmetic of
+ * scorer.py:28-31,49-89; `out` is n floats, or n doubles when out_f64.                          */
+DEWI_API int dewi_score(const void* cols, int in_f64, int64_t n, int64_t ld, const double* med7, const double* mad7,
+               const double* w6, int conditional, void* out, int out_f64, int device, void* stream);
 
 /* ---- redundancy: replaces RedundancyEstimator's normalise + matmul (redundancy.py:36-38) ---- */
 /* out[m, n] = normalize(a)[m, d] @ normalize(b)[n, d]^T, fp32, eps 1e-12 as torch F.normalize. */

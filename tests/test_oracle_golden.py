@@ -1,0 +1,90 @@
+"""The oracle (CPU restatement) against the fixtures produced by the unmodified reference
+(oracle/make_golden.py).  Runs without a GPU; this is what pins the oracle (BASELINE tier rule 3)."""
+
+import json
+
+import numpy as np
+import pytest
+
+from oracle import redundancy as ored
+from oracle import scorer as oscorer
+from oracle import search as osearch
+
+from _util import GOLD, entropy_column, load_search_golden
+
+SEARCH_CASES = ["cos_n100_d128", "cos_n2000_d64", "cos_n3000_d768", "cos_n15_d16_k5", "cos_n12_d8_k10", "l2_n500_d32"]
+SCORER_CASES = ["readme_n1001", "readme_n1000", "profile_n4096"]
+
+
+def test_manifest_lists_every_fixture():
+    man = json.loads((GOLD / "MANIFEST.json").read_text())
+    assert len(man["cases"]) == 12
+    assert len(list(GOLD.glob("*.npz"))) == 12
+
+
+@pytest.mark.parametrize("name", SEARCH_CASES)
+def test_search_oracle_bit_exact(name):
+    g = load_search_golden(name)
+    cosine = g["space"] == "cosine"
+    rows = osearch.normalize_rows_like_add(g["emb"]) if cosine else g["emb"]
+    ent = entropy_column(g["payload"])
+    for gi, (eta, pref) in enumerate(g["grid"]):
+        for qi, q in enumerate(g["queries"]):
+            idx, sc = osearch.exact_search(rows, g["payload"][:, 0], ent, q, g["k"], eta, pref, cosine)
+            assert np.array_equal(idx, g["ref_idx"][gi, qi])
+            assert np.array_equal(sc, g["ref_scores"][gi, qi])
+
+
+def test_search_oracle_object_form_and_errors():
+    g = load_search_golden("cos_n15_d16_k5")
+
+    class P:
+        def __init__(self, row):
+            self.dewi, self.ht_mean, self.hi_mean = float(row[0]), float(row[1]), float(row[3])
+
+    ix = osearch.OracleExactIndex(16)
+    with pytest.raises(ValueError):
+        ix.build()
+    for i, e in enumerate(g["emb"]):
+        ix.add(f"doc_{i:08d}", e, P(g["payload"][i]))
+    with pytest.raises(ValueError):
+        ix.add("bad", np.zeros(3, np.float32), P(g["payload"][0]))
+    ix.build()
+    eta, pref = g["grid"][0]
+    res = ix.search(g["queries"][0], k=g["k"], eta=eta, entropy_pref=pref)
+    assert [int(r[0][4:]) for r in res] == g["ref_idx"][0, 0].tolist()
+    with pytest.raises(ValueError):  # k > N (backends.py:468)
+        ix.search(g["queries"][0], k=16)
+
+
+@pytest.mark.parametrize("name", SCORER_CASES)
+def test_scorer_oracle_bit_exact(name):
+    g = np.load(GOLD / f"scorer_{name}.npz")
+    cols = {k: g["signals"][i] for i, k in enumerate(oscorer.SIGNAL_KEYS)}
+    med, mad = oscorer.robust_fit(cols)
+    assert [med[k] for k in oscorer.SIGNAL_KEYS] == g["med"].tolist()
+    assert [mad[k] for k in oscorer.SIGNAL_KEYS] == g["mad"].tolist()
+    w = tuple(g["weights"])
+    assert np.array_equal(oscorer.score_rows(cols, med, mad, w, False), g["score"])
+    assert np.array_equal(oscorer.score_rows(cols, med, mad, w, True), g["score_conditional"])
+
+
+def test_scorer_oracle_one_row_zero_mad():
+    g = np.load(GOLD / "scorer_onerow.npz")
+    sig = dict(zip([str(k) for k in g["keys"]], g["row"].tolist()))
+    w = g["weights"]
+    o = oscorer.OracleScorer(w[:5], w[5])
+    o.fit_stats([sig])
+    assert all(o.mad[k] == 1e-8 for k in sig)  # scorer.py:24 `or 1e-8`
+    assert o.score(sig) == float(g["score"]) and o.score_conditional(sig) == float(g["score_conditional"])
+
+
+@pytest.mark.parametrize("name", ["t37_i53_d512", "t64_i64_d64"])
+def test_redundancy_oracle(name):
+    g = np.load(GOLD / f"redundancy_{name}.npz")
+    sim = ored.cross_modal_similarity(g["tfeat"], g["ifeat"])
+    assert sim.shape == g["sim"].shape and sim.dtype == np.float32
+    np.testing.assert_allclose(sim, g["sim"], atol=5e-7, rtol=0)
+    mx, am, cnt, pairs = ored.join_rowstats(g["tfeat"], g["ifeat"], 0.9)
+    np.testing.assert_array_equal(am, np.argmax(sim, axis=1))
+    assert cnt.sum() == len(pairs) == int((sim >= np.float32(0.9)).sum()) > 0

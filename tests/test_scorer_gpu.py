@@ -1,0 +1,81 @@
+"""fit_stats / score parity: medians and MADs bit-exact, scores within 1e-6 relative (north star)."""
+
+import numpy as np
+import pytest
+
+import dewi_b200
+from oracle import scorer as oscorer
+
+from _util import GOLD, SIGNAL_FIELDS, synth_payload_columns
+
+pytestmark = pytest.mark.gpu
+SCORE_RTOL = 1e-6
+
+
+@pytest.mark.parametrize("name", ["readme_n1001", "readme_n1000", "profile_n4096"])
+def test_golden_scorer(name):
+    g = np.load(GOLD / f"scorer_{name}.npz")
+    w = g["weights"]
+    s = dewi_b200.DewiScorer(dewi_b200.Weights(*w[:5]), delta=float(w[5]))
+    s.fit_stats_columns(g["signals"].astype(np.float32))
+    assert [s.stats.medians[k] for k in SIGNAL_FIELDS] == g["med"].tolist()
+    assert [s.stats.mads[k] for k in SIGNAL_FIELDS] == g["mad"].tolist()
+    for cond, key in ((False, "score"), (True, "score_conditional")):
+        out = s.score_batch(g["signals"].astype(np.float32), conditional=cond, out_dtype="float64").cpu().numpy()
+        np.testing.assert_allclose(out, g[key], rtol=SCORE_RTOL, atol=0)
+        out32 = s.score_batch(g["signals"].astype(np.float32), conditional=cond).cpu().numpy()
+        np.testing.assert_allclose(out32, g[key], rtol=SCORE_RTOL, atol=0)
+
+
+def test_per_row_api_and_one_row_fit():
+    """tests/test_scorer_weights.py: fit on ONE row (MAD = 0 -> 1e-8), extra key fitted, floats out."""
+    g = np.load(GOLD / "scorer_onerow.npz")
+    sig = dict(zip([str(k) for k in g["keys"]], g["row"].tolist()))
+    w = g["weights"]
+    s = dewi_b200.DewiScorer(weights=dewi_b200.Weights(*w[:5]))
+    assert not s.is_fitted()
+    with pytest.raises(AssertionError):
+        s.score(sig)
+    s.fit_stats([sig])
+    assert s.is_fitted() and set(s.stats.medians) == set(sig)
+    assert all(s.stats.mads[k] == 1e-8 for k in sig)
+    a, b = s.score(sig), s.score_conditional(sig)
+    assert isinstance(a, float) and isinstance(b, float)
+    assert a == pytest.approx(float(g["score"]), rel=SCORE_RTOL)
+    assert b == pytest.approx(float(g["score_conditional"]), rel=SCORE_RTOL)
+
+
+def test_signals_rows_fit_like_the_readme():
+    rng = np.random.RandomState(4)
+    pay = synth_payload_columns(rng, 257, "readme")
+    rows = [dewi_b200.Signals(**{f: float(pay[i, j + 1]) for j, f in enumerate(SIGNAL_FIELDS)}) for i in range(257)]
+    s = dewi_b200.DewiScorer()
+    s.fit_stats(rows)
+    o = oscorer.OracleScorer()
+    o.fit_stats([dict(r.items()) for r in rows])
+    assert s.stats.medians == o.med and s.stats.mads == o.mad
+    for r in rows[:5]:
+        assert s.score(r) == pytest.approx(o.score(r), rel=SCORE_RTOL)
+        assert dewi_b200.Payload(**r.__dict__, dewi=s.score(r)).ht_mean == r.ht_mean  # README.md:109
+
+
+@pytest.mark.parametrize("n", [2, 3, 1 << 20, (1 << 22) + 5])
+@pytest.mark.parametrize("style", ["readme", "profile"])
+def test_differential_fit_and_score(n, style):
+    """Odd/even n, heavy duplicates, negative values and constants stress the radix selection."""
+    rng = np.random.RandomState(n % 1000 + len(style))
+    pay = synth_payload_columns(rng, n, style)
+    sig = pay[:, 1:].T.astype(np.float32).copy()
+    sig[4] = np.round(sig[4] * 8) / 8          # massive ties
+    sig[5] -= 0.5                               # negative values
+    if n > 3:
+        sig[6, : n // 2 + 1] = 0.125            # median sits inside a constant run -> MAD = 0
+    cols = {k: sig[i] for i, k in enumerate(SIGNAL_FIELDS)}
+    med, mad = oscorer.robust_fit(cols)
+    s = dewi_b200.DewiScorer(dewi_b200.Weights(0.6, 0.2, 1.0, 0.2, 0.1), delta=2.0)
+    s.fit_stats_columns(sig)
+    assert s.stats.medians == med and s.stats.mads == mad
+    ref = oscorer.score_rows(cols, med, mad, (0.6, 0.2, 1.0, 0.2, 0.1, 2.0))
+    out = s.score_batch(sig, out_dtype="float64").cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=SCORE_RTOL, atol=0)
+    assert out.min() >= 1 / (1 + np.exp(2.0)) - 1e-12 and out.max() <= 1 / (1 + np.exp(-2.0)) + 1e-12

@@ -1,0 +1,197 @@
+"""Parity of the CUDA search path with the reference's exact numpy re-rank path (through the C ABI).
+
+fp32 mode: identical top-k ids outside ties, scores within 1e-5 relative (BASELINE.json north star).
+bf16-storage mode: recall@10 >= 0.999 against the exact result on the same bf16-representable rows."""
+
+import numpy as np
+import pytest
+
+import dewi_b200
+from dewi_b200 import _native
+from oracle import search as osearch
+
+from _util import (PAYLOAD_FIELDS, bf16_round, check_topk, entropy_column, load_search_golden, make_corpus,
+                   recall_at_k)
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["cos_n100_d128", "cos_n2000_d64", "cos_n3000_d768", "cos_n15_d16_k5", "cos_n12_d8_k10", "l2_n500_d32"]
+
+
+def payload_objects(pay):
+    return [dewi_b200.Payload(**{f: float(pay[i, j]) for j, f in enumerate(PAYLOAD_FIELDS)}) for i in range(len(pay))]
+
+
+def build_index(emb, pay, space="cosine", **kw):
+    """Per-document add() exactly as a reference user would (tests/test_index.py:103-127)."""
+    ix = dewi_b200.DewiIndex(dim=emb.shape[1], space=space, backend="cuda", **kw)
+    for i, p in enumerate(payload_objects(pay)):
+        ix.add(f"doc_{i:08d}", emb[i], p)
+    ix.build()
+    return ix
+
+
+def bulk_index(emb, pay, dtype="fp32", normalized=True, **kw):
+    ix = dewi_b200.DewiIndex(dim=emb.shape[1], space="cosine", backend="cuda", dtype=dtype, **kw)
+    ix.add_batch(None, emb, payload_columns=pay.astype(np.float32), normalized=normalized)
+    ix.build()
+    return ix
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_golden_single_query_api(name):
+    """`DewiIndex.search` (1-D query contract) against outputs of the unmodified reference."""
+    g = load_search_golden(name)
+    ix = build_index(g["emb"], g["payload"], g["space"])
+    for gi, (eta, pref) in enumerate(g["grid"]):
+        for qi, q in enumerate(g["queries"]):
+            res = ix.search(q, k=g["k"], eta=eta, entropy_pref=pref)
+            assert all(isinstance(r[0], str) and isinstance(r[1], float) and isinstance(r[2], dewi_b200.Payload) for r in res)
+            got_idx = [int(r[0][4:]) for r in res]
+            check_topk(g["ref_idx"][gi, qi], g["ref_scores"][gi, qi], got_idx, [r[1] for r in res],
+                       what=f"{name} grid{gi} q{qi}")
+
+
+@pytest.mark.parametrize("name", ["cos_n2000_d64", "cos_n3000_d768"])
+@pytest.mark.parametrize("path", ["simt", "tc"])
+def test_golden_batch_both_sweeps(name, path):
+    """The tcgen05 sweep and the CUDA-core sweep are interchangeable: both reproduce the reference."""
+    g = load_search_golden(name)
+    ix = build_index(g["emb"], g["payload"], g["space"])
+    flag = _native.FLAG_FORCE_TC if path == "tc" else _native.FLAG_FORCE_SIMT
+    for gi, (eta, pref) in enumerate(g["grid"]):
+        ids, sc = ix._backend.search_batch(g["queries"], g["k"], eta, pref, flags=flag)
+        for qi in range(len(g["queries"])):
+            check_topk(g["ref_idx"][gi, qi], g["ref_scores"][gi, qi], ids[qi], sc[qi], what=f"{name}/{path} grid{gi} q{qi}")
+
+
+@pytest.mark.parametrize("n,d,b,k", [(50_000, 768, 33, 10), (20_011, 128, 130, 10), (4_096, 512, 5, 64), (300_000, 64, 7, 10)])
+def test_fp32_differential_vs_oracle(n, d, b, k):
+    """Seeded corpora incl. ragged tile tails and B that is not a multiple of the query block."""
+    emb, pay = make_corpus(n, d, seed=100 + d)
+    rng = np.random.RandomState(5)
+    queries = rng.standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay)
+    ent = entropy_column(pay)
+    for eta, pref in [(0.3, 0.5), (0.0, 0.0), (1.0, -1.0)]:
+        ids, sc = ix.search_batch(queries, k=k, eta=eta, entropy_pref=pref)
+        rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], ent, queries, k, eta, pref, True)
+        for qi in range(b):
+            check_topk(rid[qi], rsc[qi], ids[qi], sc[qi], what=f"n{n} d{d} eta{eta} pref{pref} q{qi}")
+
+
+def test_device_tensor_io_matches_host_io():
+    import torch
+
+    emb, pay = make_corpus(30_000, 256, seed=3)
+    ix = bulk_index(emb, pay)
+    q = np.random.RandomState(1).standard_normal((16, 256)).astype(np.float32)
+    ids_h, sc_h = ix.search_batch(q, k=10, eta=0.25, entropy_pref=0.0)
+    ids_d, sc_d = ix.search_batch(torch.from_numpy(q).cuda(), k=10, eta=0.25, entropy_pref=0.0)
+    assert np.array_equal(ids_h, ids_d.cpu().numpy()) and np.array_equal(sc_h, sc_d.cpu().numpy())
+    assert ix._backend.last_launches() >= 4
+
+
+def test_device_side_normalisation_close_to_numpy():
+    """add_batch(normalized=False) normalises on the device; rows agree with numpy to 1 ulp-ish."""
+    rng = np.random.RandomState(8)
+    raw = (rng.standard_normal((5000, 96)) * rng.uniform(0.1, 30, (5000, 1))).astype(np.float32)
+    pay = np.zeros((5000, 8))
+    ix = bulk_index(raw, pay, normalized=False)
+    ref = raw / np.linalg.norm(raw, axis=1, keepdims=True)
+    got = np.stack([ix._backend.get_row(i) for i in (0, 17, 4999)])
+    np.testing.assert_allclose(got, ref[[0, 17, 4999]], rtol=3e-7, atol=1e-9)
+    with pytest.raises(ValueError):
+        ix.add_batch(None, np.zeros((2, 96), np.float32), normalized=False)  # zero-norm row
+
+
+def test_bf16_storage_recall_gate():
+    """bf16 corpus: recall@10 >= 0.999 vs the exact search over the same bf16-representable rows
+    (bulk-assigned into the oracle); queries stay fp32 on both sides."""
+    n, d, b, k = 200_000, 768, 1024, 10
+    emb, pay = make_corpus(n, d, seed=77)
+    emb16 = bf16_round(emb)
+    queries = np.random.RandomState(78).standard_normal((b, d)).astype(np.float32)
+    ent = entropy_column(pay)
+    rid, rsc = osearch.exact_search_batch(emb16, pay[:, 0], ent, queries, k, 0.3, 0.5, True)
+    for precise in (False, True):
+        ix = bulk_index(emb, pay, dtype="bf16", precise_query=precise)
+        np.testing.assert_array_equal(ix._backend.get_row(123), emb16[123])
+        ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+        rec = recall_at_k(rid, ids)
+        assert rec >= 0.999, f"recall@{k} = {rec} (precise_query={precise})"
+        same = ids == rid
+        np.testing.assert_allclose(sc[same], rsc[same], rtol=1e-5)
+
+
+def test_edge_semantics():
+    g = load_search_golden("cos_n15_d16_k5")
+    ix = build_index(g["emb"], g["payload"])
+    with pytest.raises(ValueError):  # k > N (backends.py:468)
+        ix.search(g["queries"][0], k=16)
+    with pytest.raises(ValueError):  # 2-D query (index.py:91-92)
+        ix.search(g["queries"][:2], k=3)
+    with pytest.raises(ValueError):  # wrong embedding shape (backends.py:395-396)
+        ix.add("x", np.zeros(3, np.float32), dewi_b200.Payload())
+    assert len(ix.search(g["queries"][0], k=15)) == 15  # k == N: every document, sorted
+    # zero query: all similarities are 0, ranking by eta*dewi + pref*ent over the candidate set
+    res = ix.search(np.zeros(16, np.float32), k=15, eta=0.5, entropy_pref=0.25)
+    pay = g["payload"]
+    adj = np.float32(0.5) * pay[:, 0].astype(np.float32) + np.float32(0.25) * entropy_column(pay).astype(np.float32)
+    assert [int(r[0][4:]) for r in res] == np.argsort(-adj, kind="stable").tolist()
+    empty = dewi_b200.DewiIndex(dim=4)
+    with pytest.raises(ValueError):  # backends.py:409-410
+        empty.build()
+
+
+def test_payload_mutation_and_refresh():
+    """README flow: payload.dewi is assigned after add(); build()/refresh_payloads() snapshot it."""
+    emb, pay = make_corpus(500, 32, seed=9)
+    ix = dewi_b200.DewiIndex(dim=32)
+    objs = payload_objects(pay)
+    for i, p in enumerate(objs):
+        p.dewi = 0.0
+        ix.add(f"doc_{i:08d}", emb[i], p)
+    for i, p in enumerate(objs):
+        p.dewi = float(pay[i, 0])  # README.md:106-110
+    q = np.random.RandomState(2).standard_normal(32).astype(np.float32)
+    res = ix.search(q, k=10, eta=0.5, entropy_pref=0.0)  # lazy build reads the updated payloads
+    rid, rsc = osearch.exact_search(emb, pay[:, 0], entropy_column(pay), q, 10, 0.5, 0.0, True)
+    check_topk(rid, rsc, [int(r[0][4:]) for r in res], [r[1] for r in res], what="after mutation")
+    assert res[0][2] is objs[int(res[0][0][4:])]  # payloads are returned by reference
+    for p in objs:
+        p.dewi = 1.0 - p.dewi
+    ix.refresh_payloads()
+    res2 = ix.search(q, k=10, eta=0.5, entropy_pref=0.0)
+    rid2, rsc2 = osearch.exact_search(emb, 1.0 - pay[:, 0], entropy_column(pay), q, 10, 0.5, 0.0, True)
+    check_topk(rid2, rsc2, [int(r[0][4:]) for r in res2], [r[1] for r in res2], what="after refresh")
+
+
+def test_reference_behaviour_tests_rerun_on_cuda_backend(tmp_path):
+    """The reference's own test_index.py assertions (shape/order/monotonicity/persistence), re-run
+    with the CUDA backend substituted (tests/test_index.py:103-127,206-353)."""
+    np.random.seed(42)
+    dim, n, k = 128, 100, 10
+    emb = np.random.randn(n, dim).astype(np.float32)
+    ix = dewi_b200.DewiIndex(dim=dim, space="cosine", use_ann=False)
+    for i in range(n):
+        ix.add(f"doc_{i}", emb[i], dewi_b200.Payload(dewi=np.random.rand(), ht_mean=np.random.rand() * 3,
+                                                     hi_mean=np.random.rand() * 3))
+    q = np.random.randn(dim).astype(np.float32)
+    res = ix.search(q, k=k)
+    assert len(res) == k and len(ix) == n
+    assert all(res[i][1] >= res[i + 1][1] for i in range(k - 1))
+    assert all(r[0].startswith("doc_") for r in res)
+    mean_ent = [np.mean([(r[2].ht_mean + r[2].hi_mean) / 2 for r in ix.search(q, k=k, eta=0.0, entropy_pref=p)])
+                for p in (-1.0, 0.0, 1.0)]
+    assert mean_ent[0] <= mean_ent[1] <= mean_ent[2]
+    mean_dewi = [np.mean([r[2].dewi for r in ix.search(q, k=k, eta=e)]) for e in (0.0, 0.5, 1.0)]
+    assert mean_dewi[0] <= mean_dewi[1] <= mean_dewi[2]
+    ix.save(tmp_path / "idx")
+    for f in ("config.json", "ann_index/metadata.json", "ann_index/payloads.jsonl", "ann_index/embeddings.npy"):
+        assert (tmp_path / "idx" / f).exists()
+    back = dewi_b200.DewiIndex.load(tmp_path / "idx")
+    res2 = back.search(q, k=5)
+    assert [r[0] for r in res2] == [r[0] for r in ix.search(q, k=5)]
+    assert ix.get_payload("doc_3") is not None and ix.get_payload("nope") is None
+    np.testing.assert_allclose(ix.get_embedding("doc_3"), emb[3] / np.linalg.norm(emb[3]), rtol=1e-6)
