@@ -13,8 +13,9 @@ from .backends import BaseIndex, CudaIndex, IndexBackend  # noqa: F401
 from .index import DewiIndex  # noqa: F401
 from .scorer import DewiScorer, RobustStats  # noqa: F401
 from .redundancy import cross_modal_similarity, redundancy_join  # noqa: F401
+from .sharded import ShardedDewiIndex, shard_range  # noqa: F401
 
 __all__ = [
     "__version__", "DewiIndex", "BaseIndex", "CudaIndex", "IndexBackend", "Payload", "Signals", "Weights",
-    "DewiScorer", "RobustStats", "cross_modal_similarity", "redundancy_join",
+    "DewiScorer", "RobustStats", "cross_modal_similarity", "redundancy_join", "ShardedDewiIndex", "shard_range",
 ]

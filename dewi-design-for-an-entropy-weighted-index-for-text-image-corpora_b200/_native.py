@@ -47,9 +47,11 @@ SIGNATURES = {
     "dewi_index_size": (c_int, [c_void_p, POINTER(c_int64)]),
     "dewi_index_get_row": (c_int, [c_void_p, c_int64, c_void_p]),
     "dewi_index_search_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dewi_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "dewi_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "dewi_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "dewi_index_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "dewi_index_set_profiling": (c_int, [c_void_p, c_int]),
+    "dewi_index_last_sweep_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
     "dewi_fit_stats": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p]),
     "dewi_score": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), c_int, c_void_p, c_int, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),

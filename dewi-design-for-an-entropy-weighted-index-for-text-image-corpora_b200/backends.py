@@ -101,12 +101,44 @@ class LazyIds(Sequence):
         return i
 
 
-class ColumnPayloads:
-    """Read-only id -> Payload mapping over bulk payload columns ([N, 8] float32, PAYLOAD_FIELDS order)."""
+class ColumnStore:
+    """Host mirror of bulk payload columns as a list of `[n_i, 8]` float32 chunks (PAYLOAD_FIELDS
+    order); a chunk of `None` stands for `n_i` default payloads (all zeros, types.py:11-18)."""
 
-    def __init__(self, ids: Sequence[str], columns: np.ndarray):
+    def __init__(self):
+        self._chunks: List[Tuple[int, Optional[np.ndarray]]] = []
+        self._starts: List[int] = []
+        self.n = 0
+
+    def append(self, n: int, cols: Optional[np.ndarray]) -> None:
+        self._starts.append(self.n)
+        self._chunks.append((n, cols))
+        self.n += n
+
+    def row(self, i: int) -> np.ndarray:
+        import bisect
+
+        c = bisect.bisect_right(self._starts, i) - 1
+        n, cols = self._chunks[c]
+        return np.zeros(len(PAYLOAD_FIELDS), np.float32) if cols is None else cols[i - self._starts[c]]
+
+    def column(self, j: int) -> np.ndarray:
+        out = np.zeros(self.n, dtype=np.float32)
+        for start, (n, cols) in zip(self._starts, self._chunks):
+            if cols is not None:
+                out[start:start + n] = cols[:, j]
+        return out
+
+    def all_default(self) -> bool:
+        return all(cols is None for _, cols in self._chunks)
+
+
+class ColumnPayloads:
+    """Read-only id -> Payload mapping over a `ColumnStore`."""
+
+    def __init__(self, ids: Sequence[str], store: ColumnStore):
         self._ids = ids
-        self._cols = columns
+        self._store = store
 
     def _row(self, doc_id: str) -> Optional[int]:
         try:
@@ -119,7 +151,8 @@ class ColumnPayloads:
         return default if r is None else self.at(r)
 
     def at(self, row: int) -> Payload:
-        return Payload(**{f: float(self._cols[row, j]) for j, f in enumerate(PAYLOAD_FIELDS)})
+        vals = self._store.row(row)
+        return Payload(**{f: float(vals[j]) for j, f in enumerate(PAYLOAD_FIELDS)})
 
     def __getitem__(self, doc_id: str) -> Payload:
         r = self._row(doc_id)
@@ -172,7 +205,7 @@ class CudaIndex(BaseIndex):
         self._h = h
         self._pending: List[np.ndarray] = []   # normalised host rows not yet uploaded
         self._n_device = 0                     # rows resident on the GPU
-        self._columns: Optional[np.ndarray] = None  # bulk payload columns [N, 8] (bulk ingest only)
+        self._columns: Optional[ColumnStore] = None  # bulk payload columns (bulk ingest only)
         self._flags = _native.FLAG_PRECISE_QUERY if precise_query else 0
         self._host_rows: Optional[np.ndarray] = None
 
@@ -242,28 +275,28 @@ class CudaIndex(BaseIndex):
             if len(doc_ids) != n:
                 raise ValueError("doc_ids and embeddings disagree in length")
             self._doc_ids = list(self._doc_ids) + list(doc_ids)
-        if payload_columns is not None:
-            cols = np.ascontiguousarray(payload_columns, dtype=np.float32)
-            if cols.shape != (n, len(PAYLOAD_FIELDS)):
-                raise ValueError(f"payload_columns must be [n, {len(PAYLOAD_FIELDS)}]")
-            if self._payloads and not isinstance(self._payloads, ColumnPayloads):
+        if payloads is not None:
+            if payload_columns is not None or self._columns is not None:
                 raise ValueError("cannot mix payload objects and payload columns")
-            self._columns = cols if self._columns is None else np.concatenate([self._columns, cols])
-            self._payloads = ColumnPayloads(self._doc_ids, self._columns)
-        elif payloads is not None:
             if len(payloads) != n or doc_ids is None:
                 raise ValueError("payload objects need matching doc_ids")
             for d, p in zip(doc_ids, payloads):
                 self._payloads[d] = p
+        elif payload_columns is not None or self._columns is not None or not self._payloads:
+            cols = None
+            if payload_columns is not None:
+                cols = np.ascontiguousarray(payload_columns, dtype=np.float32)
+                if cols.shape != (n, len(PAYLOAD_FIELDS)):
+                    raise ValueError(f"payload_columns must be [n, {len(PAYLOAD_FIELDS)}]")
+            if self._payloads and not isinstance(self._payloads, ColumnPayloads):
+                raise ValueError("cannot mix payload objects and payload columns")
+            if self._columns is None:
+                self._columns = ColumnStore()
+            self._columns.append(n, cols)
+            self._payloads = ColumnPayloads(self._doc_ids, self._columns)
         else:
-            if self._columns is None and not self._payloads:
-                self._columns = np.zeros((0, len(PAYLOAD_FIELDS)), dtype=np.float32)
-            if self._columns is not None:
-                self._columns = np.concatenate([self._columns, np.zeros((n, len(PAYLOAD_FIELDS)), np.float32)])
-                self._payloads = ColumnPayloads(self._doc_ids, self._columns)
-            else:
-                for d in self._doc_ids[base:]:
-                    self._payloads.setdefault(d, Payload())
+            for d in self._doc_ids[base:]:
+                self._payloads.setdefault(d, Payload())
         self._is_trained = False
         self._host_rows = None
 
@@ -296,8 +329,11 @@ class CudaIndex(BaseIndex):
         if n == 0:
             return
         if self._columns is not None:
-            dewi = np.ascontiguousarray(self._columns[:, 0], dtype=np.float32)
-            ent = ((self._columns[:, 1].astype(np.float64) + self._columns[:, 3].astype(np.float64)) * 0.5).astype(np.float32)
+            if self._columns.all_default():
+                return  # device columns are zero-initialised, or were written by set_payload_columns()
+            dewi = self._columns.column(0)
+            ent = ((self._columns.column(1).astype(np.float64) + self._columns.column(3).astype(np.float64)) * 0.5
+                   ).astype(np.float32)
         else:
             dewi = np.empty(n, dtype=np.float32)
             ent = np.empty(n, dtype=np.float32)
@@ -327,6 +363,12 @@ class CudaIndex(BaseIndex):
             _native.check(self._lib.dewi_index_set_payload(self._h, ctypes.c_void_p(dp), ctypes.c_void_p(ep), int(offset), n,
                                                            dh, _native.stream_ptr()))
             torch.cuda.current_stream().synchronize()
+
+    def reserve(self, rows: int) -> None:
+        """Pre-size the device planes for `rows` rows (one allocation instead of geometric regrowth)."""
+        torch = _torch()
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.dewi_index_reserve(self._h, int(rows)))
 
     def set_id_base(self, id_base: int) -> None:
         """Global id of row 0 when this index is one shard of a row-sharded corpus."""
@@ -410,25 +452,48 @@ class CudaIndex(BaseIndex):
         """Shard-local stage (sweep + candidate selection): CUDA `[B, dim]` queries -> the shard's
         `kcand` best rows per query as `(sim, global_id, dewi, ent)` CUDA tensors `[B, kcand]`."""
         torch = _torch()
-        q = queries.detach().to(dtype=torch.float32).contiguous()
-        b = q.shape[0]
-        dev = q.device
+        b, dev = queries.shape[0], queries.device
         sim = torch.empty((b, kcand), dtype=torch.float32, device=dev)
         gid = torch.empty((b, kcand), dtype=torch.int64, device=dev)
         dewi = torch.empty((b, kcand), dtype=torch.float32, device=dev)
         ent = torch.empty((b, kcand), dtype=torch.float32, device=dev)
+        self.search_local_into(queries, kcand, sim, gid, dewi, ent, flags)
+        return sim, gid, dewi, ent
+
+    def search_local_into(self, queries, kcand: int, sim, gid, dewi, ent, flags: int = 0) -> None:
+        """`search_local` writing into caller-provided contiguous `[B, kcand]` CUDA tensors (the
+        sharded path points these at its packed exchange buffer)."""
+        torch = _torch()
+        if not self._is_trained:
+            self.build()
+        q = queries.detach().to(dtype=torch.float32).contiguous()
+        if q.ndim != 2 or q.shape[1] != self.dim or not q.is_cuda or q.device.index != self.device:
+            raise ValueError(f"Expected a CUDA tensor of shape (B, {self.dim}) on device {self.device}")
+        b = q.shape[0]
+        for t, dt in ((sim, torch.float32), (gid, torch.int64), (dewi, torch.float32), (ent, torch.float32)):
+            if tuple(t.shape) != (b, kcand) or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("output tensors must be contiguous [B, kcand] of float32/int64/float32/float32")
         with torch.cuda.device(self.device):
             rc = self._lib.dewi_index_search_local(self._h, ctypes.c_void_p(q.data_ptr()), b, int(kcand),
                                                    flags | self._flags, ctypes.c_void_p(sim.data_ptr()),
                                                    ctypes.c_void_p(gid.data_ptr()), ctypes.c_void_p(dewi.data_ptr()),
                                                    ctypes.c_void_p(ent.data_ptr()), _native.stream_ptr())
         _native.check(rc)
-        return sim, gid, dewi, ent
 
     def last_launches(self) -> int:
         n = ctypes.c_int(0)
         _native.check(self._lib.dewi_index_last_launches(self._h, ctypes.byref(n)))
         return n.value
+
+    def set_profiling(self, enable: bool = True) -> None:
+        """Bracket the sweep kernel with CUDA events (see `last_sweep_ms`)."""
+        _native.check(self._lib.dewi_index_set_profiling(self._h, int(bool(enable))))
+
+    def last_sweep_ms(self) -> Tuple[float, str]:
+        """Device time of the last search's sweep kernel and which one ran ("tcgen05" / "simt")."""
+        ms, kind = ctypes.c_float(0), ctypes.c_int(0)
+        _native.check(self._lib.dewi_index_last_sweep_ms(self._h, ctypes.byref(ms), ctypes.byref(kind)))
+        return ms.value, {1: "tcgen05", 2: "simt"}.get(kind.value, "?")
 
     # ---- stored rows / persistence ---------------------------------------------------------------
     @property

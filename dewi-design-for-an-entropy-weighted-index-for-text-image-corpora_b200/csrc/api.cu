@@ -65,6 +65,10 @@ struct dewi_index {
   DevBuf stage, qraw, qn, q0, q1, part_s, part_i, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
       out_score;
   int last_launches = 0;
+  // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
+  int profile = 0;
+  int last_sweep_kind = 0;  // 1 = tcgen05 sweep, 2 = CUDA-core sweep
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace {
@@ -193,6 +197,8 @@ int dewi_index_destroy(dewi_index_t* h) {
   cudaFree(h->dewi_col);
   cudaFree(h->ent_col);
   cudaFree(h->bad_flag);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
   for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->cand_idx, &h->cand_sim,
                     &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score})
     b->release();
@@ -331,6 +337,8 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
   const int exact_is_bf16 = h->rows_f32 ? 0 : 1;
   Partials parts;
+  if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev0, stream));
+  h->last_sweep_kind = use_tc ? 1 : 2;
   if (use_tc) {
     DEWI_TRY(ensure_corpus_maps(h, plan.n_tile));
     CUtensorMap mq0, mq1;
@@ -355,6 +363,7 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
     h->last_launches++;
     parts.n_chunks = n_chunks;
   }
+  if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev1, stream));
   parts.s = h->part_s.as<float>();
   parts.i = h->part_i.as<int>();
   parts.n_qb = n_qb;
@@ -375,15 +384,20 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   return 0;
 }
 
-int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int ncand,
-                int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
-                float* out_score, int device, void* stream_) {
-  if (B <= 0 || ncand <= 0 || k <= 0) return fail("B, ncand and k must be positive");
-  if (cand_count > ncand) cand_count = ncand;
+int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int n_shards,
+                int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
+                int64_t* out_id, float* out_score, int device, void* stream_) {
+  if (!sim || !id || !dewi_v || !ent_v || !out_id || !out_score) return fail("null argument");
+  if (B <= 0 || n_shards <= 0 || kcand <= 0 || k <= 0) return fail("B, n_shards, kcand and k must be positive");
+  if (shard_stride_bytes % 8 != 0) return fail("shard stride must be a multiple of 8 bytes");
+  const int64_t ncand = static_cast<int64_t>(n_shards) * kcand;
+  if (cand_count > ncand) cand_count = static_cast<int>(ncand);
   if (k > cand_count) return fail("k exceeds the number of candidates (k > N)");
   DEWI_CUDA(cudaSetDevice(device));
-  return launch_rerank(sim, id, dewi_v, ent_v, B, ncand, cand_count, k, w_sim, w_dewi, pref, use_pref, out_id, out_score,
-                       static_cast<cudaStream_t>(stream_));
+  // numpy evaluates (1 - eta) in float64 and rounds the weak scalar to float32 (backends.py:461)
+  return launch_rerank(sim, id, dewi_v, ent_v, B, n_shards, kcand, shard_stride_bytes, cand_count, k,
+                       static_cast<float>(1.0 - eta), static_cast<float>(eta), static_cast<float>(entropy_pref),
+                       entropy_pref != 0.0 ? 1 : 0, out_id, out_score, static_cast<cudaStream_t>(stream_));
 }
 
 int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref, int flags,
@@ -421,13 +435,34 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   const float w_dewi = static_cast<float>(eta);
   const float pref = static_cast<float>(entropy_pref);
   DEWI_TRY(launch_rerank(h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(), h->loc_ent.as<float>(),
-                         B, kcand, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
+                         B, 1, kcand, 0, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
   h->last_launches++;
   if (host_io) {
     DEWI_CUDA(cudaMemcpyAsync(out_id, d_id, static_cast<size_t>(B) * k * 8, cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaMemcpyAsync(out_score, d_sc, static_cast<size_t>(B) * k * 4, cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
   }
+  return 0;
+}
+
+int dewi_index_set_profiling(dewi_index_t* h, int enable) {
+  if (!h) return fail("null handle");
+  DEWI_TRY(set_device(h));
+  if (enable && !h->ev0) {
+    DEWI_CUDA(cudaEventCreate(&h->ev0));
+    DEWI_CUDA(cudaEventCreate(&h->ev1));
+  }
+  h->profile = enable ? 1 : 0;
+  return 0;
+}
+
+int dewi_index_last_sweep_ms(dewi_index_t* h, float* ms, int* kind) {
+  if (!h || !ms) return fail("null argument");
+  if (!h->profile || !h->ev0) return fail("profiling is not enabled on this handle");
+  DEWI_TRY(set_device(h));
+  DEWI_CUDA(cudaEventSynchronize(h->ev1));
+  DEWI_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  if (kind) *kind = h->last_sweep_kind;
   return 0;
 }
 

@@ -72,9 +72,9 @@ int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
                           float* out_ent, cudaStream_t stream);
-int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
-                  int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
-                  float* out_score, cudaStream_t stream);
+int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
+                  int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
+                  int64_t* out_id, float* out_score, cudaStream_t stream);
 
 // ---- operand preparation (prep.cu) -----------------------------------------------------------
 // rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.

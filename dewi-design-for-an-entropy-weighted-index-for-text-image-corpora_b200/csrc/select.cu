@@ -181,24 +181,35 @@ finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict_
 }
 
 // ---- rerank -------------------------------------------------------------------------------------
+// Candidate c of query b lives in shard g = c / kcand, slot j = c % kcand, at element
+// b * kcand + j of that shard's arrays; shard g's arrays start g * shard_stride BYTES after shard 0's
+// (the layout an all-gather of per-rank [B, kcand] blocks produces).
+template <typename T>
+__device__ __forceinline__ T shard_at(const T* base, int c, int b, int kcand, long long shard_stride) {
+  const int g = c / kcand, j = c - g * kcand;
+  const char* p = reinterpret_cast<const char*>(base) + static_cast<long long>(g) * shard_stride;
+  return reinterpret_cast<const T*>(p)[static_cast<size_t>(b) * kcand + j];
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, const float* __restrict__ dewi,
-              const float* __restrict__ ent, int ncand, int cand_count, int k, float w_sim, float w_dewi, float pref,
-              int use_pref, long long* __restrict__ out_id, float* __restrict__ out_score) {
+              const float* __restrict__ ent, int n_shards, int kcand, long long shard_stride, int cand_count, int k,
+              float w_sim, float w_dewi, float pref, int use_pref, long long* __restrict__ out_id,
+              float* __restrict__ out_score) {
   extern __shared__ unsigned long long sh[];
+  const int ncand = n_shards * kcand;
   const int p = next_pow2(ncand);
   unsigned long long* key = sh;
   int* val = reinterpret_cast<int*>(sh + p);
   float* adj = reinterpret_cast<float*>(val + p);
   const int b = blockIdx.x;
-  const size_t base = static_cast<size_t>(b) * ncand;
   // 1. candidate set: the cand_count best by similarity (backends.py:439-447)
   for (int t = threadIdx.x; t < p; t += blockDim.x) {
     unsigned long long kk = 0ull;
     int vv = -1;
     if (t < ncand) {
-      const long long g = id[base + t];
-      if (g >= 0) { kk = make_key(sim[base + t], static_cast<uint32_t>(g)); vv = t; }
+      const long long g = shard_at(id, t, b, kcand, shard_stride);
+      if (g >= 0) { kk = make_key(shard_at(sim, t, b, kcand, shard_stride), static_cast<uint32_t>(g)); vv = t; }
     }
     key[t] = kk;
     val[t] = vv;
@@ -210,9 +221,10 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
     unsigned long long kk = 0ull;
     float a = 0.f;
     if (slot >= 0) {
-      a = __fadd_rn(__fmul_rn(w_sim, sim[base + slot]), __fmul_rn(w_dewi, dewi[base + slot]));
-      if (use_pref) a = __fadd_rn(a, __fmul_rn(pref, ent[base + slot]));
-      kk = make_key(a, static_cast<uint32_t>(id[base + slot]));
+      a = __fadd_rn(__fmul_rn(w_sim, shard_at(sim, slot, b, kcand, shard_stride)),
+                    __fmul_rn(w_dewi, shard_at(dewi, slot, b, kcand, shard_stride)));
+      if (use_pref) a = __fadd_rn(a, __fmul_rn(pref, shard_at(ent, slot, b, kcand, shard_stride)));
+      kk = make_key(a, static_cast<uint32_t>(shard_at(id, slot, b, kcand, shard_stride)));
     }
     // entry t is read and rewritten by the same thread only: no cross-thread hazard
     key[t] = kk;
@@ -225,7 +237,7 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
     const int slot = (t < p) ? val[t] : -1;
     const size_t o = static_cast<size_t>(b) * k + t;
     if (slot >= 0) {
-      out_id[o] = id[base + slot];
+      out_id[o] = shard_at(id, slot, b, kcand, shard_stride);
       out_score[o] = adj[slot];
     } else {
       out_id[o] = -1;
@@ -271,17 +283,18 @@ int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int
   return 0;
 }
 
-int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
-                  int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
-                  float* out_score, cudaStream_t stream) {
-  const int p = next_pow2(ncand);
+int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
+                  int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
+                  int64_t* out_id, float* out_score, cudaStream_t stream) {
+  const int p = next_pow2(n_shards * kcand);
   if (p > 8192) return fail("too many gathered candidates per query");
   const size_t smem = static_cast<size_t>(p) * 16;
   auto kern = rerank_kernel;
   if (smem > 48 * 1024)
     DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<B, kSelThreads, smem, stream>>>(sim, reinterpret_cast<const long long*>(id), dewi, ent, ncand, cand_count, k,
-                                         w_sim, w_dewi, pref, use_pref, reinterpret_cast<long long*>(out_id), out_score);
+  kern<<<B, kSelThreads, smem, stream>>>(sim, reinterpret_cast<const long long*>(id), dewi, ent, n_shards, kcand,
+                                         shard_stride_bytes, cand_count, k, w_sim, w_dewi, pref, use_pref,
+                                         reinterpret_cast<long long*>(out_id), out_score);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,21 +86,30 @@ DEWI_API int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host);
  * two payload columns of that row.  All outputs are [B, kcand] device arrays.               */
 DEWI_API int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream);
-/* Stage 3: DEWI blend and final select (backends.py:461-481) over `ncand` gathered candidates per
- * query (the concatenation of every shard's stage-1 output).  Keeps the `cand_count`
- * (= min(2k, N_total), backends.py:440) best by similarity, computes in fp32
- *     adj = w_sim * sim + w_dewi * dewi  [+ pref * ent   when use_pref]
- * with w_sim = float32(1 - eta), w_dewi = float32(eta) rounded exactly as numpy does, and writes
- * the k best by adj, sorted descending.  Does not need an index handle.                        */
-DEWI_API int dewi_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int ncand,
-                int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref, int64_t* out_id,
-                float* out_score, int device, void* stream);
+/* Stage 3: DEWI blend and final select (backends.py:461-481) over the candidates gathered from
+ * `n_shards` shards.  Each shard contributed [B, kcand] arrays laid out as stage 1 writes them;
+ * shard g's arrays start g * shard_stride_bytes after shard 0's (`sim`, `id`, `dewi`, `ent` point
+ * at shard 0's) -- the layout an all-gather of per-rank blocks produces; n_shards = 1 reads
+ * stage-1 output in place.  Keeps the `cand_count` (= min(2k, N_total), backends.py:440) best by
+ * similarity, computes in fp32
+ *     adj = float32(1 - eta) * sim + float32(eta) * dewi  [+ float32(pref) * ent  when pref != 0]
+ * with the weak-scalar rounding numpy applies, and writes the k best by adj, sorted descending,
+ * into out_id / out_score [B, k].  Does not need an index handle.                              */
+DEWI_API int dewi_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards,
+                int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
+                int64_t* out_id, float* out_score, int device, void* stream);
 /* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,
                       int flags, int64_t* out_id, float* out_score, void* stream);
 /* Kernel launches issued by the last search on this handle (bench.py's `gpu_launches`). */
 DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
+
+/* Measurement aid: when enabled, searches bracket the sweep kernel (stage 1's dominant launch) with
+ * CUDA events on the caller's stream; last_sweep_ms waits for the last one and returns its device
+ * time and which sweep ran (1 = tcgen05 tensor-core sweep, 2 = CUDA-core sweep).               */
+DEWI_API int dewi_index_set_profiling(dewi_index_t* h, int enable);
+DEWI_API int dewi_index_last_sweep_ms(dewi_index_t* h, float* ms, int* kind);
 
 /* ---- scorer: replaces RobustStats.fit and DewiScorer.score (scorer.py:18-31,49-89) ---------- */
 /* Median and MAD of `f` fp32 columns of `n` values each (column c starts at cols + c*ld).

@@ -1,0 +1,72 @@
+"""Row-sharded search over real GPUs (NCCL): needs >= 2 devices, one process per GPU."""
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, n, d, b, k, dtype, ret):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dewi_b200 import ShardedDewiIndex, shard_range
+        from _util import make_corpus
+
+        emb, pay = make_corpus(n, d, seed=41)
+        queries = np.random.RandomState(42).standard_normal((b, d)).astype(np.float32)
+        lo, hi = shard_range(n, world, rank, align=128)
+        ix = ShardedDewiIndex(d, dtype=dtype, device=rank)
+        ix.add_local(emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        ix.build()
+        assert len(ix) == n and ix.id_base == lo
+        ids, sc = ix.search_batch(torch.from_numpy(queries).cuda(), k=k, eta=0.3, entropy_pref=0.5)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ret["ids"], ret["scores"] = ids.cpu().numpy(), sc.cpu().numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_nccl_sharded_search_matches_oracle(dtype):
+    import torch.multiprocessing as mp
+
+    from oracle import search as osearch
+
+    from _util import bf16_round, check_topk, entropy_column, make_corpus, recall_at_k
+
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    world = min(world, 8)
+    n, d, b, k = 60_000, 256, 32, 10
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n, d, b, k, dtype, ret), nprocs=world, join=True)
+        ids, scores = ret["ids"], ret["scores"]
+    emb, pay = make_corpus(n, d, seed=41)
+    queries = np.random.RandomState(42).standard_normal((b, d)).astype(np.float32)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries, k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for q in range(b):
+            check_topk(rid[q], rsc[q], ids[q], scores[q], what=f"nccl q{q}")
+    else:
+        assert recall_at_k(rid, ids) >= 0.999

@@ -195,3 +195,42 @@ def test_reference_behaviour_tests_rerun_on_cuda_backend(tmp_path):
     assert [r[0] for r in res2] == [r[0] for r in ix.search(q, k=5)]
     assert ix.get_payload("doc_3") is not None and ix.get_payload("nope") is None
     np.testing.assert_allclose(ix.get_embedding("doc_3"), emb[3] / np.linalg.norm(emb[3]), rtol=1e-6)
+
+
+@pytest.mark.parametrize("n_shards", [2, 5])
+def test_virtual_shards_merge_equals_single_index(n_shards):
+    """The multi-GPU merge on one device: S shard indexes with global id bases write their stage-1
+    blocks into one 'gathered' buffer, `dewi_rerank` reads it shard-strided."""
+    import ctypes
+
+    import torch
+
+    from dewi_b200.sharded import PackedCandidates, shard_range
+
+    n, d, b, k = 40_000, 128, 9, 10
+    emb, pay = make_corpus(n, d, seed=31)
+    queries = torch.from_numpy(np.random.RandomState(32).standard_normal((b, d)).astype(np.float32)).cuda()
+    kcand = 2 * k
+    pk = PackedCandidates(b, kcand, queries.device, world=n_shards)
+    blocks = pk.gathered.view(n_shards, pk.words)
+    shards = []
+    for g in range(n_shards):
+        lo, hi = shard_range(n, n_shards, g, align=64)
+        ix = dewi_b200.CudaIndex(d)
+        ix.add_batch(None, emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        ix.set_id_base(lo)
+        ix.build()
+        ids, sim, dewi, ent = pk.views(blocks[g])
+        ix.search_local_into(queries, kcand, sim, ids, dewi, ent)
+        shards.append(ix)
+    ids, sim, dewi, ent = pk.views(pk.gathered)
+    out_ids = torch.empty((b, k), dtype=torch.int64, device="cuda")
+    out_sc = torch.empty((b, k), dtype=torch.float32, device="cuda")
+    lib = _native.load_library()
+    _native.check(lib.dewi_rerank(ctypes.c_void_p(sim.data_ptr()), ctypes.c_void_p(ids.data_ptr()),
+                                  ctypes.c_void_p(dewi.data_ptr()), ctypes.c_void_p(ent.data_ptr()), b, n_shards, kcand,
+                                  pk.stride_bytes, kcand, k, 0.3, 0.5, ctypes.c_void_p(out_ids.data_ptr()),
+                                  ctypes.c_void_p(out_sc.data_ptr()), 0, _native.stream_ptr()))
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), queries.cpu().numpy(), k, 0.3, 0.5, True)
+    for q in range(b):
+        check_topk(rid[q], rsc[q], out_ids[q].cpu().numpy(), out_sc[q].cpu().numpy(), what=f"S{n_shards} q{q}")
