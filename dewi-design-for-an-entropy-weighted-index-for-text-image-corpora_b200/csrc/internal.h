@@ -48,7 +48,8 @@ struct Partials {
 struct TcPlan {
   int mode;
   int n_tile;    // corpus rows per MMA (N): 128 or 256
-  int n_stages;  // smem ring depth
+  int n_stages;  // corpus ring depth
+  int q_stages;  // query ring depth
   int n_chunks;  // corpus chunks (work items per query block)
   int grid;
   size_t smem_bytes;

@@ -10,10 +10,11 @@
 // Queries sit on the MMA M dimension so that TMEM lane == query: an epilogue thread owns one query
 // and scans its lane's columns against that query's running threshold -- no cross-thread traffic.
 //
-// Warp roles (192 threads, one CTA per SM, persistent over work items):
-//   warp 0      TMA producer   : E tile k-blocks (+ the matching Q k-blocks) into a smem ring
+// Warp roles (224 threads, one CTA per SM, persistent over work items):
+//   warp 0      TMA producer   : corpus (E) tile k-blocks into a deep smem ring (HBM stream)
 //   warp 1      MMA issuer     : tcgen05.mma.kind::f16 into one of two TMEM accumulators; owns TMEM alloc
-//   warps 2..5  epilogue       : tcgen05.ld -> threshold test -> rare insertion into smem top-kc lists
+//   warps 2..5  epilogue       : tcgen05.ld -> threshold test -> append to smem candidate lists, lockstep prune
+//   warp 6      TMA producer   : query (Q) k-blocks into a shallow ring (L2-resident, re-read per tile)
 //
 // Precision modes (operand planes are bf16, products are exact, accumulation fp32):
 //   mode 0  Q0.E0                      bf16 corpus, single query plane (over-fetch + exact re-score follow)
@@ -29,8 +30,12 @@ namespace dewi {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;
+constexpr int kQWarp = 6;  // query-ring producer (kept apart so the corpus ring can run ahead)
 constexpr int kEpiWarp0 = 2;
+constexpr int kPending = 16;   // list slots beyond kc: candidates appended between two prunes
+constexpr int kGroup = 8;      // columns examined between two overflow checks (kGroup <= kPending / 2)
+constexpr int kQStagesMax = 3;
 
 struct TcArgs {
   int n_rows;
@@ -40,7 +45,8 @@ struct TcArgs {
   int n_chunks;
   int n_items;
   int kc;
-  int n_stages;
+  int e_stages;
+  int q_stages;
   float* part_s;
   int* part_i;
 };
@@ -56,6 +62,43 @@ __device__ __forceinline__ void tile_range(int chunk, int n_chunks, int n_tiles,
   t1 = static_cast<int>((static_cast<long long>(chunk + 1) * n_tiles) / n_chunks);
 }
 
+// ---- epilogue candidate lists ----------------------------------------------------------------------
+// Each epilogue thread owns one query (TMEM lane) and an UNSORTED list of up to kc + kPending
+// (score, row) pairs in shared memory, laid out [slot][query] so that lanes never share a bank.
+// Scores above the query's admission threshold are appended (two predicated stores); when any lane
+// of the warp is about to overflow, all lanes prune together, in lockstep, down to their kc best
+// and raise their thresholds.  Appending is cheap when candidates are rare (the steady state);
+// pruning is lane-parallel when candidates are frequent (the first tiles of an item).
+struct LaneList {
+  float* s;   // &list_s[qlane]
+  int* i;     // &list_i[qlane]
+  int cnt;
+  float thr;
+};
+
+__device__ __forceinline__ void lane_prune(LaneList& l, int kc) {
+  // remove the smallest entries until kc remain; then thr = smallest kept score
+  while (l.cnt > kc) {
+    float m = l.s[0];
+    int p = 0;
+#pragma unroll 4
+    for (int k = 1; k < l.cnt; ++k) {
+      const float x = l.s[k * kQueryBlock];
+      if (x < m) { m = x; p = k; }
+    }
+    const int last = l.cnt - 1;
+    l.s[p * kQueryBlock] = l.s[last * kQueryBlock];
+    l.i[p * kQueryBlock] = l.i[last * kQueryBlock];
+    l.cnt = last;
+  }
+  if (l.cnt == kc) {
+    float m = l.s[0];
+#pragma unroll 4
+    for (int k = 1; k < kc; ++k) m = fminf(m, l.s[k * kQueryBlock]);
+    l.thr = m;
+  }
+}
+
 template <int MODE, int N_TILE>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
@@ -64,19 +107,26 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   using T = ModeTraits<MODE>;
   constexpr uint32_t kEPlaneBytes = N_TILE * 128;
   constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
-  constexpr uint32_t kStageBytes = T::PE * kEPlaneBytes + T::PQ * kQPlaneBytes;
+  constexpr uint32_t kEStageBytes = T::PE * kEPlaneBytes;
+  constexpr uint32_t kQStageBytes = T::PQ * kQPlaneBytes;
   constexpr uint32_t kTmemCols = 2 * N_TILE;
   constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kQueryBlock, N_TILE);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B operand tiles.
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = smem;
-  float* list_s = reinterpret_cast<float*>(ring + static_cast<size_t>(a.n_stages) * kStageBytes);
-  int* list_i = reinterpret_cast<int*>(list_s + a.kc * kQueryBlock);
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(list_i + a.kc * kQueryBlock);
-  uint64_t* bar_empty = bar_full + kMaxStages;
-  uint64_t* bar_acc_full = bar_empty + kMaxStages;
+  // Two rings: corpus k-blocks come from HBM and need depth; query k-blocks come from L2 (the same
+  // 12 blocks over and over) and need little.
+  uint8_t* ring_e = smem;
+  uint8_t* ring_q = ring_e + static_cast<size_t>(a.e_stages) * kEStageBytes;
+  const int kl = a.kc + kPending;
+  float* list_s = reinterpret_cast<float*>(ring_q + static_cast<size_t>(a.q_stages) * kQStageBytes);
+  int* list_i = reinterpret_cast<int*>(list_s + kl * kQueryBlock);
+  uint64_t* bar_e_full = reinterpret_cast<uint64_t*>(list_i + kl * kQueryBlock);
+  uint64_t* bar_e_empty = bar_e_full + kMaxStages;
+  uint64_t* bar_q_full = bar_e_empty + kMaxStages;
+  uint64_t* bar_q_empty = bar_q_full + kQStagesMax;
+  uint64_t* bar_acc_full = bar_q_empty + kQStagesMax;
   uint64_t* bar_acc_empty = bar_acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
@@ -88,9 +138,13 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
     ptx::prefetch_tmap(&map_q0);
     if (T::PE > 1) ptx::prefetch_tmap(&map_e1);
     if (T::PQ > 1) ptx::prefetch_tmap(&map_q1);
-    for (int s = 0; s < a.n_stages; ++s) {
-      ptx::mbar_init(&bar_full[s], 1);
-      ptx::mbar_init(&bar_empty[s], 1);
+    for (int s = 0; s < a.e_stages; ++s) {
+      ptx::mbar_init(&bar_e_full[s], 1);
+      ptx::mbar_init(&bar_e_empty[s], 1);
+    }
+    for (int s = 0; s < a.q_stages; ++s) {
+      ptx::mbar_init(&bar_q_full[s], 1);
+      ptx::mbar_init(&bar_q_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&bar_acc_full[b], 1);
@@ -108,29 +162,46 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer: corpus ring =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int se = 0;
+      uint32_t pe = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+        int t0, t1;
+        tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_e_empty[se], pe ^ 1);
+            uint8_t* st = ring_e + static_cast<size_t>(se) * kEStageBytes;
+            ptx::mbar_arrive_expect_tx(&bar_e_full[se], kEStageBytes);
+            ptx::tma_load_2d(st, &map_e0, &bar_e_full[se], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
+            if (T::PE > 1)
+              ptx::tma_load_2d(st + kEPlaneBytes, &map_e1, &bar_e_full[se], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
+            if (++se == a.e_stages) { se = 0; pe ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kQWarp) {
+    // ===================== TMA producer: query ring =====================
+    if (lane == 0) {
+      int sq = 0;
+      uint32_t pq = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int qb = item % a.n_qb;
         int t0, t1;
         tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_empty[stage], phase ^ 1);
-            uint8_t* st = ring + static_cast<size_t>(stage) * kStageBytes;
-            ptx::mbar_arrive_expect_tx(&bar_full[stage], kStageBytes);
-            ptx::tma_load_2d(st, &map_e0, &bar_full[stage], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
-            if (T::PE > 1)
-              ptx::tma_load_2d(st + kEPlaneBytes, &map_e1, &bar_full[stage], kb * kKBlock, t * N_TILE,
-                               ptx::kEvictFirst);
-            uint8_t* sq = st + T::PE * kEPlaneBytes;
-            ptx::tma_load_2d(sq, &map_q0, &bar_full[stage], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+            ptx::mbar_wait(&bar_q_empty[sq], pq ^ 1);
+            uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
+            ptx::mbar_arrive_expect_tx(&bar_q_full[sq], kQStageBytes);
+            ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
             if (T::PQ > 1)
-              ptx::tma_load_2d(sq + kQPlaneBytes, &map_q1, &bar_full[stage], kb * kKBlock, qb * kQueryBlock,
+              ptx::tma_load_2d(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
                                ptx::kEvictLast);
-            if (++stage == a.n_stages) { stage = 0; phase ^= 1; }
+            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
           }
         }
       }
@@ -139,8 +210,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      int se = 0, sq = 0;
+      uint32_t pe = 0, pq = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -151,13 +222,15 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * N_TILE);
           for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_full[stage], phase);  // TMA bytes have landed
+            ptx::mbar_wait(&bar_q_full[sq], pq);
+            ptx::mbar_wait(&bar_e_full[se], pe);  // TMA bytes have landed
             ptx::tc_fence_after();
-            const uint32_t st = ptx::smem_u32(ring + static_cast<size_t>(stage) * kStageBytes);
-            const uint64_t de0 = ptx::make_desc_sw128(st);
-            const uint64_t de1 = ptx::make_desc_sw128(st + kEPlaneBytes);
-            const uint64_t dq0 = ptx::make_desc_sw128(st + T::PE * kEPlaneBytes);
-            const uint64_t dq1 = ptx::make_desc_sw128(st + T::PE * kEPlaneBytes + kQPlaneBytes);
+            const uint32_t ste = ptx::smem_u32(ring_e + static_cast<size_t>(se) * kEStageBytes);
+            const uint32_t stq = ptx::smem_u32(ring_q + static_cast<size_t>(sq) * kQStageBytes);
+            const uint64_t de0 = ptx::make_desc_sw128(ste);
+            const uint64_t de1 = ptx::make_desc_sw128(ste + kEPlaneBytes);
+            const uint64_t dq0 = ptx::make_desc_sw128(stq);
+            const uint64_t dq1 = ptx::make_desc_sw128(stq + kQPlaneBytes);
 #pragma unroll
             for (int k = 0; k < kKBlock / 16; ++k) {
               const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
@@ -165,9 +238,11 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
               if (MODE >= 1) ptx::mma_bf16_ss(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
               if (MODE == 2) ptx::mma_bf16_ss(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
             }
-            ptx::mma_commit(&bar_empty[stage]);  // smem slot reusable once these MMAs retire
+            ptx::mma_commit(&bar_e_empty[se]);  // smem slots reusable once these MMAs retire
+            ptx::mma_commit(&bar_q_empty[sq]);
             if (kb == a.n_kb - 1) ptx::mma_commit(&bar_acc_full[acc]);
-            if (++stage == a.n_stages) { stage = 0; phase ^= 1; }
+            if (++se == a.e_stages) { se = 0; pe ^= 1; }
+            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -181,17 +256,16 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
     const int qlane = quarter * 32 + lane;    // query within the 128-query block == TMEM lane
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int kc = a.kc;
+    LaneList l;
+    l.s = list_s + qlane;
+    l.i = list_i + qlane;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       int t0, t1;
       tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
-      for (int k = 0; k < kc; ++k) {
-        list_s[k * kQueryBlock + qlane] = -INFINITY;
-        list_i[k * kQueryBlock + qlane] = -1;
-      }
-      float thr = -INFINITY;  // smallest score in the list == admission threshold
-      int minpos = 0;
+      l.cnt = 0;
+      l.thr = -INFINITY;
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
@@ -210,21 +284,20 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
           float mx = v[0];
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-          if (mx > thr) {
+          if (__any_sync(0xffffffffu, mx > l.thr)) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (v[j] > thr) {
-                list_s[minpos * kQueryBlock + qlane] = v[j];
-                list_i[minpos * kQueryBlock + qlane] = r0 + j;
-                float m = list_s[qlane];
-                int p = 0;
-                for (int k = 1; k < kc; ++k) {
-                  const float x = list_s[k * kQueryBlock + qlane];
-                  if (x < m) { m = x; p = k; }
+            for (int g = 0; g < 32 / kGroup; ++g) {
+#pragma unroll
+              for (int jj = 0; jj < kGroup; ++jj) {
+                const int j = g * kGroup + jj;
+                if (v[j] > l.thr) {
+                  l.s[l.cnt * kQueryBlock] = v[j];
+                  l.i[l.cnt * kQueryBlock] = r0 + j;
+                  ++l.cnt;
                 }
-                thr = m;
-                minpos = p;
               }
+              // a lane enters a group with cnt <= kc + kPending - kGroup, so the appends above fit
+              if (__any_sync(0xffffffffu, l.cnt > kc + kPending - kGroup)) lane_prune(l, kc);
             }
           }
         }
@@ -234,12 +307,14 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      // flush this item's lists: [item][k][query]
-      float* ps = a.part_s + static_cast<size_t>(item) * kc * kQueryBlock;
-      int* pi = a.part_i + static_cast<size_t>(item) * kc * kQueryBlock;
+      // flush this item's kc best: [item][k][query]
+      lane_prune(l, kc);
+      float* ps = a.part_s + static_cast<size_t>(item) * kc * kQueryBlock + qlane;
+      int* pi = a.part_i + static_cast<size_t>(item) * kc * kQueryBlock + qlane;
       for (int k = 0; k < kc; ++k) {
-        ps[k * kQueryBlock + qlane] = list_s[k * kQueryBlock + qlane];
-        pi[k * kQueryBlock + qlane] = list_i[k * kQueryBlock + qlane];
+        const bool live = k < l.cnt;
+        ps[k * kQueryBlock] = live ? l.s[k * kQueryBlock] : -INFINITY;
+        pi[k * kQueryBlock] = live ? l.i[k * kQueryBlock] : -1;
       }
     }
   }
@@ -271,12 +346,11 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-size_t stage_bytes(int mode, int n_tile) {
-  const int pe = (mode == 2) ? 2 : 1, pq = (mode == 0) ? 1 : 2;
-  return static_cast<size_t>(pe) * n_tile * 128 + static_cast<size_t>(pq) * kQueryBlock * 128;
-}
+size_t e_stage_bytes(int mode, int n_tile) { return static_cast<size_t>((mode == 2) ? 2 : 1) * n_tile * 128; }
+size_t q_stage_bytes(int mode) { return static_cast<size_t>((mode == 0) ? 1 : 2) * kQueryBlock * 128; }
 size_t fixed_bytes(int kc) {
-  return static_cast<size_t>(kc) * kQueryBlock * 8 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
+         1024 /*alignment slack*/;
 }
 
 template <int MODE, int N_TILE>
@@ -299,11 +373,13 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   const size_t smem_max = 227 * 1024;
   int n_tile = (mode == 2) ? 128 : 256;
-  size_t fixed = fixed_bytes(kc);
+  const size_t fixed = fixed_bytes(kc);
+  const int q_stages = 2;
   int stages = 0;
   for (;;) {
-    if (fixed < smem_max) stages = static_cast<int>((smem_max - fixed) / stage_bytes(mode, n_tile));
-    if (stages >= 2 || n_tile == 128) break;
+    const size_t used = fixed + q_stages * q_stage_bytes(mode);
+    stages = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode, n_tile)) : 0;
+    if (stages >= 3 || n_tile == 128) break;
     n_tile = 128;
   }
   if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
@@ -322,9 +398,10 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   plan->mode = mode;
   plan->n_tile = n_tile;
   plan->n_stages = stages;
+  plan->q_stages = q_stages;
   plan->n_chunks = static_cast<int>(chunks);
   plan->grid = static_cast<int>(std::min<int64_t>(grid, chunks * n_qb));
-  plan->smem_bytes = fixed + static_cast<size_t>(stages) * stage_bytes(mode, n_tile);
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode, n_tile) + q_stages * q_stage_bytes(mode);
   return 0;
 }
 
@@ -353,7 +430,8 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
   a.n_chunks = plan.n_chunks;
   a.n_items = plan.n_chunks * n_qb;
   a.kc = kc;
-  a.n_stages = plan.n_stages;
+  a.e_stages = plan.n_stages;
+  a.q_stages = plan.q_stages;
   a.part_s = part_s;
   a.part_i = part_i;
   if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256>(plan, e0, e1, q0, q1, a, stream);

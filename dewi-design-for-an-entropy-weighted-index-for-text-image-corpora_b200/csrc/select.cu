@@ -56,8 +56,9 @@ __host__ __device__ inline int next_pow2(int v) {
 // Streams the query's n_chunks*kc partial candidates through a shared-memory window, keeping the
 // running best kc_out (sorted).  Window = best list + a batch of new candidates, bitonic-sorted.
 constexpr int kWindow = 2048;
+constexpr int kMergeThreads = 1024;  // one compare-exchange per thread per bitonic stage
 
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kMergeThreads)
 merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ part_i, int n_chunks, int n_qb, int kc,
                     int kc_out, int* __restrict__ cand_idx, float* __restrict__ cand_sim) {
   __shared__ unsigned long long key[kWindow];
@@ -250,7 +251,7 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
 
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream) {
   if (kc_out > kWindow / 2) return fail("candidate count too large for merge window");
-  merge_select_kernel<<<B, kSelThreads, 0, stream>>>(p.s, p.i, p.n_chunks, p.n_qb, p.kc, kc_out, cand_idx, cand_sim);
+  merge_select_kernel<<<B, kMergeThreads, 0, stream>>>(p.s, p.i, p.n_chunks, p.n_qb, p.kc, kc_out, cand_idx, cand_sim);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
