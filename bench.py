@@ -295,21 +295,21 @@ def main():
         return float(ms.item())
 
     # ---- value: device-resident queries --------------------------------------------------------------
+    # The library brackets each sweep launch with an event pair on the same stream (ring of 64, no
+    # synchronisation added), so the roofline figure comes from the very steps that are timed.
+    local.set_profiling(True)
     with ClockSampler(local_rank) as clocks:
         total_ms = timed(step_device, args.steps, args.warmup)
     ms_per_step = total_ms / args.steps
     value = args.batch * args.steps / (total_ms / 1e3)
     launches_per_step = local.last_launches() + (1 if world > 1 else 0)
 
-    # ---- roofline: the sweep kernel alone, CUDA events inside the library ----------------------------
-    local.set_profiling(True)
-    sweep_ms, kind = [], "?"
-    for i in range(max(3, min(args.steps, 10))):
-        step_device(i)
-        ms, kind = local.last_sweep_ms()
-        sweep_ms.append(ms)
+    # ---- roofline: the sweep kernel alone, live over the timed region ----------------------------------
+    n_prof = min(args.steps, 64)
+    sweep_ms = [local.sweep_ms(i) for i in range(n_prof)]
+    kind = sweep_ms[0][1]
+    sweep = float(np.mean([m for m, _ in sweep_ms]))
     local.set_profiling(False)
-    sweep = float(np.mean(sweep_ms))
     elem = 2 if args.dtype == "bf16" else 4
     shard_bytes = (hi - lo) * args.dim * elem
     flops = 2.0 * args.batch * (hi - lo) * args.dim
@@ -357,10 +357,9 @@ def main():
             continue
         qb = gen_queries(torch, 100 + b, b, args.dim).to(device)
         steps_b = 3 if b >= 1024 else 5
-        ms_b = timed(lambda i: step_device(i, qb), steps_b, 2) / steps_b
         local.set_profiling(True)
-        step_device(0, qb)
-        kms, _ = local.last_sweep_ms()
+        ms_b = timed(lambda i: step_device(i, qb), steps_b, 2) / steps_b
+        kms = float(np.mean([local.sweep_ms(i)[0] for i in range(steps_b)]))
         local.set_profiling(False)
         r = roofline_for(b, kms, 2.0 * b * (hi - lo) * args.dim)
         batch_sweep.append({"batch": b, "value": b / (ms_b / 1e3), "ms_per_step": ms_b, "kernel_ms": kms, "bound": r["bound"],

@@ -23,6 +23,7 @@ FLAG_FORCE_TC = 1 << 2
 FLAG_HOST_IO = 1 << 3
 FLAG_PRECISE_QUERY = 1 << 4
 FLAG_SCOPE_FULL = 1 << 5
+FLAG_NO_PAIR = 1 << 6
 
 
 class NativeUnavailable(ImportError):
@@ -51,7 +52,7 @@ SIGNATURES = {
     "dewi_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "dewi_index_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
     "dewi_index_set_profiling": (c_int, [c_void_p, c_int]),
-    "dewi_index_last_sweep_ms": (c_int, [c_void_p, POINTER(c_float), POINTER(c_int)]),
+    "dewi_index_sweep_ms": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]),
     "dewi_fit_stats": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p]),
     "dewi_score": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), c_int, c_void_p, c_int, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),

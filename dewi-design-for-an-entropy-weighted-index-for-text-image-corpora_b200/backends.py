@@ -486,14 +486,15 @@ class CudaIndex(BaseIndex):
         return n.value
 
     def set_profiling(self, enable: bool = True) -> None:
-        """Bracket the sweep kernel with CUDA events (see `last_sweep_ms`)."""
+        """Bracket every search's sweep kernel with CUDA events (see `sweep_ms`)."""
         _native.check(self._lib.dewi_index_set_profiling(self._h, int(bool(enable))))
 
-    def last_sweep_ms(self) -> Tuple[float, str]:
-        """Device time of the last search's sweep kernel and which one ran ("tcgen05" / "simt")."""
+    def sweep_ms(self, back: int = 0) -> Tuple[float, str]:
+        """Device time of the sweep kernel of the `back`-th most recent profiled search (0 = last) and
+        which sweep ran ("tcgen05" / "simt")."""
         ms, kind = ctypes.c_float(0), ctypes.c_int(0)
-        _native.check(self._lib.dewi_index_last_sweep_ms(self._h, ctypes.byref(ms), ctypes.byref(kind)))
-        return ms.value, {1: "tcgen05", 2: "simt"}.get(kind.value, "?")
+        _native.check(self._lib.dewi_index_sweep_ms(self._h, int(back), ctypes.byref(ms), ctypes.byref(kind)))
+        return ms.value, {1: "tcgen05", 2: "simt", 3: "tcgen05-pair"}.get(kind.value, "?")
 
     # ---- stored rows / persistence ---------------------------------------------------------------
     @property

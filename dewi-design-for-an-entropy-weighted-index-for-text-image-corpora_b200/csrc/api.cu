@@ -68,7 +68,9 @@ struct dewi_index {
   // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
   int profile = 0;
   int last_sweep_kind = 0;  // 1 = tcgen05 sweep, 2 = CUDA-core sweep
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  static constexpr int kEvRing = 64;
+  cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
+  long long searches = 0;  // sweeps bracketed since profiling was enabled
 };
 
 namespace {
@@ -197,8 +199,10 @@ int dewi_index_destroy(dewi_index_t* h) {
   cudaFree(h->dewi_col);
   cudaFree(h->ent_col);
   cudaFree(h->bad_flag);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < dewi_index::kEvRing; ++i) {
+    if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
+    if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
+  }
   for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->cand_idx, &h->cand_sim,
                     &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score})
     b->release();
@@ -306,8 +310,8 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   DEWI_TRY(set_device(h));
   h->last_launches = 0;
   const int dim = h->dim;
-  const int b_pad = static_cast<int>(round_up(B, kQueryBlock));
-  const int n_qb = b_pad / kQueryBlock;
+  int b_pad = static_cast<int>(round_up(B, kQueryBlock));
+  int n_qb = b_pad / kQueryBlock;
   const int kc_valid = static_cast<int>(std::min<int64_t>(kcand, h->n));
 
   bool use_tc = h->space == DEWI_SPACE_COSINE && h->plane0 && tc_supported(dim, h->n) && !(flags & DEWI_FLAG_FORCE_SIMT) &&
@@ -316,12 +320,24 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   // list capacity: over-fetch so that rounding in the bf16-plane sweep cannot push a true top-2k row out
   int kc = (mode == 0) ? std::max(32, kc_valid + 16) : kc_valid + 8;
   TcPlan plan;
-  if (use_tc) {
+  Tc2Plan plan2;
+  // more than one query block: the CTA-pair sweep (two query blocks share every corpus tile)
+  bool use_pair = use_tc && n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
+  if (use_pair) {
+    const int n_qb2 = static_cast<int>(round_up(n_qb, 2));
+    if (tc2_make_plan(mode, dim, h->n, n_qb2, kc, h->sm_count, &plan2) == 0) {
+      n_qb = n_qb2;
+      b_pad = n_qb * kQueryBlock;
+    } else {
+      use_pair = false;
+    }
+  }
+  if (use_tc && !use_pair) {
     if (tc_make_plan(mode, dim, h->n, n_qb, kc, h->sm_count, &plan) != 0) {
       if (flags & DEWI_FLAG_FORCE_TC) return 1;
       use_tc = false;
     }
-  } else if (flags & DEWI_FLAG_FORCE_TC) {
+  } else if (!use_tc && (flags & DEWI_FLAG_FORCE_TC)) {
     return fail("tcgen05 sweep not applicable (needs cosine space and dim % 64 == 0)");
   }
 
@@ -337,20 +353,26 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
   const int exact_is_bf16 = h->rows_f32 ? 0 : 1;
   Partials parts;
-  if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev0, stream));
-  h->last_sweep_kind = use_tc ? 1 : 2;
+  const int ev_slot = static_cast<int>(h->searches % dewi_index::kEvRing);
+  if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev0[ev_slot], stream));
+  h->last_sweep_kind = use_tc ? (use_pair ? 3 : 1) : 2;
   if (use_tc) {
-    DEWI_TRY(ensure_corpus_maps(h, plan.n_tile));
+    DEWI_TRY(ensure_corpus_maps(h, use_pair ? tc2_box_rows() : plan.n_tile));
     CUtensorMap mq0, mq1;
     DEWI_TRY(tc_encode_rows_map(&mq0, h->q0.p, b_pad, dim, kQueryBlock));
     DEWI_TRY(tc_encode_rows_map(&mq1, h->q1.p, b_pad, dim, kQueryBlock));
-    const size_t items = static_cast<size_t>(plan.n_chunks) * n_qb;
+    const int n_chunks = use_pair ? plan2.n_chunks : plan.n_chunks;
+    const size_t items = static_cast<size_t>(n_chunks) * n_qb;
     DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
     DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
-    DEWI_TRY(tc_launch(plan, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
-                       h->part_i.as<int>(), stream));
+    if (use_pair)
+      DEWI_TRY(tc2_launch(plan2, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
+                          h->part_i.as<int>(), stream));
+    else
+      DEWI_TRY(tc_launch(plan, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
+                         h->part_i.as<int>(), stream));
     h->last_launches++;
-    parts.n_chunks = plan.n_chunks;
+    parts.n_chunks = n_chunks;
   } else {
     kc = kc_valid;
     int n_chunks = 1;
@@ -363,7 +385,10 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
     h->last_launches++;
     parts.n_chunks = n_chunks;
   }
-  if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev1, stream));
+  if (h->profile) {
+    DEWI_CUDA(cudaEventRecord(h->ev1[ev_slot], stream));
+    h->searches++;
+  }
   parts.s = h->part_s.as<float>();
   parts.i = h->part_i.as<int>();
   parts.n_qb = n_qb;
@@ -448,20 +473,25 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
 int dewi_index_set_profiling(dewi_index_t* h, int enable) {
   if (!h) return fail("null handle");
   DEWI_TRY(set_device(h));
-  if (enable && !h->ev0) {
-    DEWI_CUDA(cudaEventCreate(&h->ev0));
-    DEWI_CUDA(cudaEventCreate(&h->ev1));
+  if (enable && !h->ev0[0]) {
+    for (int i = 0; i < dewi_index::kEvRing; ++i) {
+      DEWI_CUDA(cudaEventCreate(&h->ev0[i]));
+      DEWI_CUDA(cudaEventCreate(&h->ev1[i]));
+    }
   }
   h->profile = enable ? 1 : 0;
+  h->searches = 0;
   return 0;
 }
 
-int dewi_index_last_sweep_ms(dewi_index_t* h, float* ms, int* kind) {
+int dewi_index_sweep_ms(dewi_index_t* h, int back, float* ms, int* kind) {
   if (!h || !ms) return fail("null argument");
-  if (!h->profile || !h->ev0) return fail("profiling is not enabled on this handle");
+  if (!h->ev0[0]) return fail("profiling was never enabled on this handle");
+  if (back < 0 || back >= dewi_index::kEvRing || back >= h->searches) return fail("no such profiled search");
   DEWI_TRY(set_device(h));
-  DEWI_CUDA(cudaEventSynchronize(h->ev1));
-  DEWI_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  const int slot = static_cast<int>((h->searches - 1 - back) % dewi_index::kEvRing);
+  DEWI_CUDA(cudaEventSynchronize(h->ev1[slot]));
+  DEWI_CUDA(cudaEventElapsedTime(ms, h->ev0[slot], h->ev1[slot]));
   if (kind) *kind = h->last_sweep_kind;
   return 0;
 }

@@ -61,6 +61,21 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
               cudaStream_t stream);
 
+// ---- tcgen05 sweep on CTA pairs, for more than one query block (search_tc2.cu) -----------------
+struct Tc2Plan {
+  int mode;
+  int n_stages;
+  int q_stages;
+  int n_chunks;
+  int grid;
+  size_t smem_bytes;
+};
+int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan);
+int tc2_box_rows();
+int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
+               cudaStream_t stream);
+
 // ---- CUDA-core exact sweep (search_simt.cu) --------------------------------------------------
 int simt_plan(int64_t n_rows, int B, int sm_count, int* n_chunks);
 int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, int space, const float* qn, int B, int kc,

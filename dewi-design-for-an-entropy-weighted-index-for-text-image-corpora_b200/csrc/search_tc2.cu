@@ -1,0 +1,319 @@
+// K1b -- the similarity sweep for large query batches on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Same contract as search_tc.cu (reference src/dewi/backends.py:431-447 fused on chip), for B > 128
+// where the contraction is tensor-bound and the ceiling of the 1-CTA kernel is L2 -> shared-memory
+// operand traffic (48 KB per 128x256x64 MMA block).  Two CTAs of a cluster issue ONE
+// tcgen05.mma.cta_group::2 with M = 256 (two 128-query blocks, one per CTA) x N = 256 corpus rows:
+// each CTA stages its own query block and only HALF of the corpus tile (128 rows), the tensor core
+// reads the other half from the peer's shared memory.  Per CTA that is 32 KB of operands per
+// 128x256x64 block of work -- 1.5x less L2 traffic per flop -- and the corpus tile is fetched once
+// per pair instead of once per CTA.
+//
+// Roles per CTA (224 threads): w0 corpus-ring TMA producer (own half tile), w6 query-ring TMA producer
+// (own query block), w1 MMA issuer (leader CTA only) + TMEM allocation, w2-5 epilogue over the CTA's
+// own 128 TMEM lanes (identical to the 1-CTA kernel: sweep_epilogue.cuh).
+// Barriers: "full" barriers live in the leader (both CTAs' TMA transactions are accounted there);
+// "empty" and "accumulator full" are signalled in both CTAs by a multicast tcgen05.commit;
+// "accumulator empty" collects 8 epilogue-warp arrivals (4 local + 4 remote) in the leader.
+#include <algorithm>
+
+#include "internal.h"
+#include "ptx.cuh"
+#include "sweep_epilogue.cuh"
+
+namespace dewi {
+namespace {
+
+using namespace sweep;
+
+constexpr int kThreads = 224;
+constexpr int kQWarp = 6;
+constexpr int kNTile = 256;           // corpus rows per MMA (N); each CTA stages kNTile / 2
+constexpr int kHalfRows = kNTile / 2;
+
+struct Tc2Args {
+  int n_rows;
+  int n_tiles;
+  int n_kb;
+  int n_qpairs;   // query-block pairs
+  int n_chunks;
+  int n_items;    // n_chunks * n_qpairs, dealt to clusters
+  int kc;
+  int e_stages;
+  int q_stages;
+  float* part_s;  // [chunk][qb][kc][128]
+  int* part_i;
+};
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
+                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
+                  const Tc2Args a) {
+  using T = ModeTraits<MODE>;
+  constexpr uint32_t kEPlaneBytes = kHalfRows * 128;   // this CTA's half of a corpus k-block
+  constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
+  constexpr uint32_t kEStageBytes = T::PE * kEPlaneBytes;
+  constexpr uint32_t kQStageBytes = T::PQ * kQPlaneBytes;
+  constexpr uint32_t kTmemCols = 2 * kNTile;
+  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(2 * kQueryBlock, kNTile);
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring_e = smem;
+  uint8_t* ring_q = ring_e + static_cast<size_t>(a.e_stages) * kEStageBytes;
+  const int kl = a.kc + kPending;
+  float* list_s = reinterpret_cast<float*>(ring_q + static_cast<size_t>(a.q_stages) * kQStageBytes);
+  int* list_i = reinterpret_cast<int*>(list_s + kl * kQueryBlock);
+  uint64_t* bar_e_full = reinterpret_cast<uint64_t*>(list_i + kl * kQueryBlock);
+  uint64_t* bar_e_empty = bar_e_full + kMaxStages;
+  uint64_t* bar_q_full = bar_e_empty + kMaxStages;
+  uint64_t* bar_q_empty = bar_q_full + kQStagesMax;
+  uint64_t* bar_acc_full = bar_q_empty + kQStagesMax;
+  uint64_t* bar_acc_empty = bar_acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&map_e0);
+    ptx::prefetch_tmap(&map_q0);
+    if (T::PE > 1) ptx::prefetch_tmap(&map_e1);
+    if (T::PQ > 1) ptx::prefetch_tmap(&map_q1);
+    for (int s = 0; s < a.e_stages; ++s) {
+      ptx::mbar_init(&bar_e_full[s], 2);   // one producer arrival per CTA of the pair
+      ptx::mbar_init(&bar_e_empty[s], 1);
+    }
+    for (int s = 0; s < a.q_stages; ++s) {
+      ptx::mbar_init(&bar_q_full[s], 2);
+      ptx::mbar_init(&bar_q_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&bar_acc_full[b], 1);
+      ptx::mbar_init(&bar_acc_empty[b], 8);  // 4 epilogue warps x 2 CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // barrier inits and TMEM allocation visible to the peer before any remote arrive
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: this CTA's half of each corpus k-block =====================
+    if (lane == 0) {
+      int se = 0;
+      uint32_t pe = 0;
+      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+        int t0, t1;
+        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          const int row0 = t * kNTile + static_cast<int>(rank) * kHalfRows;
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_e_empty[se], pe ^ 1);
+            uint8_t* st = ring_e + static_cast<size_t>(se) * kEStageBytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_e_full[se], 2 * kEStageBytes);
+            else ptx::mbar_arrive_leader(&bar_e_full[se]);
+            ptx::tma_load_2d_pair(st, &map_e0, &bar_e_full[se], kb * kKBlock, row0, ptx::kEvictFirst);
+            if (T::PE > 1)
+              ptx::tma_load_2d_pair(st + kEPlaneBytes, &map_e1, &bar_e_full[se], kb * kKBlock, row0, ptx::kEvictFirst);
+            if (++se == a.e_stages) { se = 0; pe ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == kQWarp) {
+    // ===================== TMA producer: this CTA's query block =====================
+    if (lane == 0) {
+      int sq = 0;
+      uint32_t pq = 0;
+      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+        const int qb = (item % a.n_qpairs) * 2 + static_cast<int>(rank);
+        int t0, t1;
+        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_q_empty[sq], pq ^ 1);
+            uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_q_full[sq], 2 * kQStageBytes);
+            else ptx::mbar_arrive_leader(&bar_q_full[sq]);
+            ptx::tma_load_2d_pair(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+            if (T::PQ > 1)
+              ptx::tma_load_2d_pair(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
+                                    ptx::kEvictLast);
+            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, one thread, on behalf of the pair) =====================
+    if (rank == 0 && lane == 0) {
+      int se = 0, sq = 0;
+      uint32_t pe = 0, pq = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+        int t0, t1;
+        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
+        for (int t = t0; t < t1; ++t) {
+          ptx::mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
+          ptx::tc_fence_after();
+          const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kNTile);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            ptx::mbar_wait(&bar_q_full[sq], pq);
+            ptx::mbar_wait(&bar_e_full[se], pe);
+            ptx::tc_fence_after();
+            const uint32_t ste = ptx::smem_u32(ring_e + static_cast<size_t>(se) * kEStageBytes);
+            const uint32_t stq = ptx::smem_u32(ring_q + static_cast<size_t>(sq) * kQStageBytes);
+            const uint64_t de0 = ptx::make_desc_sw128(ste);
+            const uint64_t de1 = ptx::make_desc_sw128(ste + kEPlaneBytes);
+            const uint64_t dq0 = ptx::make_desc_sw128(stq);
+            const uint64_t dq1 = ptx::make_desc_sw128(stq + kQPlaneBytes);
+#pragma unroll
+            for (int k = 0; k < kKBlock / 16; ++k) {
+              const uint64_t adv = static_cast<uint64_t>(k * 2);
+              ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              if (MODE >= 1) ptx::mma_bf16_ss_pair(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
+              if (MODE == 2) ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+            }
+            ptx::mma_commit_pair(&bar_e_empty[se], 3);  // frees the slot in both CTAs
+            ptx::mma_commit_pair(&bar_q_empty[sq], 3);
+            if (kb == a.n_kb - 1) ptx::mma_commit_pair(&bar_acc_full[acc], 3);
+            if (++se == a.e_stages) { se = 0; pe ^= 1; }
+            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: this CTA's 128 queries =====================
+    const int quarter = warp & 3;
+    const int qlane = quarter * 32 + lane;
+    const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const int kc = a.kc;
+    const int n_qb = a.n_qpairs * 2;
+    LaneList l;
+    l.s = list_s + qlane;
+    l.i = list_i + qlane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+      const int chunk = item / a.n_qpairs;
+      const int qb = (item % a.n_qpairs) * 2 + static_cast<int>(rank);
+      int t0, t1;
+      tile_range(chunk, a.n_chunks, a.n_tiles, t0, t1);
+      l.cnt = 0;
+      l.thr = -INFINITY;
+      for (int t = t0; t < t1; ++t) {
+        ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
+        ptx::tc_fence_after();
+        scan_tile<kNTile>(l, kc, tmem_lane + static_cast<uint32_t>(acc * kNTile), t * kNTile, a.n_rows);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_leader(&bar_acc_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+      const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
+      flush_item(l, kc, a.part_s + slot, a.part_i + slot);
+    }
+  }
+
+  // Neither CTA may leave while the pair's MMAs can still read its shared memory or while remote
+  // arrivals are in flight.
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
+size_t e_stage_bytes(int mode) { return static_cast<size_t>((mode == 2) ? 2 : 1) * kHalfRows * 128; }
+size_t q_stage_bytes(int mode) { return static_cast<size_t>((mode == 0) ? 1 : 2) * kQueryBlock * 128; }
+size_t fixed_bytes(int kc) {
+  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
+         1024 /*alignment slack*/;
+}
+
+template <int MODE>
+int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+               const CUtensorMap& q1, const Tc2Args& args, cudaStream_t stream) {
+  auto kern = search_tc2_kernel<MODE>;
+  DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
+  kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan) {
+  if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
+  if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
+  const size_t smem_max = 227 * 1024;
+  const size_t fixed = fixed_bytes(kc);
+  const int q_stages = 3;
+  const size_t used = fixed + q_stages * q_stage_bytes(mode);
+  int stages = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode)) : 0;
+  if (stages < 3) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
+  stages = std::min(stages, kMaxStages);
+  const int64_t n_tiles = ceil_div(n_rows, kNTile);
+  const int n_qpairs = n_qb / 2;
+  const int max_clusters = std::max(1, sm_count / 2);
+  const int clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_tiles * n_qpairs));
+  // chunks x query-pairs work items, dealt round-robin to the clusters: choose the chunk count so that
+  // the item count is a multiple of the cluster count (equal work) when the corpus is long enough
+  const int64_t want = ceil_div(static_cast<int64_t>(clusters), n_qpairs);
+  int64_t chunks = want;
+  for (int64_t c = want; c <= want + clusters && c <= n_tiles; ++c) {
+    if ((c * n_qpairs) % clusters == 0) { chunks = c; break; }
+  }
+  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
+  plan->mode = mode;
+  plan->n_stages = stages;
+  plan->q_stages = q_stages;
+  plan->n_chunks = static_cast<int>(chunks);
+  plan->grid = 2 * static_cast<int>(std::min<int64_t>(clusters, chunks * n_qpairs));
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode) + q_stages * q_stage_bytes(mode);
+  return 0;
+}
+
+int tc2_box_rows() { return kHalfRows; }
+
+int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
+               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
+               cudaStream_t stream) {
+  Tc2Args a;
+  a.n_rows = static_cast<int>(n_rows);
+  a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
+  a.n_kb = dim / kKBlock;
+  a.n_qpairs = n_qb / 2;
+  a.n_chunks = plan.n_chunks;
+  a.n_items = plan.n_chunks * a.n_qpairs;
+  a.kc = kc;
+  a.e_stages = plan.n_stages;
+  a.q_stages = plan.q_stages;
+  a.part_s = part_s;
+  a.part_i = part_i;
+  if (plan.mode == 0) return launch_one<0>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1) return launch_one<1>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 2) return launch_one<2>(plan, e0, e1, q0, q1, a, stream);
+  return fail("unsupported CTA-pair sweep configuration");
+}
+
+}  // namespace dewi

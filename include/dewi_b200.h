@@ -51,7 +51,8 @@ enum {
   DEWI_FLAG_FORCE_TC = 1 << 2,         /* fail instead of falling back to the CUDA-core sweep      */
   DEWI_FLAG_HOST_IO = 1 << 3,          /* queries / outputs are HOST pointers (copies inside call) */
   DEWI_FLAG_PRECISE_QUERY = 1 << 4,    /* bf16 corpus: hi+lo query planes (2 MMAs) not 1 + rescore */
-  DEWI_FLAG_SCOPE_FULL = 1 << 5        /* (non-reference) blend over the whole corpus; unsupported */
+  DEWI_FLAG_SCOPE_FULL = 1 << 5,       /* (non-reference) blend over the whole corpus; unsupported */
+  DEWI_FLAG_NO_PAIR = 1 << 6           /* B > 128: keep the 1-CTA sweep instead of the CTA-pair one  */
 };
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -105,11 +106,12 @@ DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int
 /* Kernel launches issued by the last search on this handle (bench.py's `gpu_launches`). */
 DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
 
-/* Measurement aid: when enabled, searches bracket the sweep kernel (stage 1's dominant launch) with
- * CUDA events on the caller's stream; last_sweep_ms waits for the last one and returns its device
- * time and which sweep ran (1 = tcgen05 tensor-core sweep, 2 = CUDA-core sweep).               */
+/* Measurement aid: while enabled, every search brackets its sweep kernel (stage 1's dominant launch)
+ * with a CUDA event pair on the caller's stream, kept in a ring of 64 (no synchronisation is added to
+ * the search).  sweep_ms waits for the `back`-th most recent bracket (0 = last) and returns its device
+ * time and which sweep ran (1 = tcgen05 sweep, 2 = CUDA-core sweep, 3 = tcgen05 CTA-pair sweep).                    */
 DEWI_API int dewi_index_set_profiling(dewi_index_t* h, int enable);
-DEWI_API int dewi_index_last_sweep_ms(dewi_index_t* h, float* ms, int* kind);
+DEWI_API int dewi_index_sweep_ms(dewi_index_t* h, int back, float* ms, int* kind);
 
 /* ---- scorer: replaces RobustStats.fit and DewiScorer.score (scorer.py:18-31,49-89) ---------- */
 /* Median and MAD of `f` fp32 columns of `n` values each (column c starts at cols + c*ld).

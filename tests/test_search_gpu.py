@@ -234,3 +234,25 @@ def test_virtual_shards_merge_equals_single_index(n_shards):
     rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), queries.cpu().numpy(), k, 0.3, 0.5, True)
     for q in range(b):
         check_topk(rid[q], rsc[q], out_ids[q].cpu().numpy(), out_sc[q].cpu().numpy(), what=f"S{n_shards} q{q}")
+
+
+@pytest.mark.parametrize("dtype,b", [("fp32", 300), ("bf16", 1024), ("bf16", 129)])
+def test_cta_pair_sweep_matches_single_cta_sweep_and_oracle(dtype, b):
+    """B > 128 runs the cta_group::2 sweep (two query blocks per corpus tile); DEWI_FLAG_NO_PAIR keeps
+    the 1-CTA sweep.  Both must agree with each other and with the oracle."""
+    n, d, k = 70_001, 256, 10
+    emb, pay = make_corpus(n, d, seed=55)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    queries = np.random.RandomState(56).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    ids2, sc2 = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    ids1, sc1 = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_NO_PAIR)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries[:64], k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for q in range(64):
+            check_topk(rid[q], rsc[q], ids2[q], sc2[q], what=f"pair q{q}")
+            check_topk(rid[q], rsc[q], ids1[q], sc1[q], what=f"single q{q}")
+        assert (ids1 == ids2).mean() > 0.999
+    else:
+        assert recall_at_k(rid, ids2[:64]) >= 0.999 and recall_at_k(rid, ids1[:64]) >= 0.999
+        assert recall_at_k(ids1, ids2) >= 0.999
