@@ -106,7 +106,7 @@ def run_c4(args, torch, dewi_b200, peaks):
 
 
 def run_c5(args, torch, dewi_b200, peaks):
-    n, d, tau = args.rows or 100_000, 512, 0.9
+    n, d, tau = args.rows or 1_000_000, 512, 0.9
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(44)
@@ -114,20 +114,29 @@ def run_c5(args, torch, dewi_b200, peaks):
     dup = torch.randperm(n, generator=g, device=dev)[: n // 100]  # planted 1 % near-duplicates
     src = torch.randperm(n, generator=g, device=dev)[: n // 100]
     x[dup] = x[src] + 0.05 * torch.randn((n // 100, d), generator=g, device=dev)
-    res = {}
+    runs = []
+    for precision, rows in (("bf16", n), ("fp32", max(n // 4, 1))):
+        res = {}
+        xs = x[:rows]
 
-    def go():
-        res["out"] = dewi_b200.redundancy_join(x, tau=tau, pair_cap=1 << 22)
+        def go():
+            res["out"] = dewi_b200.redundancy_join(xs, tau=tau, pair_cap=1 << 22, precision=precision)
 
-    ms = timed(torch, go, 2, 1)
-    flops = float(n) * (n - 1) * d  # symmetric self-join: N(N-1)/2 pairs x 2D flops
-    ach = flops / (ms / 1e3) / 1e12
+        ms = timed(torch, go, 2, 1)
+        # algorithmic work of a symmetric self-join: N(N-1)/2 pair-dots of 2D flops each; the kernel evaluates
+        # the full N x N product (row statistics need every row's whole neighbourhood), i.e. twice that
+        alg = float(rows) * (rows - 1) * d
+        runs.append({"precision": precision, "rows": rows, "ms": ms, "pairs_found": res["out"]["n_pairs"],
+                     "pair_dots_per_s": rows * (rows - 1) / 2 / (ms / 1e3), "algorithmic_tflops": alg / (ms / 1e3) / 1e12,
+                     "executed_tflops": 2 * alg / (ms / 1e3) / 1e12})
+    main = runs[0]
     return {
-        "metric": "pair-dots/sec (redundancy self-join, cosine threshold)", "unit": "pairs/s", "dtype": "f32",
-        "value": n * (n - 1) / 2 / (ms / 1e3), "ms": ms, "pairs_found": res["out"]["n_pairs"],
-        "config": {"workload": f"C5 (bounded): {n} x {d} self-join, tau={tau}, 1 B200"},
-        "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": ach / peaks["bf16_sustained"]},
+        "metric": "pair-dots/sec (redundancy self-join, cosine threshold)", "unit": "pairs/s", "dtype": "bf16 planes, f32 accumulate",
+        "value": main["pair_dots_per_s"], "runs": runs,
+        "config": {"workload": f"C5 (bounded): {n} x {d} self-join, tau={tau}, 1 B200 (full size is 10M rows over 8 GPUs)"},
+        "roofline": {"bound": "tensor", "achieved": main["algorithmic_tflops"], "peak": peaks["bf16_sustained"],
+                     "unit": "TFLOP/s", "frac": main["algorithmic_tflops"] / peaks["bf16_sustained"],
+                     "executed_frac": main["executed_tflops"] / peaks["bf16_sustained"]},
     }
 
 

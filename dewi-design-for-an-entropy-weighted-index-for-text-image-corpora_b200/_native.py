@@ -24,6 +24,9 @@ FLAG_HOST_IO = 1 << 3
 FLAG_PRECISE_QUERY = 1 << 4
 FLAG_SCOPE_FULL = 1 << 5
 FLAG_NO_PAIR = 1 << 6
+JOIN_BF16 = 1 << 0
+JOIN_FORCE_SIMT = 1 << 1
+JOIN_FORCE_TC = 1 << 2
 
 
 class NativeUnavailable(ImportError):
@@ -56,7 +59,7 @@ SIGNATURES = {
     "dewi_fit_stats": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p]),
     "dewi_score": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), c_int, c_void_p, c_int, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
-    "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
+    "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
 }
 
 _lib = None

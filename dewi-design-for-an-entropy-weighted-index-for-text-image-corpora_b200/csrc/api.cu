@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "internal.h"
@@ -146,17 +147,37 @@ int dewi_abi_version(void) { return DEWI_B200_ABI_VERSION; }
 const char* dewi_last_error(void) { return g_last_error.c_str(); }
 
 int dewi_device_check(int device, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count <= 0)
-    return fail(std::string("no CUDA device available: ") + cudaGetErrorString(e) + " -- this library has no CPU fallback");
-  if (device < 0 || device >= count) return fail("device ordinal out of range");
-  cudaDeviceProp prop;
-  DEWI_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10)
-    return fail(std::string("device '") + prop.name + "' is compute capability " + std::to_string(prop.major) + "." +
-                std::to_string(prop.minor) + "; libdewi_b200 is built for sm_100a (B200) only");
-  if (sm_count) *sm_count = prop.multiProcessorCount;
+  // cudaGetDeviceProperties costs milliseconds: look each device up once
+  static std::mutex mu;
+  static int n_devices = -1;
+  static int cc_major[64], cc_minor[64], sms[64];
+  static char names[64][96];
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (n_devices < 0) {
+      int count = 0;
+      cudaError_t e = cudaGetDeviceCount(&count);
+      if (e != cudaSuccess || count <= 0)
+        return fail(std::string("no CUDA device available: ") + cudaGetErrorString(e) +
+                    " -- this library has no CPU fallback");
+      count = std::min(count, 64);
+      for (int d = 0; d < count; ++d) {
+        cudaDeviceProp prop;
+        DEWI_CUDA(cudaGetDeviceProperties(&prop, d));
+        cc_major[d] = prop.major;
+        cc_minor[d] = prop.minor;
+        sms[d] = prop.multiProcessorCount;
+        strncpy(names[d], prop.name, sizeof(names[d]) - 1);
+        names[d][sizeof(names[d]) - 1] = 0;
+      }
+      n_devices = count;
+    }
+  }
+  if (device < 0 || device >= n_devices) return fail("device ordinal out of range");
+  if (cc_major[device] != 10)
+    return fail(std::string("device '") + names[device] + "' is compute capability " + std::to_string(cc_major[device]) +
+                "." + std::to_string(cc_minor[device]) + "; libdewi_b200 is built for sm_100a (B200) only");
+  if (sm_count) *sm_count = sms[device];
   if (free_bytes || total_bytes) {
     size_t f = 0, t = 0;
     DEWI_CUDA(cudaSetDevice(device));

@@ -175,18 +175,94 @@ extern "C" int dewi_similarity_dense(const float* a, int64_t m, const float* b, 
   return rc;
 }
 
-extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
+namespace dewi {
+namespace {
+
+struct JoinBufs {
+  void* p[8] = {};
+  ~JoinBufs() {
+    for (void* q : p) cudaFree(q);
+  }
+};
+
+// Tensor-core path: rows normalised into bf16 planes, A on the query side of the CTA-pair sweep.
+int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int bf16_only,
+                float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
+                float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream) {
+  int sms = 0;
+  DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
+  const int64_t m_pad = round_up(m, 2 * kQueryBlock);
+  const size_t plane_a = static_cast<size_t>(m_pad) * d * 2, plane_b = static_cast<size_t>(n) * d * 2;
+  JoinBufs w;
+  __nv_bfloat16 *a_hi, *a_lo = nullptr, *b_hi, *b_lo = nullptr;
+  DEWI_CUDA(cudaMalloc(&w.p[0], plane_a));
+  a_hi = static_cast<__nv_bfloat16*>(w.p[0]);
+  if (!bf16_only) {
+    DEWI_CUDA(cudaMalloc(&w.p[1], plane_a));
+    a_lo = static_cast<__nv_bfloat16*>(w.p[1]);
+  }
+  DEWI_TRY(launch_prep_queries(a, static_cast<int>(m), static_cast<int>(m_pad), d, 1, nullptr, a_hi, a_lo, stream));
+  if (self_join) {
+    b_hi = a_hi;
+    b_lo = a_lo;
+  } else {
+    DEWI_CUDA(cudaMalloc(&w.p[2], plane_b));
+    b_hi = static_cast<__nv_bfloat16*>(w.p[2]);
+    if (!bf16_only) {
+      DEWI_CUDA(cudaMalloc(&w.p[3], plane_b));
+      b_lo = static_cast<__nv_bfloat16*>(w.p[3]);
+    }
+    DEWI_TRY(launch_prep_queries(b, static_cast<int>(n), static_cast<int>(n), d, 1, nullptr, b_hi, b_lo, stream));
+  }
+  DEWI_CUDA(cudaMalloc(&w.p[4], static_cast<size_t>(m) * 8));
+  DEWI_CUDA(cudaMalloc(&w.p[5], 8));
+  unsigned long long* best = static_cast<unsigned long long*>(w.p[4]);
+  unsigned long long* count = static_cast<unsigned long long*>(w.p[5]);
+  DEWI_CUDA(cudaMemsetAsync(best, 0, static_cast<size_t>(m) * 8, stream));
+  DEWI_CUDA(cudaMemsetAsync(count, 0, 8, stream));
+  DEWI_CUDA(cudaMemsetAsync(row_count, 0, static_cast<size_t>(m) * 4, stream));
+  CUtensorMap ma0, ma1, mb0, mb1;
+  DEWI_TRY(tc_encode_rows_map(&ma0, a_hi, m_pad, d, kQueryBlock));
+  DEWI_TRY(tc_encode_rows_map(&mb0, b_hi, n, d, tc2_box_rows()));
+  ma1 = ma0;
+  mb1 = mb0;
+  if (!bf16_only) {
+    DEWI_TRY(tc_encode_rows_map(&ma1, a_lo, m_pad, d, kQueryBlock));
+    DEWI_TRY(tc_encode_rows_map(&mb1, b_lo, n, d, tc2_box_rows()));
+  }
+  DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, ma0, ma1, m, m_pad, n, d, sms, tau, self_join, best, row_count,
+                           pair_i, pair_j, pair_sim, pair_cap, count, stream));
+  join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
+                                                                             reinterpret_cast<long long*>(row_argmax));
+  DEWI_CUDA(cudaGetLastError());
+  unsigned long long cnt = 0;
+  DEWI_CUDA(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, stream));
+  DEWI_CUDA(cudaStreamSynchronize(stream));
+  *pair_count_host = static_cast<int64_t>(cnt);
+  return 0;
+}
+
+}  // namespace
+}  // namespace dewi
+
+extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int flags,
                          float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
                          float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
   if (!a || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
   if (self_join) { b = a; n = m; }
   if (!b) return fail("null argument");
   if (m <= 0 || n <= 0 || d <= 0) return fail("join needs positive sizes");
-  if (n >= (int64_t(1) << 32)) return fail("join supports fewer than 2^32 columns");
+  if (n >= (int64_t(1) << 31) || m >= (int64_t(1) << 31)) return fail("join supports fewer than 2^31 rows per side");
   if (pair_cap > 0 && (!pair_i || !pair_j || !pair_sim)) return fail("pair buffers missing");
   DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
   DEWI_CUDA(cudaSetDevice(device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool tensor_ok = tc_supported(d, n) && !(flags & DEWI_JOIN_FORCE_SIMT);
+  const bool big = static_cast<double>(m) * static_cast<double>(n) >= 4.0e6;
+  if (tensor_ok && (big || (flags & DEWI_JOIN_FORCE_TC)))
+    return join_tensor(a, m, b, n, d, tau, self_join, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_max, row_argmax, row_count,
+                       pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, stream);
+  if (flags & DEWI_JOIN_FORCE_TC) return fail("tensor-core join needs d % 64 == 0");
   float *an = nullptr, *bn = nullptr;
   unsigned long long *best = nullptr, *count = nullptr;
   int rc = 0;

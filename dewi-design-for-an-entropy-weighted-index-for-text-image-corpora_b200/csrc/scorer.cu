@@ -20,15 +20,25 @@ namespace {
 
 constexpr int kBins = 2048;
 constexpr int kMaxCols = 32;
+// windowed path (large n): sample -> key window around the target rank -> one full pass
+constexpr long long kWindowMinRows = 4ll << 20;  // below this the plain radix passes are cheap enough
+constexpr int kSampleRuns = 1024;                // evenly spaced runs of ...
+constexpr int kSampleRunLen = 1024;              // ... contiguous elements (coalesced)
+constexpr int kSample = kSampleRuns * kSampleRunLen;
+constexpr int kSampleMargin = 4096;              // +- sample ranks: 8 sigma of a 2^20 sample's median rank
 
 struct SelState {
-  // per column, per slot (two middle ranks)
+  // radix selection, per column, two rank slots
   unsigned int prefix[kMaxCols][2];
   unsigned long long rank[kMaxCols][2];
-  float value[kMaxCols][2];
+  int same[kMaxCols];  // both slots still share one prefix -> one histogram serves both
   float med[kMaxCols];
   float mad[kMaxCols];
-  int same[kMaxCols];  // both slots still share one prefix -> one histogram serves both
+  // windowed path
+  unsigned int lo[kMaxCols], hi[kMaxCols];  // inclusive key window
+  unsigned long long below[kMaxCols];       // keys < lo
+  unsigned int wcnt[kMaxCols];              // keys appended to the window buffer
+  int miss[kMaxCols];                       // window overflowed or does not hold the target ranks
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -46,44 +56,62 @@ __device__ __forceinline__ void pass_bits(int pass, int& shift, int& nbins, unsi
   else { shift = 0; nbins = 1024; himask = 0xFFFFFC00u; }
 }
 
-template <bool MAD>
+// Key sources.  RAW: fp32 column value; DEV: |v - med| in fp32 (scorer.py:24); KEYS: a buffer of keys.
+enum { SRC_RAW = 0, SRC_DEV = 1, SRC_KEYS = 2 };
+
+template <int SRC>
+__device__ __forceinline__ unsigned int load_key(const void* col, long long i, float med) {
+  if (SRC == SRC_KEYS) return __ldg(static_cast<const unsigned int*>(col) + i);
+  float v = __ldg(static_cast<const float*>(col) + i);
+  if (SRC == SRC_DEV) v = fabsf(__fsub_rn(v, med));
+  return orderable(v);
+}
+
+// Histogram of the current digit over the keys whose higher digits match a slot's prefix.  Real
+// signal columns put most keys into a handful of bins, so equal bins are combined inside the warp
+// (match.any) before the shared-memory atomic; one global atomic per non-empty bin at the end.
+template <int SRC>
 __global__ void __launch_bounds__(512)
-hist_kernel(const float* __restrict__ cols, long long n, long long ld, int pass, const SelState* __restrict__ st,
-            unsigned int* __restrict__ ghist) {
-  __shared__ unsigned int sh[2][kBins];
+hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* __restrict__ n_dev, long long ld, int pass,
+            const SelState* __restrict__ st, unsigned int* __restrict__ ghist) {
+  __shared__ unsigned int sh[2 * kBins];
   const int c = blockIdx.y;
   int shift, nbins;
   unsigned int himask;
   pass_bits(pass, shift, nbins, himask);
-  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) (&sh[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) sh[i] = 0u;
   __syncthreads();
   const unsigned int p0 = st->prefix[c][0] & himask, p1 = st->prefix[c][1] & himask;
   const bool same = st->same[c] != 0;
-  const float med = MAD ? st->med[c] : 0.f;
-  const float* col = cols + static_cast<size_t>(c) * ld;
+  const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
+  const long long n = n_dev ? static_cast<long long>(min(static_cast<long long>(n_dev[c]), n_host)) : n_host;
+  const char* col = static_cast<const char*>(src) + static_cast<size_t>(c) * ld * 4;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const unsigned int binmask = static_cast<unsigned int>(nbins - 1);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float v = __ldg(col + i);
-    if (MAD) v = fabsf(__fsub_rn(v, med));
-    const unsigned int key = orderable(v);
-    const unsigned int hi = key & himask;
-    const unsigned int bin = (key >> shift) & binmask;
-    if (hi == p0) atomicAdd(&sh[0][bin], 1u);
-    if (!same && hi == p1) atomicAdd(&sh[1][bin], 1u);
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n; base += stride) {
+    const long long i = base + threadIdx.x;  // whole warps iterate together (base is warp-uniform)
+    unsigned int tgt = 0xFFFFFFFFu;
+    if (i < n) {
+      const unsigned int key = load_key<SRC>(col, i, med);
+      const unsigned int hi = key & himask;
+      const unsigned int bin = (key >> shift) & binmask;
+      if (hi == p0) tgt = bin;
+      else if (!same && hi == p1) tgt = kBins + bin;
+    }
+    const unsigned int peers = __match_any_sync(0xffffffffu, tgt);
+    if (tgt != 0xFFFFFFFFu && (__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&sh[tgt], __popc(peers));
   }
   __syncthreads();
   unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) {
-    const unsigned int v = (&sh[0][0])[i];
+    const unsigned int v = sh[i];
     if (v) atomicAdd(&g[i], v);
   }
 }
 
 // One block per column: locate the bin holding each slot's rank, extend the prefix, clear the histogram.
-template <bool MAD>
 __global__ void __launch_bounds__(1024)
-pick_kernel(int pass, long long n, SelState* st, unsigned int* ghist) {
+pick_kernel(int pass, SelState* st, unsigned int* ghist) {
   __shared__ unsigned long long cum[kBins];
   __shared__ unsigned long long wsum[32];
   const int c = blockIdx.x;
@@ -140,23 +168,159 @@ pick_kernel(int pass, long long n, SelState* st, unsigned int* ghist) {
     for (int i = threadIdx.x; i < kBins; i += blockDim.x) g[i] = 0u;
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    if (was_same && st->prefix[c][0] != st->prefix[c][1]) st->same[c] = 0;
-    if (pass == 2) {
-      const float v0 = from_orderable(st->prefix[c][0]);
-      const float v1 = from_orderable(st->prefix[c][1]);
-      // np.median: mean of the middle element(s) in float32 -> (v0 + v1) / 2, or v0 when n is odd
-      const float m = (n & 1) ? v0 : __fmul_rn(__fadd_rn(v0, v1), 0.5f);
-      if (MAD) st->mad[c] = m; else st->med[c] = m;
-      // re-arm for the next statistic
-      const unsigned long long r0 = (n & 1) ? static_cast<unsigned long long>((n - 1) / 2) : static_cast<unsigned long long>(n / 2 - 1);
-      const unsigned long long r1 = (n & 1) ? r0 : static_cast<unsigned long long>(n / 2);
-      st->prefix[c][0] = st->prefix[c][1] = 0u;
-      st->rank[c][0] = r0;
-      st->rank[c][1] = r1;
-      st->same[c] = 1;
+  if (threadIdx.x == 0 && was_same && st->prefix[c][0] != st->prefix[c][1]) st->same[c] = 0;
+}
+
+// The two middle ranks of n sorted values (equal when n is odd): np.median averages them in fp32.
+__device__ __forceinline__ void middle_ranks(long long n, unsigned long long& r0, unsigned long long& r1) {
+  r0 = (n & 1) ? static_cast<unsigned long long>((n - 1) / 2) : static_cast<unsigned long long>(n / 2 - 1);
+  r1 = (n & 1) ? r0 : static_cast<unsigned long long>(n / 2);
+}
+
+// Glue between selection stages (one thread per column).
+//   ARM_FULL   : select the middle ranks of all n keys
+//   ARM_SAMPLE : select the window bounds in the sample: ranks s/2 -+ margin
+//   ARM_WINDOW : the sample selection just finished: prefix[] are the window bounds -> lo/hi
+//   ARM_INSIDE : the window pass just finished: select ranks (middle - below) inside the window
+//   FINAL_MED / FINAL_MAD : the selection of the middle ranks finished: prefix[] -> med / mad
+enum { ARM_FULL, ARM_SAMPLE, ARM_WINDOW, ARM_INSIDE, FINAL_MED, FINAL_MAD };
+
+__global__ void glue_kernel(int op, int f, long long n, unsigned int window_cap, SelState* st) {
+  const int c = threadIdx.x;
+  if (c >= f) return;
+  unsigned long long r0, r1;
+  middle_ranks(n, r0, r1);
+  if (op == ARM_FULL) {
+    st->prefix[c][0] = st->prefix[c][1] = 0u;
+    st->rank[c][0] = r0;
+    st->rank[c][1] = r1;
+    st->same[c] = 1;
+  } else if (op == ARM_SAMPLE) {
+    st->prefix[c][0] = st->prefix[c][1] = 0u;
+    st->rank[c][0] = kSample / 2 - kSampleMargin;
+    st->rank[c][1] = kSample / 2 + kSampleMargin;
+    st->same[c] = 1;
+  } else if (op == ARM_WINDOW) {
+    st->lo[c] = st->prefix[c][0];
+    st->hi[c] = st->prefix[c][1];
+    st->below[c] = 0ull;
+    st->wcnt[c] = 0u;
+  } else if (op == ARM_INSIDE) {
+    const unsigned long long below = st->below[c], cnt = st->wcnt[c];
+    const bool ok = cnt <= window_cap && below <= r0 && r1 < below + cnt;
+    if (!ok) st->miss[c] = 1;
+    st->prefix[c][0] = st->prefix[c][1] = 0u;
+    st->rank[c][0] = ok ? r0 - below : 0ull;
+    st->rank[c][1] = ok ? r1 - below : 0ull;
+    st->same[c] = 1;
+  } else {
+    const float v0 = from_orderable(st->prefix[c][0]);
+    const float v1 = from_orderable(st->prefix[c][1]);
+    // np.median: mean of the middle element(s) in float32 -> (v0 + v1) / 2, or v0 when n is odd
+    const float m = (n & 1) ? v0 : __fmul_rn(__fadd_rn(v0, v1), 0.5f);
+    if (op == FINAL_MED) st->med[c] = m; else st->mad[c] = m;
+  }
+}
+
+// Keys of kSampleRuns evenly spaced runs of kSampleRunLen contiguous elements -> skeys[c][kSample].
+template <int SRC>
+__global__ void __launch_bounds__(256)
+sample_kernel(const float* __restrict__ cols, long long n, long long ld, const SelState* __restrict__ st,
+              unsigned int* __restrict__ skeys) {
+  const int c = blockIdx.y;
+  const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
+  const float* col = cols + static_cast<size_t>(c) * ld;
+  for (int run = blockIdx.x; run < kSampleRuns; run += gridDim.x) {
+    const long long start = static_cast<long long>((static_cast<__int128>(run) * (n - kSampleRunLen)) / (kSampleRuns - 1));
+    for (int j = threadIdx.x; j < kSampleRunLen; j += blockDim.x)
+      skeys[static_cast<size_t>(c) * kSample + run * kSampleRunLen + j] = load_key<SRC>(col, start + j, med);
+  }
+}
+
+// THE full pass of the windowed path: count keys below the window, collect the keys inside it.
+// Appends go through a per-block shared buffer so that global atomics are one per flush.
+constexpr int kWinBuf = 4096;
+template <int SRC>
+__global__ void __launch_bounds__(512)
+window_kernel(const float* __restrict__ cols, long long n, long long ld, SelState* st, unsigned int* __restrict__ wkeys,
+              unsigned int window_cap) {
+  __shared__ unsigned int buf[kWinBuf];
+  __shared__ unsigned int buf_n, flush_base;
+  __shared__ unsigned long long below_blk;
+  const int c = blockIdx.y;
+  const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
+  const unsigned int lo = st->lo[c], hi = st->hi[c];
+  const float* col = cols + static_cast<size_t>(c) * ld;
+  unsigned int* out = wkeys + static_cast<size_t>(c) * window_cap;
+  if (threadIdx.x == 0) { buf_n = 0u; below_blk = 0ull; }
+  __syncthreads();
+  unsigned long long below = 0ull;
+  const long long per_iter = static_cast<long long>(blockDim.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * per_iter;
+  for (long long base = static_cast<long long>(blockIdx.x) * per_iter; base < n; base += stride) {
+    const long long i0 = base + static_cast<long long>(threadIdx.x) * 4;
+    float v[4];
+    int nv = 0;
+    if (i0 + 3 < n && ((reinterpret_cast<uintptr_t>(col + i0) & 15) == 0)) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(col + i0));
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+      nv = 4;
+    } else {
+      for (; nv < 4 && i0 + nv < n; ++nv) v[nv] = __ldg(col + i0 + nv);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bool inside = false;
+      unsigned int key = 0u;
+      if (j < nv) {
+        float x = v[j];
+        if (SRC == SRC_DEV) x = fabsf(__fsub_rn(x, med));
+        key = orderable(x);
+        below += (key < lo) ? 1ull : 0ull;
+        inside = key >= lo && key <= hi;
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, inside);
+      if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned int wbase = 0u;
+        if (lane == 0) wbase = atomicAdd(&buf_n, __popc(m));
+        wbase = __shfl_sync(0xffffffffu, wbase, 0);
+        if (inside) {
+          const unsigned int slot = wbase + __popc(m & ((1u << lane) - 1u));
+          if (slot < kWinBuf) buf[slot] = key;
+          else {  // shared buffer full: rare, go straight to global
+            const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
+            if (g < window_cap) out[g] = key;
+          }
+        }
+      }
+    }
+    // flush when the buffer could overflow in the next iteration (block-uniform decision)
+    __syncthreads();
+    if (buf_n > kWinBuf - 2048) {
+      const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
+      if (threadIdx.x == 0) flush_base = atomicAdd(&st->wcnt[c], cnt);
+      __syncthreads();
+      for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
+        if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
+      __syncthreads();
+      if (threadIdx.x == 0) buf_n = 0u;
+      __syncthreads();
     }
   }
+  // block totals
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+  if ((threadIdx.x & 31) == 0 && below) atomicAdd(&below_blk, below);
+  __syncthreads();
+  const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
+  if (threadIdx.x == 0) {
+    if (below_blk) atomicAdd(&st->below[c], below_blk);
+    flush_base = cnt ? atomicAdd(&st->wcnt[c], cnt) : 0u;
+  }
+  __syncthreads();
+  for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
+    if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
 }
 
 struct ScoreParams {
@@ -198,6 +362,57 @@ score_kernel(const InT* __restrict__ cols, long long n, long long ld, const Scor
   }
 }
 
+struct FitWork {
+  SelState* st = nullptr;
+  unsigned int* ghist = nullptr;
+  unsigned int* skeys = nullptr;
+  unsigned int* wkeys = nullptr;
+  ~FitWork() {
+    cudaFree(st);
+    cudaFree(ghist);
+    cudaFree(skeys);
+    cudaFree(wkeys);
+  }
+};
+
+template <int SRC>
+void select3(const void* src, long long n_host, const unsigned int* n_dev, long long ld, int f, SelState* st,
+             unsigned int* ghist, cudaStream_t stream) {
+  const int threads = 512;
+  int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * 8), std::max(1, 148 * 4 / f)));
+  dim3 grid(std::max(bx, 1), f);
+  for (int pass = 0; pass < 3; ++pass) {
+    hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist);
+    pick_kernel<<<f, 1024, 0, stream>>>(pass, st, ghist);
+  }
+}
+
+// Exact radix selection over the whole column: 3 full passes per statistic.
+void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, cudaStream_t stream) {
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_FULL, f, n, 0u, w.st);
+  select3<SRC_RAW>(cols, n, nullptr, ld, f, w.st, w.ghist, stream);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(FINAL_MED, f, n, 0u, w.st);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_FULL, f, n, 0u, w.st);
+  select3<SRC_DEV>(cols, n, nullptr, ld, f, w.st, w.ghist, stream);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(FINAL_MAD, f, n, 0u, w.st);
+}
+
+// One full pass per statistic: window bounds from a sample, keys inside the window collected, the
+// middle ranks selected among them.  st->miss[c] reports a window that did not hold the ranks.
+template <int SRC>
+void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsigned int cap, FitWork& w, int final_op,
+                       cudaStream_t stream) {
+  sample_kernel<SRC><<<dim3(64, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
+  select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, stream);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_WINDOW, f, n, cap, w.st);
+  const int bx = std::max(1, 148 * 4 / f);
+  window_kernel<SRC><<<dim3(bx, f), 512, 0, stream>>>(cols, n, ld, w.st, w.wkeys, cap);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_INSIDE, f, n, cap, w.st);
+  select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, stream);
+  glue_kernel<<<1, kMaxCols, 0, stream>>>(final_op, f, n, cap, w.st);
+}
+
 }  // namespace
 }  // namespace dewi
 
@@ -212,58 +427,41 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
   DEWI_CUDA(cudaSetDevice(device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SelState init;
-  memset(&init, 0, sizeof(init));
-  const unsigned long long r0 = (n & 1) ? (n - 1) / 2 : n / 2 - 1;
-  const unsigned long long r1 = (n & 1) ? r0 : n / 2;
-  for (int c = 0; c < f; ++c) {
-    init.rank[c][0] = r0;
-    init.rank[c][1] = r1;
-    init.same[c] = 1;
+  const bool windowed = n >= kWindowMinRows;
+  // expected window population is 2 * margin / sample = 0.8 % of n; allow twice that
+  const unsigned int cap = windowed ? static_cast<unsigned int>(std::min<int64_t>(n / 64 + 65536, 1ll << 30)) : 0u;
+  FitWork w;
+  DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
+  DEWI_CUDA(cudaMalloc(&w.ghist, static_cast<size_t>(f) * 2 * kBins * 4));
+  if (windowed) {
+    DEWI_CUDA(cudaMalloc(&w.skeys, static_cast<size_t>(f) * kSample * 4));
+    DEWI_CUDA(cudaMalloc(&w.wkeys, static_cast<size_t>(f) * cap * 4));
   }
-  SelState* st = nullptr;
-  unsigned int* ghist = nullptr;
-  DEWI_CUDA(cudaMalloc(&st, sizeof(SelState)));
-  DEWI_CUDA(cudaMalloc(&ghist, static_cast<size_t>(f) * 2 * kBins * 4));
-  int rc = 0;
-  do {
-    if (cudaMemcpyAsync(st, &init, sizeof(init), cudaMemcpyHostToDevice, stream) != cudaSuccess ||
-        cudaMemsetAsync(ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream) != cudaSuccess) {
-      rc = fail("fit_stats: state upload failed");
-      break;
-    }
-    const int threads = 512;
-    int bx = static_cast<int>(std::min<int64_t>(ceil_div(n, threads * 8), std::max(1, 148 * 4 / f)));
-    bx = std::max(bx, 1);
-    dim3 grid(bx, f);
-    for (int phase = 0; phase < 2 && rc == 0; ++phase) {
-      for (int pass = 0; pass < 3; ++pass) {
-        if (phase == 0) {
-          hist_kernel<false><<<grid, threads, 0, stream>>>(cols, n, ld, pass, st, ghist);
-          pick_kernel<false><<<f, 1024, 0, stream>>>(pass, n, st, ghist);
-        } else {
-          hist_kernel<true><<<grid, threads, 0, stream>>>(cols, n, ld, pass, st, ghist);
-          pick_kernel<true><<<f, 1024, 0, stream>>>(pass, n, st, ghist);
-        }
-      }
-      if (cudaGetLastError() != cudaSuccess) rc = fail("fit_stats: kernel launch failed");
-    }
-    if (rc) break;
-    SelState res;
-    if (cudaMemcpyAsync(&res, st, sizeof(res), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-        cudaStreamSynchronize(stream) != cudaSuccess) {
-      rc = fail(std::string("fit_stats: ") + cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
-    for (int c = 0; c < f; ++c) {
-      med_host[c] = static_cast<double>(res.med[c]);
-      const double m = static_cast<double>(res.mad[c]);
-      mad_host[c] = (m == 0.0) ? 1e-8 : m;  // scorer.py:24: `... or 1e-8`
-    }
-  } while (0);
-  cudaFree(st);
-  cudaFree(ghist);
-  return rc;
+  DEWI_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SelState), stream));
+  DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
+  SelState res;
+  bool need_full = !windowed;
+  if (windowed) {
+    fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
+    fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
+    DEWI_CUDA(cudaGetLastError());
+    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+    for (int c = 0; c < f; ++c) need_full = need_full || res.miss[c] != 0;  // e.g. a huge tie group at the median
+    if (need_full) DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
+  }
+  if (need_full) {
+    fit_full(cols, n, f, ld, w, stream);
+    DEWI_CUDA(cudaGetLastError());
+    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+  }
+  for (int c = 0; c < f; ++c) {
+    med_host[c] = static_cast<double>(res.med[c]);
+    const double m = static_cast<double>(res.mad[c]);
+    mad_host[c] = (m == 0.0) ? 1e-8 : m;  // scorer.py:24: `... or 1e-8`
+  }
+  return 0;
 }
 
 extern "C" int dewi_score(const void* cols, int in_f64, int64_t n, int64_t ld, const double* med7, const double* mad7,

@@ -43,9 +43,78 @@ struct Tc2Args {
   int q_stages;
   float* part_s;  // [chunk][qb][kc][128]
   int* part_i;
+  // EPI_JOIN: thresholded similarity join instead of candidate lists (dewi_join)
+  int m_rows;                      // rows of A (the "query" side); rows >= m_rows are padding
+  float tau;
+  int self_join;                   // exclude i == j, emit only pairs with j > i
+  unsigned long long* row_best;    // [m_rows] packed (orderable(sim) << 32 | ~j), atomicMax
+  int* row_count;                  // [m_rows] sims >= tau
+  long long* pair_i;
+  long long* pair_j;
+  float* pair_sim;
+  long long pair_cap;
+  unsigned long long* pair_count;
 };
 
-template <int MODE>
+enum { EPI_TOPK = 0, EPI_JOIN = 1 };
+
+__device__ __forceinline__ unsigned int orderable_u32(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Join epilogue state of one A row (TMEM lane): running best match and threshold count.
+struct JoinRow {
+  float best;
+  int best_j;
+  int count;
+};
+
+template <int N_TILE>
+__device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int i_row, uint32_t tcol, int col_base) {
+#pragma unroll 1
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    float v[32];
+    ptx::tmem_ld_32x32(tcol + c * 32, v);
+    const int j0 = col_base + c * 32;
+    if (j0 + 32 > a.n_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j0 + j >= a.n_rows) v[j] = -INFINITY;
+    }
+    if (a.self_join && i_row >= j0 && i_row < j0 + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j0 + j == i_row) v[j] = -INFINITY;  // the diagonal
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+    if (mx > r.best) {  // rare after the first tiles: the running maximum seldom improves
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (v[j] > r.best) { r.best = v[j]; r.best_j = j0 + j; }
+    }
+    if (mx >= a.tau && i_row < a.m_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (v[j] >= a.tau) {
+          ++r.count;
+          if (!a.self_join || j0 + j > i_row) {
+            const unsigned long long slot = atomicAdd(a.pair_count, 1ull);
+            if (static_cast<long long>(slot) < a.pair_cap) {
+              a.pair_i[slot] = i_row;
+              a.pair_j[slot] = j0 + j;
+              a.pair_sim[slot] = v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int MODE, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                   const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
@@ -218,18 +287,29 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       tile_range(chunk, a.n_chunks, a.n_tiles, t0, t1);
       l.cnt = 0;
       l.thr = -INFINITY;
+      JoinRow jr = {-INFINITY, -1, 0};
+      const int i_row = qb * kQueryBlock + qlane;
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
-        scan_tile<kNTile>(l, kc, tmem_lane + static_cast<uint32_t>(acc * kNTile), t * kNTile, a.n_rows);
+        const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * kNTile);
+        if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
+        else join_scan_tile<kNTile>(jr, a, i_row, tcol, t * kNTile);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(&bar_acc_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
-      flush_item(l, kc, a.part_s + slot, a.part_i + slot);
+      if (EPI == EPI_TOPK) {
+        const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
+        flush_item(l, kc, a.part_s + slot, a.part_i + slot);
+      } else if (i_row < a.m_rows) {
+        if (jr.best_j >= 0)
+          atomicMax(&a.row_best[i_row], (static_cast<unsigned long long>(orderable_u32(jr.best)) << 32) |
+                                            static_cast<unsigned int>(~static_cast<unsigned int>(jr.best_j)));
+        if (jr.count) atomicAdd(&a.row_count[i_row], jr.count);
+      }
     }
   }
 
@@ -250,10 +330,10 @@ size_t fixed_bytes(int kc) {
          1024 /*alignment slack*/;
 }
 
-template <int MODE>
+template <int MODE, int EPI>
 int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, const Tc2Args& args, cudaStream_t stream) {
-  auto kern = search_tc2_kernel<MODE>;
+  auto kern = search_tc2_kernel<MODE, EPI>;
   DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
   kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
   DEWI_CUDA(cudaGetLastError());
@@ -310,10 +390,56 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.q_stages = plan.q_stages;
   a.part_s = part_s;
   a.part_i = part_i;
-  if (plan.mode == 0) return launch_one<0>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 1) return launch_one<1>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 2) return launch_one<2>(plan, e0, e1, q0, q1, a, stream);
+  a.m_rows = 0;
+  a.tau = 0.f;
+  a.self_join = 0;
+  a.row_best = nullptr;
+  a.row_count = nullptr;
+  a.pair_i = a.pair_j = nullptr;
+  a.pair_sim = nullptr;
+  a.pair_cap = 0;
+  a.pair_count = nullptr;
+  if (plan.mode == 0) return launch_one<0, EPI_TOPK>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1) return launch_one<1, EPI_TOPK>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 2) return launch_one<2, EPI_TOPK>(plan, e0, e1, q0, q1, a, stream);
   return fail("unsupported CTA-pair sweep configuration");
+}
+
+// Thresholded join on the tensor cores: rows of A are the "queries" (128 per CTA, on TMEM lanes), rows of
+// B stream through as the "corpus".  mode 0 = single bf16 plane (sims carry bf16 rounding, ~1e-3),
+// mode 2 = hi/lo planes on both sides (three MMAs, ~1e-6).
+int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
+                    int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join,
+                    unsigned long long* row_best, int* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+                    int64_t pair_cap, unsigned long long* pair_count, cudaStream_t stream) {
+  Tc2Plan plan;
+  const int n_qb = static_cast<int>(m_pad / kQueryBlock);
+  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan));
+  Tc2Args a;
+  a.n_rows = static_cast<int>(n_rows);
+  a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
+  a.n_kb = dim / kKBlock;
+  a.n_qpairs = n_qb / 2;
+  a.n_chunks = plan.n_chunks;
+  a.n_items = plan.n_chunks * a.n_qpairs;
+  a.kc = 0;
+  a.e_stages = plan.n_stages;
+  a.q_stages = plan.q_stages;
+  a.part_s = nullptr;
+  a.part_i = nullptr;
+  a.m_rows = static_cast<int>(m_rows);
+  a.tau = tau;
+  a.self_join = self_join;
+  a.row_best = row_best;
+  a.row_count = row_count;
+  a.pair_i = reinterpret_cast<long long*>(pair_i);
+  a.pair_j = reinterpret_cast<long long*>(pair_j);
+  a.pair_sim = pair_sim;
+  a.pair_cap = pair_cap;
+  a.pair_count = pair_count;
+  if (mode == 0) return launch_one<0, EPI_JOIN>(plan, b0, b1, a0, a1, a, stream);
+  if (mode == 2) return launch_one<2, EPI_JOIN>(plan, b0, b1, a0, a1, a, stream);
+  return fail("unsupported join precision mode");
 }
 
 }  // namespace dewi

@@ -45,8 +45,13 @@ def cross_modal_similarity(tfeat, ifeat, device: Optional[int] = None):
     return out.cpu().numpy()  # the reference returns `.cpu().numpy()` (redundancy.py:38)
 
 
-def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device: Optional[int] = None):
+def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device: Optional[int] = None,
+                    precision: str = "fp32", force: Optional[str] = None):
     """Thresholded similarity join.  `b=None` is the self-join (diagonal excluded, pairs j > i).
+
+    precision "fp32": similarities good to ~1e-6 (bf16 hi+lo planes on the tensor cores, or the fp32
+    CUDA-core kernel for small inputs / d % 64 != 0); "bf16": one bf16 plane, ~1e-3, 3x fewer MMAs.
+    force: None | "simt" | "tc" pins the kernel (tests).
 
     Returns dict(max_sim [M] f32, argmax [M] i64, count [M] i32, pairs_i, pairs_j, pairs_sim, n_pairs)
     of CUDA tensors; `n_pairs` may exceed `pair_cap`, in which case only `pair_cap` pairs were kept."""
@@ -67,10 +72,12 @@ def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device
     pj = torch.empty(pair_cap, dtype=torch.int64, device=tdev)
     ps = torch.empty(pair_cap, dtype=torch.float32, device=tdev)
     cnt = ctypes.c_int64(0)
+    flags = (_native.JOIN_BF16 if precision in ("bf16", "bfloat16") else 0) | \
+        {None: 0, "simt": _native.JOIN_FORCE_SIMT, "tc": _native.JOIN_FORCE_TC}[force]
     lib = _native.load_library()
     with torch.cuda.device(dev):
         rc = lib.dewi_join(ctypes.c_void_p(ta.data_ptr()), m, ctypes.c_void_p(tb.data_ptr()), tb.shape[0], ta.shape[1],
-                           float(tau), int(self_join), ctypes.c_void_p(row_max.data_ptr()),
+                           float(tau), int(self_join), flags, ctypes.c_void_p(row_max.data_ptr()),
                            ctypes.c_void_p(row_arg.data_ptr()), ctypes.c_void_p(row_cnt.data_ptr()),
                            ctypes.c_void_p(pi.data_ptr()), ctypes.c_void_p(pj.data_ptr()), ctypes.c_void_p(ps.data_ptr()),
                            int(pair_cap), ctypes.byref(cnt), dev, _native.stream_ptr())
