@@ -11,6 +11,7 @@
 //   Python-float arithmetic; HBM-bound: 7 fp32 loads and one store per row.
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "internal.h"
@@ -238,10 +239,16 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, const S
 }
 
 // THE full pass of the windowed path: count keys below the window, collect the keys inside it.
-// Appends go through a per-block shared buffer so that global atomics are one per flush.
-constexpr int kWinBuf = 4096;
+// 16 elements per thread per iteration (four 128-bit loads in flight); window hits (~0.8 % of the
+// keys) go to a per-block shared buffer through one warp-aggregated shared atomic, flushed to the
+// global window with one global atomic every kFlushEvery iterations.
+constexpr int kWinBuf = 6144;
+constexpr int kWinThreads = 512;
+constexpr int kWinPerThread = 16;
+constexpr int kFlushEvery = 8;
+
 template <int SRC>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kWinThreads)
 window_kernel(const float* __restrict__ cols, long long n, long long ld, SelState* st, unsigned int* __restrict__ wkeys,
               unsigned int window_cap) {
   __shared__ unsigned int buf[kWinBuf];
@@ -252,80 +259,94 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, SelStat
   const unsigned int lo = st->lo[c], hi = st->hi[c];
   const float* col = cols + static_cast<size_t>(c) * ld;
   unsigned int* out = wkeys + static_cast<size_t>(c) * window_cap;
+  const int lane = threadIdx.x & 31;
+  const bool aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
   if (threadIdx.x == 0) { buf_n = 0u; below_blk = 0ull; }
   __syncthreads();
-  unsigned long long below = 0ull;
-  const long long per_iter = static_cast<long long>(blockDim.x) * 4;
-  const long long stride = static_cast<long long>(gridDim.x) * per_iter;
-  for (long long base = static_cast<long long>(blockIdx.x) * per_iter; base < n; base += stride) {
-    const long long i0 = base + static_cast<long long>(threadIdx.x) * 4;
-    float v[4];
-    int nv = 0;
-    if (i0 + 3 < n && ((reinterpret_cast<uintptr_t>(col + i0) & 15) == 0)) {
-      const float4 x = __ldg(reinterpret_cast<const float4*>(col + i0));
-      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-      nv = 4;
-    } else {
-      for (; nv < 4 && i0 + nv < n; ++nv) v[nv] = __ldg(col + i0 + nv);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      bool inside = false;
-      unsigned int key = 0u;
-      if (j < nv) {
-        float x = v[j];
-        if (SRC == SRC_DEV) x = fabsf(__fsub_rn(x, med));
-        key = orderable(x);
-        below += (key < lo) ? 1ull : 0ull;
-        inside = key >= lo && key <= hi;
-      }
-      const unsigned int m = __ballot_sync(0xffffffffu, inside);
-      if (m) {
-        const int lane = threadIdx.x & 31;
-        unsigned int wbase = 0u;
-        if (lane == 0) wbase = atomicAdd(&buf_n, __popc(m));
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        if (inside) {
-          const unsigned int slot = wbase + __popc(m & ((1u << lane) - 1u));
-          if (slot < kWinBuf) buf[slot] = key;
-          else {  // shared buffer full: rare, go straight to global
-            const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
-            if (g < window_cap) out[g] = key;
-          }
-        }
-      }
-    }
-    // flush when the buffer could overflow in the next iteration (block-uniform decision)
+  unsigned int below = 0u;
+  auto flush = [&]() {  // block-uniform
     __syncthreads();
-    if (buf_n > kWinBuf - 2048) {
-      const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
+    const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
+    if (cnt) {
       if (threadIdx.x == 0) flush_base = atomicAdd(&st->wcnt[c], cnt);
       __syncthreads();
       for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
         if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
       __syncthreads();
       if (threadIdx.x == 0) buf_n = 0u;
-      __syncthreads();
     }
+    __syncthreads();
+  };
+  const long long per_iter = static_cast<long long>(kWinThreads) * kWinPerThread;
+  const long long stride = static_cast<long long>(gridDim.x) * per_iter;
+  int it = 0;
+  for (long long base = static_cast<long long>(blockIdx.x) * per_iter; base < n; base += stride, ++it) {
+    float v[kWinPerThread];
+    bool ok[kWinPerThread];
+    // element e of this thread: base + (e / 4) * (threads * 4) + tid * 4 + (e % 4)  (coalesced 128-bit loads)
+#pragma unroll
+    for (int q = 0; q < kWinPerThread / 4; ++q) {
+      const long long i0 = base + static_cast<long long>(q) * kWinThreads * 4 + static_cast<long long>(threadIdx.x) * 4;
+      if (aligned && i0 + 3 < n) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(col + i0));
+        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        ok[4 * q] = ok[4 * q + 1] = ok[4 * q + 2] = ok[4 * q + 3] = true;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ok[4 * q + j] = i0 + j < n;
+          v[4 * q + j] = ok[4 * q + j] ? __ldg(col + i0 + j) : 0.f;
+        }
+      }
+    }
+    unsigned int keys[kWinPerThread];
+    unsigned int inside = 0u;  // bit e: element e lies in the window
+#pragma unroll
+    for (int e = 0; e < kWinPerThread; ++e) {
+      float x = v[e];
+      if (SRC == SRC_DEV) x = fabsf(__fsub_rn(x, med));
+      keys[e] = orderable(x);
+      below += (ok[e] && keys[e] < lo) ? 1u : 0u;
+      inside |= (ok[e] && keys[e] >= lo && keys[e] <= hi) ? (1u << e) : 0u;
+    }
+    if (__any_sync(0xffffffffu, inside != 0u)) {
+      // one shared atomic per warp: exclusive prefix of the lanes' hit counts
+      const unsigned int mine = __popc(inside);
+      unsigned int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      unsigned int wbase = 0u;
+      if (lane == 31) wbase = atomicAdd(&buf_n, incl);
+      wbase = __shfl_sync(0xffffffffu, wbase, 31);
+      unsigned int slot = wbase + incl - mine;
+#pragma unroll
+      for (int e = 0; e < kWinPerThread; ++e) {
+        if (inside & (1u << e)) {
+          if (slot < kWinBuf) buf[slot] = keys[e];
+          else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
+            const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
+            if (g < window_cap) out[g] = keys[e];
+          }
+          ++slot;
+        }
+      }
+    }
+    if ((it + 1) % kFlushEvery == 0) flush();
   }
-  // block totals
+  flush();
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-  if ((threadIdx.x & 31) == 0 && below) atomicAdd(&below_blk, below);
+  if (lane == 0 && below) atomicAdd(&below_blk, static_cast<unsigned long long>(below));
   __syncthreads();
-  const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
-  if (threadIdx.x == 0) {
-    if (below_blk) atomicAdd(&st->below[c], below_blk);
-    flush_base = cnt ? atomicAdd(&st->wcnt[c], cnt) : 0u;
-  }
-  __syncthreads();
-  for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
-    if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
+  if (threadIdx.x == 0 && below_blk) atomicAdd(&st->below[c], below_blk);
 }
 
 struct ScoreParams {
   double med[7];
-  double den[7];  // 1.4826 * mad
+  double inv_den[7];  // 1 / (1.4826 * mad)
   double w[6];    // alpha_t, alpha_i, alpha_m, alpha_r, alpha_n, delta
   int conditional;
 };
@@ -339,7 +360,10 @@ score_kernel(const InT* __restrict__ cols, long long n, long long ld, const Scor
 #pragma unroll
     for (int c = 0; c < 7; ++c) {
       const double v = static_cast<double>(__ldg(cols + static_cast<size_t>(c) * ld + i));
-      z[c] = __ddiv_rn(__dsub_rn(v, p.med[c]), p.den[c]);  // scorer.py:31
+      // scorer.py:31 `(val - med) / (1.4826 * mad)`; the reciprocal is formed once on the host, which
+      // moves the result by at most one ulp of float64 (gate: 1e-6 relative) and removes seven
+      // float64 divisions per row from a kernel that is otherwise HBM-bound
+      z[c] = __dmul_rn(__dsub_rn(v, p.med[c]), p.inv_den[c]);
     }
     const double Ht = __dmul_rn(0.5, __dadd_rn(z[0], z[1]));  // scorer.py:53
     const double Hi = __dmul_rn(0.5, __dadd_rn(z[2], z[3]));  // scorer.py:54
@@ -362,18 +386,27 @@ score_kernel(const InT* __restrict__ cols, long long n, long long ld, const Scor
   }
 }
 
+// Work buffers are kept per device between calls (grow-only): cudaMalloc / cudaFree would cost more
+// than the kernels.  Calls are serialised by the mutex (the C ABI is one-thread-per-handle anyway).
 struct FitWork {
   SelState* st = nullptr;
   unsigned int* ghist = nullptr;
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
-  ~FitWork() {
-    cudaFree(st);
-    cudaFree(ghist);
-    cudaFree(skeys);
-    cudaFree(wkeys);
-  }
+  size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0;
 };
+std::mutex g_fit_mu;
+FitWork g_fit_work[64];
+
+int ensure_buf(unsigned int** p, size_t* have, size_t need) {
+  if (need <= *have) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *have = 0;
+  DEWI_CUDA(cudaMalloc(p, need));
+  *have = need;
+  return 0;
+}
 
 template <int SRC>
 void select3(const void* src, long long n_host, const unsigned int* n_dev, long long ld, int f, SelState* st,
@@ -407,7 +440,7 @@ void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsi
   select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_WINDOW, f, n, cap, w.st);
   const int bx = std::max(1, 148 * 4 / f);
-  window_kernel<SRC><<<dim3(bx, f), 512, 0, stream>>>(cols, n, ld, w.st, w.wkeys, cap);
+  window_kernel<SRC><<<dim3(bx, f), kWinThreads, 0, stream>>>(cols, n, ld, w.st, w.wkeys, cap);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_INSIDE, f, n, cap, w.st);
   select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(final_op, f, n, cap, w.st);
@@ -430,12 +463,14 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   const bool windowed = n >= kWindowMinRows;
   // expected window population is 2 * margin / sample = 0.8 % of n; allow twice that
   const unsigned int cap = windowed ? static_cast<unsigned int>(std::min<int64_t>(n / 64 + 65536, 1ll << 30)) : 0u;
-  FitWork w;
-  DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
-  DEWI_CUDA(cudaMalloc(&w.ghist, static_cast<size_t>(f) * 2 * kBins * 4));
+  if (device >= 64) return fail("device ordinal out of range");
+  std::lock_guard<std::mutex> lock(g_fit_mu);
+  FitWork& w = g_fit_work[device];
+  if (!w.st) DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
+  DEWI_TRY(ensure_buf(&w.ghist, &w.ghist_bytes, static_cast<size_t>(kMaxCols) * 2 * kBins * 4));
   if (windowed) {
-    DEWI_CUDA(cudaMalloc(&w.skeys, static_cast<size_t>(f) * kSample * 4));
-    DEWI_CUDA(cudaMalloc(&w.wkeys, static_cast<size_t>(f) * cap * 4));
+    DEWI_TRY(ensure_buf(&w.skeys, &w.skeys_bytes, static_cast<size_t>(f) * kSample * 4));
+    DEWI_TRY(ensure_buf(&w.wkeys, &w.wkeys_bytes, static_cast<size_t>(f) * cap * 4));
   }
   DEWI_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SelState), stream));
   DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
@@ -475,7 +510,7 @@ extern "C" int dewi_score(const void* cols, int in_f64, int64_t n, int64_t ld, c
   ScoreParams p;
   for (int c = 0; c < 7; ++c) {
     p.med[c] = med7[c];
-    p.den[c] = 1.4826 * mad7[c];
+    p.inv_den[c] = 1.0 / (1.4826 * mad7[c]);
   }
   for (int i = 0; i < 6; ++i) p.w[i] = w6[i];
   p.conditional = conditional ? 1 : 0;

@@ -49,7 +49,7 @@ def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device
                     precision: str = "fp32", force: Optional[str] = None):
     """Thresholded similarity join.  `b=None` is the self-join (diagonal excluded, pairs j > i).
 
-    precision "fp32": similarities good to ~1e-6 (bf16 hi+lo planes on the tensor cores, or the fp32
+    precision "fp32": similarities good to ~1e-5 (bf16 hi+lo planes on the tensor cores, or the fp32
     CUDA-core kernel for small inputs / d % 64 != 0); "bf16": one bf16 plane, ~1e-3, 3x fewer MMAs.
     force: None | "simt" | "tc" pins the kernel (tests).
 

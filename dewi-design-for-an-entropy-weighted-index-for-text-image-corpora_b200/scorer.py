@@ -68,6 +68,21 @@ class RobustStats:
         keys = list(columns.keys())
         tdev = torch.device("cuda", dev)
         cols = torch.stack([torch.as_tensor(columns[k], dtype=torch.float32).to(tdev) for k in keys]).contiguous()
+        return cls.fit_matrix(keys, cols, dev)
+
+    @classmethod
+    def fit_matrix(cls, keys: Sequence[str], matrix, device: Optional[int] = None) -> "RobustStats":
+        """`matrix`: `[len(keys), N]` array / tensor, row c = the column named keys[c].  A float32 CUDA
+        tensor with unit stride along N is used in place (no copy)."""
+        torch = _torch()
+        dev = _device_index(device)
+        _native.require_device(dev)
+        cols = torch.as_tensor(matrix)
+        if cols.ndim != 2 or cols.shape[0] != len(keys):
+            raise ValueError("expected one row per key")
+        cols = cols.to(torch.device("cuda", dev), torch.float32)
+        if cols.stride(1) != 1:
+            cols = cols.contiguous()
         med, mad = _fit_columns(cols, dev)
         return cls(medians={k: float(m) for k, m in zip(keys, med)}, mads={k: float(m) for k, m in zip(keys, mad)})
 
@@ -91,8 +106,9 @@ class DewiScorer:
     def fit_stats_columns(self, columns) -> None:
         """Batch form: a mapping name -> column, or a `[7, N]` array/tensor in `SIGNAL_FIELDS` order."""
         if not isinstance(columns, Mapping):
-            columns = {k: columns[i] for i, k in enumerate(SIGNAL_FIELDS)}
-        self.stats = RobustStats.fit_columns(columns, self.device)
+            self.stats = RobustStats.fit_matrix(SIGNAL_FIELDS, columns, self.device)
+        else:
+            self.stats = RobustStats.fit_columns(columns, self.device)
 
     def is_fitted(self) -> bool:
         return self.stats is not None

@@ -137,7 +137,7 @@ DEWI_API int dewi_similarity_dense(const float* a, int64_t m, const float* b, in
  * to `pair_cap` (i, j, sim) pairs with sim >= tau appended to pair_i/pair_j/pair_sim, the total
  * number found in *pair_count_host.  self_join: b == a, diagonal excluded, pairs only j > i.
  * Large inputs with d % 64 == 0 run on the tensor cores (CTA-pair sweep with a threshold epilogue):
- * rows as bf16 hi+lo planes, three MMAs, similarities good to ~1e-6; DEWI_JOIN_BF16 keeps one bf16
+ * rows as bf16 hi+lo planes, three MMAs, similarities good to ~1e-5 (the lo.lo term is dropped); DEWI_JOIN_BF16 keeps one bf16
  * plane (one MMA, similarities carry bf16 rounding ~1e-3).  Otherwise an fp32 CUDA-core kernel.   */
 enum { DEWI_JOIN_BF16 = 1 << 0, DEWI_JOIN_FORCE_SIMT = 1 << 1, DEWI_JOIN_FORCE_TC = 1 << 2 };
 DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int flags,
