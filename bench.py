@@ -99,17 +99,25 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0:  # sampling is live before the timed region starts
+                time.sleep(0.01)
+            self.lines.clear()
         except OSError:
             self.proc = None
         return self
 
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
+
     def __exit__(self, *exc):
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.03)
             self.proc.terminate()
             self.thread.join(timeout=2)
 

@@ -81,7 +81,9 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   uint64_t* bar_acc_empty = bar_acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (the shuffle tells the compiler so); whole warps walk the role loops and
+  // the TMA / MMA issue sites are predicated on elect.sync, which keeps their operands in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -114,29 +116,33 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer: corpus ring =====================
-    if (lane == 0) {
+    {
       int se = 0;
       uint32_t pe = 0;
+      // single query block: the corpus is streamed once, do not let it displace the queries in L2
+      const uint64_t e_policy = a.n_qb > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int t0, t1;
         tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < a.n_kb; ++kb) {
             ptx::mbar_wait(&bar_e_empty[se], pe ^ 1);
-            uint8_t* st = ring_e + static_cast<size_t>(se) * kEStageBytes;
-            ptx::mbar_arrive_expect_tx(&bar_e_full[se], kEStageBytes);
-            ptx::tma_load_2d(st, &map_e0, &bar_e_full[se], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
-            if (T::PE > 1)
-              ptx::tma_load_2d(st + kEPlaneBytes, &map_e1, &bar_e_full[se], kb * kKBlock, t * N_TILE, ptx::kEvictFirst);
+            if (ptx::elect_one()) {
+              uint8_t* st = ring_e + static_cast<size_t>(se) * kEStageBytes;
+              ptx::mbar_arrive_expect_tx(&bar_e_full[se], kEStageBytes);
+              ptx::tma_load_2d(st, &map_e0, &bar_e_full[se], kb * kKBlock, t * N_TILE, e_policy);
+              if (T::PE > 1)
+                ptx::tma_load_2d(st + kEPlaneBytes, &map_e1, &bar_e_full[se], kb * kKBlock, t * N_TILE, e_policy);
+            }
+            __syncwarp();
             if (++se == a.e_stages) { se = 0; pe ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == kQWarp) {
     // ===================== TMA producer: query ring =====================
-    if (lane == 0) {
+    {
       int sq = 0;
       uint32_t pq = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -146,25 +152,28 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < a.n_kb; ++kb) {
             ptx::mbar_wait(&bar_q_empty[sq], pq ^ 1);
-            uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
-            ptx::mbar_arrive_expect_tx(&bar_q_full[sq], kQStageBytes);
-            ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
-            if (T::PQ > 1)
-              ptx::tma_load_2d(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
-                               ptx::kEvictLast);
+            if (ptx::elect_one()) {
+              uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
+              ptx::mbar_arrive_expect_tx(&bar_q_full[sq], kQStageBytes);
+              ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+              if (T::PQ > 1)
+                ptx::tma_load_2d(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
+                                 ptx::kEvictLast);
+            }
+            __syncwarp();
             if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    {
       int se = 0, sq = 0;
       uint32_t pe = 0, pq = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t ring_e_addr = ptx::smem_u32(ring_e), ring_q_addr = ptx::smem_u32(ring_q);
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int t0, t1;
         tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
@@ -176,22 +185,25 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
             ptx::mbar_wait(&bar_q_full[sq], pq);
             ptx::mbar_wait(&bar_e_full[se], pe);  // TMA bytes have landed
             ptx::tc_fence_after();
-            const uint32_t ste = ptx::smem_u32(ring_e + static_cast<size_t>(se) * kEStageBytes);
-            const uint32_t stq = ptx::smem_u32(ring_q + static_cast<size_t>(sq) * kQStageBytes);
-            const uint64_t de0 = ptx::make_desc_sw128(ste);
-            const uint64_t de1 = ptx::make_desc_sw128(ste + kEPlaneBytes);
-            const uint64_t dq0 = ptx::make_desc_sw128(stq);
-            const uint64_t dq1 = ptx::make_desc_sw128(stq + kQPlaneBytes);
+            if (ptx::elect_one()) {
+              const uint32_t ste = ring_e_addr + static_cast<uint32_t>(se) * kEStageBytes;
+              const uint32_t stq = ring_q_addr + static_cast<uint32_t>(sq) * kQStageBytes;
+              const uint64_t de0 = ptx::make_desc_sw128(ste);
+              const uint64_t de1 = ptx::make_desc_sw128(ste + kEPlaneBytes);
+              const uint64_t dq0 = ptx::make_desc_sw128(stq);
+              const uint64_t dq1 = ptx::make_desc_sw128(stq + kQPlaneBytes);
 #pragma unroll
-            for (int k = 0; k < kKBlock / 16; ++k) {
-              const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
-              ptx::mma_bf16_ss(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
-              if (MODE >= 1) ptx::mma_bf16_ss(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
-              if (MODE == 2) ptx::mma_bf16_ss(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+              for (int k = 0; k < kKBlock / 16; ++k) {
+                const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
+                ptx::mma_bf16_ss(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                if (MODE >= 1) ptx::mma_bf16_ss(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
+                if (MODE == 2) ptx::mma_bf16_ss(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+              }
+              ptx::mma_commit(&bar_e_empty[se]);  // smem slots reusable once these MMAs retire
+              ptx::mma_commit(&bar_q_empty[sq]);
+              if (kb == a.n_kb - 1) ptx::mma_commit(&bar_acc_full[acc]);
             }
-            ptx::mma_commit(&bar_e_empty[se]);  // smem slots reusable once these MMAs retire
-            ptx::mma_commit(&bar_q_empty[sq]);
-            if (kb == a.n_kb - 1) ptx::mma_commit(&bar_acc_full[acc]);
+            __syncwarp();
             if (++se == a.e_stages) { se = 0; pe ^= 1; }
             if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
           }
@@ -200,7 +212,6 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
         }
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: TMEM -> per-query candidate lists =====================
     const int quarter = warp & 3;             // TMEM lane quarter this warp may read

@@ -9,13 +9,15 @@
 // 128x256x64 block of work -- 1.5x less L2 traffic per flop -- and the corpus tile is fetched once
 // per pair instead of once per CTA.
 //
-// Roles per CTA (224 threads): w0 corpus-ring TMA producer (own half tile), w6 query-ring TMA producer
-// (own query block), w1 MMA issuer (leader CTA only) + TMEM allocation, w2-5 epilogue over the CTA's
-// own 128 TMEM lanes (identical to the 1-CTA kernel: sweep_epilogue.cuh).
+// Roles per CTA (192 threads): w0 TMA producer (own query k-block + own half of the corpus k-block into
+// one ring stage), w1 MMA issuer (leader CTA only) + TMEM allocation, w2-5 epilogue over the CTA's own
+// 128 TMEM lanes (identical to the 1-CTA kernel: sweep_epilogue.cuh).  Role loops are walked by whole
+// warps with the issue sites predicated on elect.sync, so operands stay in uniform registers.
 // Barriers: "full" barriers live in the leader (both CTAs' TMA transactions are accounted there);
 // "empty" and "accumulator full" are signalled in both CTAs by a multicast tcgen05.commit;
 // "accumulator empty" collects 8 epilogue-warp arrivals (4 local + 4 remote) in the leader.
 #include <algorithm>
+#include <cstdlib>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -26,8 +28,7 @@ namespace {
 
 using namespace sweep;
 
-constexpr int kThreads = 224;
-constexpr int kQWarp = 6;
+constexpr int kThreads = 192;
 constexpr int kNTile = 256;           // corpus rows per MMA (N); each CTA stages kNTile / 2
 constexpr int kHalfRows = kNTile / 2;
 
@@ -122,27 +123,27 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   using T = ModeTraits<MODE>;
   constexpr uint32_t kEPlaneBytes = kHalfRows * 128;   // this CTA's half of a corpus k-block
   constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
-  constexpr uint32_t kEStageBytes = T::PE * kEPlaneBytes;
-  constexpr uint32_t kQStageBytes = T::PQ * kQPlaneBytes;
+  constexpr uint32_t kEBytes = T::PE * kEPlaneBytes;
+  constexpr uint32_t kStageBytes = kEBytes + T::PQ * kQPlaneBytes;   // [corpus half planes | query planes]
   constexpr uint32_t kTmemCols = 2 * kNTile;
   constexpr uint32_t kIdesc = ptx::make_idesc_bf16(2 * kQueryBlock, kNTile);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring_e = smem;
-  uint8_t* ring_q = ring_e + static_cast<size_t>(a.e_stages) * kEStageBytes;
+  // ONE ring: both operands of a k-block arrive from L2 at the same rate here, and one full / one empty
+  // barrier per k-block keeps the single-threaded MMA issue loop short.
+  uint8_t* ring = smem;
   const int kl = a.kc + kPending;
-  float* list_s = reinterpret_cast<float*>(ring_q + static_cast<size_t>(a.q_stages) * kQStageBytes);
+  float* list_s = reinterpret_cast<float*>(ring + static_cast<size_t>(a.e_stages) * kStageBytes);
   int* list_i = reinterpret_cast<int*>(list_s + kl * kQueryBlock);
-  uint64_t* bar_e_full = reinterpret_cast<uint64_t*>(list_i + kl * kQueryBlock);
-  uint64_t* bar_e_empty = bar_e_full + kMaxStages;
-  uint64_t* bar_q_full = bar_e_empty + kMaxStages;
-  uint64_t* bar_q_empty = bar_q_full + kQStagesMax;
-  uint64_t* bar_acc_full = bar_q_empty + kQStagesMax;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(list_i + kl * kQueryBlock);
+  uint64_t* bar_empty = bar_full + kMaxStages;
+  uint64_t* bar_acc_full = bar_empty + kMaxStages;
   uint64_t* bar_acc_empty = bar_acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  // warp-uniform role index (the shuffle tells the compiler so)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader
   const int cluster_id = blockIdx.x >> 1;
@@ -154,12 +155,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     if (T::PE > 1) ptx::prefetch_tmap(&map_e1);
     if (T::PQ > 1) ptx::prefetch_tmap(&map_q1);
     for (int s = 0; s < a.e_stages; ++s) {
-      ptx::mbar_init(&bar_e_full[s], 2);   // one producer arrival per CTA of the pair
-      ptx::mbar_init(&bar_e_empty[s], 1);
-    }
-    for (int s = 0; s < a.q_stages; ++s) {
-      ptx::mbar_init(&bar_q_full[s], 2);
-      ptx::mbar_init(&bar_q_empty[s], 1);
+      ptx::mbar_init(&bar_full[s], 2);   // one producer arrival per CTA of the pair
+      ptx::mbar_init(&bar_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&bar_acc_full[b], 1);
@@ -177,61 +174,43 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer: this CTA's half of each corpus k-block =====================
-    if (lane == 0) {
-      int se = 0;
-      uint32_t pe = 0;
-      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-        int t0, t1;
-        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
-        for (int t = t0; t < t1; ++t) {
-          const int row0 = t * kNTile + static_cast<int>(rank) * kHalfRows;
-          for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_e_empty[se], pe ^ 1);
-            uint8_t* st = ring_e + static_cast<size_t>(se) * kEStageBytes;
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_e_full[se], 2 * kEStageBytes);
-            else ptx::mbar_arrive_leader(&bar_e_full[se]);
-            ptx::tma_load_2d_pair(st, &map_e0, &bar_e_full[se], kb * kKBlock, row0, ptx::kEvictFirst);
-            if (T::PE > 1)
-              ptx::tma_load_2d_pair(st + kEPlaneBytes, &map_e1, &bar_e_full[se], kb * kKBlock, row0, ptx::kEvictFirst);
-            if (++se == a.e_stages) { se = 0; pe ^= 1; }
-          }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == kQWarp) {
-    // ===================== TMA producer: this CTA's query block =====================
-    if (lane == 0) {
-      int sq = 0;
-      uint32_t pq = 0;
-      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-        const int qb = (item % a.n_qpairs) * 2 + static_cast<int>(rank);
-        int t0, t1;
-        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
-        for (int t = t0; t < t1; ++t) {
-          for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_q_empty[sq], pq ^ 1);
-            uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
-            if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_q_full[sq], 2 * kQStageBytes);
-            else ptx::mbar_arrive_leader(&bar_q_full[sq]);
-            ptx::tma_load_2d_pair(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+    // ===================== TMA producer: this CTA's query k-block + its half of the corpus k-block =====================
+    int st = 0;
+    uint32_t ph = 0;
+    // a corpus tile is read again by the clusters working on the other query-block pairs of the same
+    // chunk: leave it in L2 at normal priority unless this is the only pair
+    const uint64_t e_policy = a.n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+      const int qrow = ((item % a.n_qpairs) * 2 + static_cast<int>(rank)) * kQueryBlock;
+      int t0, t1;
+      tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
+      for (int t = t0; t < t1; ++t) {
+        const int row0 = t * kNTile + static_cast<int>(rank) * kHalfRows;
+        for (int kb = 0; kb < a.n_kb; ++kb) {
+          ptx::mbar_wait(&bar_empty[st], ph ^ 1);
+          if (ptx::elect_one()) {
+            uint8_t* sp = ring + static_cast<size_t>(st) * kStageBytes;
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_full[st], 2 * kStageBytes);
+            else ptx::mbar_arrive_leader(&bar_full[st]);
+            ptx::tma_load_2d_pair(sp, &map_e0, &bar_full[st], kb * kKBlock, row0, e_policy);
+            if (T::PE > 1) ptx::tma_load_2d_pair(sp + kEPlaneBytes, &map_e1, &bar_full[st], kb * kKBlock, row0, e_policy);
+            ptx::tma_load_2d_pair(sp + kEBytes, &map_q0, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
             if (T::PQ > 1)
-              ptx::tma_load_2d_pair(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
-                                    ptx::kEvictLast);
-            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
+              ptx::tma_load_2d_pair(sp + kEBytes + kQPlaneBytes, &map_q1, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
           }
+          __syncwarp();
+          if (++st == a.e_stages) { st = 0; ph ^= 1; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA, one thread, on behalf of the pair) =====================
-    if (rank == 0 && lane == 0) {
-      int se = 0, sq = 0;
-      uint32_t pe = 0, pq = 0;
+    // ===================== MMA issuer (leader CTA; the whole warp walks the loop, one elected lane issues) ==========
+    if (rank == 0) {
+      int st = 0;
+      uint32_t ph = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t ring_addr = ptx::smem_u32(ring);
       for (int item = cluster_id; item < a.n_items; item += n_clusters) {
         int t0, t1;
         tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
@@ -240,34 +219,32 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kNTile);
           for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_q_full[sq], pq);
-            ptx::mbar_wait(&bar_e_full[se], pe);
+            ptx::mbar_wait(&bar_full[st], ph);  // both CTAs' TMA bytes have landed
             ptx::tc_fence_after();
-            const uint32_t ste = ptx::smem_u32(ring_e + static_cast<size_t>(se) * kEStageBytes);
-            const uint32_t stq = ptx::smem_u32(ring_q + static_cast<size_t>(sq) * kQStageBytes);
-            const uint64_t de0 = ptx::make_desc_sw128(ste);
-            const uint64_t de1 = ptx::make_desc_sw128(ste + kEPlaneBytes);
-            const uint64_t dq0 = ptx::make_desc_sw128(stq);
-            const uint64_t dq1 = ptx::make_desc_sw128(stq + kQPlaneBytes);
+            if (ptx::elect_one()) {
+              const uint32_t sp = ring_addr + static_cast<uint32_t>(st) * kStageBytes;
+              const uint64_t de0 = ptx::make_desc_sw128(sp);
+              const uint64_t de1 = ptx::make_desc_sw128(sp + kEPlaneBytes);
+              const uint64_t dq0 = ptx::make_desc_sw128(sp + kEBytes);
+              const uint64_t dq1 = ptx::make_desc_sw128(sp + kEBytes + kQPlaneBytes);
 #pragma unroll
-            for (int k = 0; k < kKBlock / 16; ++k) {
-              const uint64_t adv = static_cast<uint64_t>(k * 2);
-              ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
-              if (MODE >= 1) ptx::mma_bf16_ss_pair(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
-              if (MODE == 2) ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+              for (int k = 0; k < kKBlock / 16; ++k) {
+                const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
+                ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de0 + adv, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                if (MODE >= 1) ptx::mma_bf16_ss_pair(tmem_d, dq1 + adv, de0 + adv, kIdesc, 1u);
+                if (MODE == 2) ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
+              }
+              ptx::mma_commit_pair(&bar_empty[st], 3);  // frees the slot in both CTAs
+              if (kb == a.n_kb - 1) ptx::mma_commit_pair(&bar_acc_full[acc], 3);
             }
-            ptx::mma_commit_pair(&bar_e_empty[se], 3);  // frees the slot in both CTAs
-            ptx::mma_commit_pair(&bar_q_empty[sq], 3);
-            if (kb == a.n_kb - 1) ptx::mma_commit_pair(&bar_acc_full[acc], 3);
-            if (++se == a.e_stages) { se = 0; pe ^= 1; }
-            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
+            __syncwarp();
+            if (++st == a.e_stages) { st = 0; ph ^= 1; }
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
         }
       }
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: this CTA's 128 queries =====================
     const int quarter = warp & 3;
@@ -323,11 +300,12 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   }
 }
 
-size_t e_stage_bytes(int mode) { return static_cast<size_t>((mode == 2) ? 2 : 1) * kHalfRows * 128; }
-size_t q_stage_bytes(int mode) { return static_cast<size_t>((mode == 0) ? 1 : 2) * kQueryBlock * 128; }
+size_t stage_bytes(int mode) {
+  const int pe = (mode == 2) ? 2 : 1, pq = (mode == 0) ? 1 : 2;
+  return static_cast<size_t>(pe) * kHalfRows * 128 + static_cast<size_t>(pq) * kQueryBlock * 128;
+}
 size_t fixed_bytes(int kc) {
-  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
-         1024 /*alignment slack*/;
+  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
 }
 
 template <int MODE, int EPI>
@@ -347,10 +325,9 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
   const size_t smem_max = 227 * 1024;
   const size_t fixed = fixed_bytes(kc);
-  const int q_stages = 3;
-  const size_t used = fixed + q_stages * q_stage_bytes(mode);
-  int stages = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode)) : 0;
-  if (stages < 3) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
+  int stages = fixed < smem_max ? static_cast<int>((smem_max - fixed) / stage_bytes(mode)) : 0;
+  if (const char* env = getenv("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));
+  if (stages < 2) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
   stages = std::min(stages, kMaxStages);
   const int64_t n_tiles = ceil_div(n_rows, kNTile);
   const int n_qpairs = n_qb / 2;
@@ -366,10 +343,10 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
   plan->mode = mode;
   plan->n_stages = stages;
-  plan->q_stages = q_stages;
+  plan->q_stages = 0;
   plan->n_chunks = static_cast<int>(chunks);
   plan->grid = 2 * static_cast<int>(std::min<int64_t>(clusters, chunks * n_qpairs));
-  plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode) + q_stages * q_stage_bytes(mode);
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * stage_bytes(mode);
   return 0;
 }
 

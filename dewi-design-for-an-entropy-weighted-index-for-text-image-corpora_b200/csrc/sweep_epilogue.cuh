@@ -9,7 +9,7 @@ namespace sweep {
 
 constexpr int kPending = 16;   // list slots beyond kc: candidates appended between two prunes
 constexpr int kGroup = 8;      // columns examined between two overflow checks (kGroup <= kPending / 2)
-constexpr int kQStagesMax = 4;
+constexpr int kQStagesMax = 8;
 
 template <int MODE>
 struct ModeTraits {
