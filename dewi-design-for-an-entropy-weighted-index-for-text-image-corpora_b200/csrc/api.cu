@@ -368,7 +368,7 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   DEWI_TRY(h->q1.ensure(static_cast<size_t>(b_pad) * dim * 2));
   const int qnorm = (h->space == DEWI_SPACE_COSINE && !(flags & DEWI_FLAG_QUERY_NORMALIZED)) ? 1 : 0;
   DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
-                               h->q1.as<__nv_bfloat16>(), stream));
+                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/1));
   h->last_launches++;
 
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);

@@ -31,6 +31,10 @@ constexpr int kQueryBlock = 128;  // queries per MMA M-tile == TMEM lanes
 constexpr int kKBlock = 64;       // bf16 elements per 128-byte swizzle row
 constexpr int kMaxStages = 8;
 
+// Query j of a 128-query block sits on TMEM lane / partial-list column query_lane(j): consecutive
+// queries go to different epilogue warps, so a small batch keeps all four of them busy instead of one.
+__host__ __device__ inline int query_lane(int j) { return (j & 3) * 32 + (j >> 2); }
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
@@ -101,8 +105,9 @@ int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const 
 // rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
                        __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream);
-// queries fp32 [B, dim] -> qn fp32 [b_pad, dim], q hi/lo bf16 [b_pad, dim] (rows >= B zeroed).
+// queries fp32 [B, dim] -> qn fp32 [b_pad, dim] (natural order), q hi/lo bf16 [b_pad, dim] (rows >= B
+// zeroed).  lane_order: plane row of query b is (b / 128) * 128 + query_lane(b % 128).
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream);
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0);
 
 }  // namespace dewi

@@ -21,17 +21,21 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 }
 
 __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, long long n_out, int dim, int normalize,
-                                 int guard_zero, float* __restrict__ dst_f32, __nv_bfloat16* __restrict__ hi,
-                                 __nv_bfloat16* __restrict__ lo, int* __restrict__ bad_flag) {
+                                 int guard_zero, int lane_order, float* __restrict__ dst_f32,
+                                 __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                 int* __restrict__ bad_flag) {
   const int lane = threadIdx.x & 31;
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n_out; row += warps) {
     const size_t off = static_cast<size_t>(row) * dim;
+    // bf16 planes may use the TMEM-lane order of the sweep (internal.h: query_lane)
+    const long long prow = lane_order ? (row / kQueryBlock) * kQueryBlock + query_lane(static_cast<int>(row % kQueryBlock)) : row;
+    const size_t poff = static_cast<size_t>(prow) * dim;
     if (row >= n) {  // zero padding rows (query block padding)
       for (int d = lane; d < dim; d += 32) {
         if (dst_f32) dst_f32[off + d] = 0.f;
-        if (hi) hi[off + d] = __float2bfloat16_rn(0.f);
-        if (lo) lo[off + d] = __float2bfloat16_rn(0.f);
+        if (hi) hi[poff + d] = __float2bfloat16_rn(0.f);
+        if (lo) lo[poff + d] = __float2bfloat16_rn(0.f);
       }
       continue;
     }
@@ -60,20 +64,20 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
       if (hi) {
         __nv_bfloat16 h, l;
         split_bf16(x, h, l);
-        hi[off + d] = h;
-        if (lo) lo[off + d] = l;
+        hi[poff + d] = h;
+        if (lo) lo[poff + d] = l;
       }
     }
   }
 }
 
-int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, int guard_zero, float* dst_f32,
-           __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
+int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, int guard_zero, int lane_order,
+           float* dst_f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
   if (n_out <= 0) return 0;
   const int threads = 256;
   const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), 148 * 16);
-  prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero, dst_f32,
-                                                                    hi, lo, bad_flag);
+  prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero,
+                                                                    lane_order, dst_f32, hi, lo, bad_flag);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -82,13 +86,13 @@ int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, i
 
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
                        __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
-  return launch(src, n, n, dim, normalize, 1, dst_f32, hi, lo, bad_flag, stream);
+  return launch(src, n, n, dim, normalize, 1, 0, dst_f32, hi, lo, bad_flag, stream);
 }
 
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream) {
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order) {
   // a zero query stays zero (backends.py:422-424: divide only when the norm is positive)
-  return launch(q, B, b_pad, dim, normalize, 0, qn, hi, lo, nullptr, stream);
+  return launch(q, B, b_pad, dim, normalize, 0, lane_order, qn, hi, lo, nullptr, stream);
 }
 
 }  // namespace dewi

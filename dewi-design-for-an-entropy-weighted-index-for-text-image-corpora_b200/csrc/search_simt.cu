@@ -159,7 +159,7 @@ search_simt_kernel(const RowT* __restrict__ rows, long long n_rows, int dim, con
     if (warp < nq) {
       const int q = warp;
       const int b = g0 + q;
-      const int qb = b / kQueryBlock, ql = b % kQueryBlock;
+      const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
       float* ps = part_s + (static_cast<size_t>(blockIdx.x) * n_qb + qb) * kc * kQueryBlock;
       int* pi = part_i + (static_cast<size_t>(blockIdx.x) * n_qb + qb) * kc * kQueryBlock;
       const int total = kSimtWarps * kc;

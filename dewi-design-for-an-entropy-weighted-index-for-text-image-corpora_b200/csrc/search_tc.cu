@@ -21,6 +21,7 @@
 //   mode 1  Q0.E0 + Q1.E0              bf16 corpus, query split hi+lo
 //   mode 2  Q0.E0 + Q1.E0 + Q0.E1      fp32 corpus as hi+lo planes (drops only the lo.lo term, ~2^-18)
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "internal.h"

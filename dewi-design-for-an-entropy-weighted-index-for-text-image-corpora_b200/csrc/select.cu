@@ -64,7 +64,7 @@ merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ pa
   __shared__ unsigned long long key[kWindow];
   __shared__ int val[kWindow];
   const int b = blockIdx.x;
-  const int qb = b / kQueryBlock, ql = b % kQueryBlock;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
   const int total = n_chunks * kc;
   const int batch = kWindow - kc_out;
   for (int t = threadIdx.x; t < kc_out; t += blockDim.x) { key[t] = 0ull; val[t] = -1; }

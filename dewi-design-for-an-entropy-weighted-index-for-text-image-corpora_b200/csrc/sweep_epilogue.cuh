@@ -58,10 +58,41 @@ __device__ __forceinline__ void lane_prune(LaneList& l, int kc) {
   }
 }
 
+// Warp-cooperative prune of ONE lane's list (the steady state, where lanes overflow one at a time):
+// every entry's rank among the `cnt` entries is counted by all 32 lanes together (each lane owns up to
+// two entries and compares them with every entry, read as a shared-memory broadcast), the kc best
+// are written back in rank order, and the kc-th becomes the threshold.  ~cnt broadcast loads instead
+// of the (cnt - kc) x cnt dependent scans of lane_prune run by a single active lane.
+// Requires kc + kPending <= 64.  `col_s` / `col_i` point at the target lane's column.
+__device__ __forceinline__ float coop_prune(float* col_s, int* col_i, int cnt, int kc, int lane) {
+  const int e0 = lane, e1 = lane + 32;
+  const bool has0 = e0 < cnt, has1 = e1 < cnt;
+  const float v0 = has0 ? col_s[e0 * kQueryBlock] : 0.f, v1 = has1 ? col_s[e1 * kQueryBlock] : 0.f;
+  const int i0 = has0 ? col_i[e0 * kQueryBlock] : 0, i1 = has1 ? col_i[e1 * kQueryBlock] : 0;
+  int r0 = 0, r1 = 0;
+#pragma unroll 4
+  for (int f = 0; f < cnt; ++f) {
+    const float vf = col_s[f * kQueryBlock];  // same address in every lane: broadcast
+    r0 += (vf > v0 || (vf == v0 && f < e0)) ? 1 : 0;
+    r1 += (vf > v1 || (vf == v1 && f < e1)) ? 1 : 0;
+  }
+  __syncwarp();  // all reads done before the in-place rewrite
+  if (has0 && r0 < kc) { col_s[r0 * kQueryBlock] = v0; col_i[r0 * kQueryBlock] = i0; }
+  if (has1 && r1 < kc) { col_s[r1 * kQueryBlock] = v1; col_i[r1 * kQueryBlock] = i1; }
+  // the entry ranked kc-1 is the new admission threshold
+  const bool mine0 = has0 && r0 == kc - 1, mine1 = has1 && r1 == kc - 1;
+  const unsigned int who = __ballot_sync(0xffffffffu, mine0 || mine1);
+  const float t = __shfl_sync(0xffffffffu, mine0 ? v0 : v1, who ? (__ffs(who) - 1) : 0);
+  __syncwarp();
+  return t;
+}
+
 // One accumulator tile: this thread's TMEM lane, N_TILE fp32 columns starting at `tcol`; column j is
 // corpus row row_base + j.
 template <int N_TILE>
 __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, int row_base, int n_rows) {
+  const int lane = threadIdx.x & 31;
+  const bool coop_ok = kc + kPending <= 64;
 #pragma unroll 1
   for (int c = 0; c < N_TILE / 32; ++c) {
     float v[32];
@@ -88,7 +119,22 @@ __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, in
           }
         }
         // a lane enters a group with cnt <= kc + kPending - kGroup, so the appends above fit
-        if (__any_sync(0xffffffffu, l.cnt > kc + kPending - kGroup)) lane_prune(l, kc);
+        unsigned int over = __ballot_sync(0xffffffffu, l.cnt > kc + kPending - kGroup);
+        if (over) {
+          if (!coop_ok || __popc(over) >= 8) {
+            lane_prune(l, kc);  // many lanes full at once (the first tiles of an item): lane-parallel
+          } else {
+            __syncwarp();
+            while (over) {  // a few lanes: the warp prunes them one at a time, cooperatively
+              const int tgt = __ffs(over) - 1;
+              over &= over - 1;
+              const int tcnt = __shfl_sync(0xffffffffu, l.cnt, tgt);
+              // lanes of one warp own consecutive columns: the target's column is (mine - lane + tgt)
+              const float t = coop_prune(l.s - lane + tgt, l.i - lane + tgt, tcnt, kc, lane);
+              if (lane == tgt) { l.cnt = kc; l.thr = t; }
+            }
+          }
+        }
       }
     }
   }
