@@ -24,6 +24,7 @@ FLAG_HOST_IO = 1 << 3
 FLAG_PRECISE_QUERY = 1 << 4
 FLAG_SCOPE_FULL = 1 << 5
 FLAG_NO_PAIR = 1 << 6
+FLAG_NO_SEED = 1 << 7
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2

@@ -63,7 +63,7 @@ struct dewi_index {
   int64_t map_rows = -1;
   int map_box = 0;
   // workspaces
-  DevBuf stage, qraw, qn, q0, q1, part_s, part_i, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
+  DevBuf stage, qraw, qn, q0, q1, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
       out_score;
   int last_launches = 0;
   // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
@@ -224,7 +224,7 @@ int dewi_index_destroy(dewi_index_t* h) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
   }
-  for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->cand_idx, &h->cand_sim,
+  for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
                     &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score})
     b->release();
   delete h;
@@ -382,16 +382,65 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
     CUtensorMap mq0, mq1;
     DEWI_TRY(tc_encode_rows_map(&mq0, h->q0.p, b_pad, dim, kQueryBlock));
     DEWI_TRY(tc_encode_rows_map(&mq1, h->q1.p, b_pad, dim, kQueryBlock));
+    {  // size the partial-list buffers for the main sweep up front: growing them later would cudaFree
+       // (a device-wide synchronisation) between the pre-pass and the main sweep
+      const size_t main_items = static_cast<size_t>(use_pair ? plan2.n_chunks : plan.n_chunks) * n_qb;
+      DEWI_TRY(h->part_s.ensure(main_items * kc * kQueryBlock * 4));
+      DEWI_TRY(h->part_i.ensure(main_items * kc * kQueryBlock * 4));
+    }
+    auto sweep = [&](const TcPlan& p1, const Tc2Plan& p2, int64_t rows, const SweepSeed& sd) -> int {
+      const int chunks = use_pair ? p2.n_chunks : p1.n_chunks;
+      const size_t items = static_cast<size_t>(chunks) * n_qb;
+      DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
+      DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
+      if (use_pair)
+        DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
+                            h->part_i.as<int>(), sd, stream));
+      else
+        DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
+                           h->part_i.as<int>(), sd, stream));
+      h->last_launches++;
+      return 0;
+    };
+    // Threshold seeding: sweep a sample (the first 1/128 of the rows, at least one tile per CTA) first,
+    // recording only each work item's best score per query; the kc-th largest of those maxima (they
+    // belong to distinct rows) is a lower bound of the query's kc-th best score overall, so the main
+    // sweep starts with that admission threshold instead of -inf and its candidate lists see ~kc
+    // entries per CTA instead of ~kc * ln(rows per CTA), with no expensive list warm-up anywhere.
+    // Exactness is unaffected (sweep_epilogue.cuh: seed_threshold).
+    SweepSeed seed;
+    {
+      const int n_tile = use_pair ? 2 * tc2_box_rows() : plan.n_tile;
+      const int64_t tiles_total = ceil_div(h->n, n_tile);
+      const int64_t workers = use_pair ? std::max(1, h->sm_count / 2) : h->sm_count;
+      if (!(flags & DEWI_FLAG_NO_SEED) && tiles_total >= 16 * workers) {
+        const int64_t sample_rows = std::max<int64_t>(workers, tiles_total / 128) * n_tile;
+        TcPlan s1{};
+        Tc2Plan s2{};
+        // the pre-pass is cut into ~4 kc chunks per query block so that the kc-th largest chunk maximum is
+        // a tight bound (at least one tile each)
+        const int want = static_cast<int>(std::min<int64_t>(std::max<int64_t>(workers, 4 * kc), 2048));
+        const int rc = use_pair ? tc2_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s2, want)
+                                : tc_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s1, want);
+        const int s_chunks = use_pair ? s2.n_chunks : s1.n_chunks;
+        if (rc == 0 && s_chunks >= kc && s_chunks <= 2048) {
+          DEWI_TRY(h->seed_max.ensure(static_cast<size_t>(s_chunks) * n_qb * kQueryBlock * 4));
+          DEWI_TRY(h->seed_sim.ensure(static_cast<size_t>(B) * 4));
+          SweepSeed pre;
+          pre.max_out = h->seed_max.as<float>();
+          DEWI_TRY(sweep(s1, s2, sample_rows, pre));
+          DEWI_TRY(launch_seed_from_maxima(h->seed_max.as<float>(), s_chunks, n_qb, B, kc, h->seed_sim.as<float>(), stream));
+          h->last_launches++;
+          seed.values = h->seed_sim.as<float>();
+          seed.stride = 1;
+          seed.off = 0;
+          seed.n_queries = B;
+        }
+      }
+    }
     const int n_chunks = use_pair ? plan2.n_chunks : plan.n_chunks;
-    const size_t items = static_cast<size_t>(n_chunks) * n_qb;
-    DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
-    DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
-    if (use_pair)
-      DEWI_TRY(tc2_launch(plan2, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
-                          h->part_i.as<int>(), stream));
-    else
-      DEWI_TRY(tc_launch(plan, h->map_e0, h->map_e1, mq0, mq1, h->n, dim, n_qb, kc, h->part_s.as<float>(),
-                         h->part_i.as<int>(), stream));
+    DEWI_TRY(sweep(plan, plan2, h->n, seed));
+    h->last_launches--;  // counted once more just below
     h->last_launches++;
     parts.n_chunks = n_chunks;
   } else {

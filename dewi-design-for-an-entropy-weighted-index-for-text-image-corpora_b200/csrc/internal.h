@@ -47,6 +47,14 @@ struct Partials {
   int kc = 0;
 };
 
+// Per-query admission thresholds for a sweep: values[b * stride + off] (device), or none.  A sweep given
+// `max_out` instead runs as the pre-pass: it only records each work item's maximum score per query.
+struct SweepSeed {
+  const float* values = nullptr;
+  int stride = 0, off = 0, n_queries = 0;
+  float* max_out = nullptr;
+};
+
 // ---- tcgen05 sweep (search_tc.cu) ------------------------------------------------------------
 // mode 0: S = Q0.E0 ; mode 1: S = (Q0+Q1).E0 ; mode 2: S = Q0.E0 + Q1.E0 + Q0.E1
 struct TcPlan {
@@ -59,11 +67,11 @@ struct TcPlan {
   size_t smem_bytes;
 };
 int tc_supported(int dim, int64_t n_rows);
-int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan);
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks = 0);
 int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              cudaStream_t stream);
+              const SweepSeed& seed, cudaStream_t stream);
 
 // ---- tcgen05 sweep on CTA pairs, for more than one query block (search_tc2.cu) -----------------
 struct Tc2Plan {
@@ -74,11 +82,11 @@ struct Tc2Plan {
   int grid;
   size_t smem_bytes;
 };
-int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan);
+int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks = 0);
 int tc2_box_rows();
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               cudaStream_t stream);
+               const SweepSeed& seed, cudaStream_t stream);
 
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
                     int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join,
@@ -91,6 +99,8 @@ int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, in
                 int n_chunks, float* part_s, int* part_i, cudaStream_t stream);
 
 // ---- selection / re-rank (select.cu) ---------------------------------------------------------
+// seed[b] = the kc-th largest of query b's per-item maxima [n_chunks][n_qb][128] (-inf when n_chunks < kc)
+int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream);
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
 int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
                    float* cand_sim, cudaStream_t stream);

@@ -49,6 +49,9 @@ struct TcArgs {
   int q_stages;
   float* part_s;
   int* part_i;
+  const float* seed;  // optional admission thresholds from the sample pre-pass (see seed_threshold)
+  int seed_stride, seed_off, n_queries;
+  float* max_out;     // pre-pass mode: [item][128] maximum score per query, no candidate lists
 };
 
 template <int MODE, int N_TILE>
@@ -228,21 +231,24 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
       int t0, t1;
       tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
       l.cnt = 0;
-      l.thr = -INFINITY;
+      l.thr = seed_threshold(a.seed, a.seed_stride, a.seed_off, a.n_queries, item % a.n_qb, qlane);
+      float best = -INFINITY;
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * N_TILE);
         const int row_base = t * N_TILE;
-        scan_tile<N_TILE>(l, kc, tcol, row_base, a.n_rows);
+        if (a.max_out) best = max_tile<N_TILE>(best, tcol, row_base, a.n_rows);
+        else scan_tile<N_TILE>(l, kc, tcol, row_base, a.n_rows);
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&bar_acc_empty[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      flush_item(l, kc, a.part_s + static_cast<size_t>(item) * kc * kQueryBlock + qlane,
-                 a.part_i + static_cast<size_t>(item) * kc * kQueryBlock + qlane);
+      if (a.max_out) a.max_out[static_cast<size_t>(item) * kQueryBlock + qlane] = best;
+      else flush_item(l, kc, a.part_s + static_cast<size_t>(item) * kc * kQueryBlock + qlane,
+                      a.part_i + static_cast<size_t>(item) * kc * kQueryBlock + qlane);
     }
   }
 
@@ -296,7 +302,7 @@ int tc_supported(int dim, int64_t n_rows) {
   return dim % kKBlock == 0 && dim >= kKBlock && dim <= 8192 && n_rows >= 1 && n_rows < (int64_t(1) << 31);
 }
 
-int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan) {
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   const size_t smem_max = 227 * 1024;
   int n_tile = (mode == 2) ? 128 : 256;
@@ -321,6 +327,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   for (int64_t c = want; c <= want + grid && c <= n_tiles; ++c) {
     if ((c * n_qb) % grid == 0) { chunks = c; break; }
   }
+  if (force_chunks > 0) chunks = force_chunks;
   chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
   plan->mode = mode;
   plan->n_tile = n_tile;
@@ -348,7 +355,7 @@ int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim
 
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              cudaStream_t stream) {
+              const SweepSeed& seed, cudaStream_t stream) {
   TcArgs a;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, plan.n_tile));
@@ -361,6 +368,11 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
   a.q_stages = plan.q_stages;
   a.part_s = part_s;
   a.part_i = part_i;
+  a.seed = seed.values;
+  a.seed_stride = seed.stride;
+  a.seed_off = seed.off;
+  a.n_queries = seed.n_queries;
+  a.max_out = seed.max_out;
   if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256>(plan, e0, e1, q0, q1, a, stream);
   if (plan.mode == 0 && plan.n_tile == 128) return launch_one<0, 128>(plan, e0, e1, q0, q1, a, stream);
   if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256>(plan, e0, e1, q0, q1, a, stream);

@@ -44,6 +44,9 @@ struct Tc2Args {
   int q_stages;
   float* part_s;  // [chunk][qb][kc][128]
   int* part_i;
+  const float* seed;  // optional admission thresholds from the sample pre-pass (see seed_threshold)
+  int seed_stride, seed_off, n_queries;
+  float* max_out;     // pre-pass mode: [chunk][qb][128] maximum score per query, no candidate lists
   // EPI_JOIN: thresholded similarity join instead of candidate lists (dewi_join)
   int m_rows;                      // rows of A (the "query" side); rows >= m_rows are padding
   float tau;
@@ -263,14 +266,16 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       int t0, t1;
       tile_range(chunk, a.n_chunks, a.n_tiles, t0, t1);
       l.cnt = 0;
-      l.thr = -INFINITY;
+      l.thr = seed_threshold(a.seed, a.seed_stride, a.seed_off, a.n_queries, qb, qlane);
+      float best = -INFINITY;
       JoinRow jr = {-INFINITY, -1, 0};
       const int i_row = qb * kQueryBlock + qlane;
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * kNTile);
-        if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
+        if (EPI == EPI_TOPK && a.max_out) best = max_tile<kNTile>(best, tcol, t * kNTile, a.n_rows);
+        else if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
         else join_scan_tile<kNTile>(jr, a, i_row, tcol, t * kNTile);
         ptx::tc_fence_before();
         __syncwarp();
@@ -278,7 +283,9 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (EPI == EPI_TOPK) {
+      if (EPI == EPI_TOPK && a.max_out) {
+        a.max_out[(static_cast<size_t>(chunk) * n_qb + qb) * kQueryBlock + qlane] = best;
+      } else if (EPI == EPI_TOPK) {
         const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
         flush_item(l, kc, a.part_s + slot, a.part_i + slot);
       } else if (i_row < a.m_rows) {
@@ -320,7 +327,7 @@ int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 
 }  // namespace
 
-int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan) {
+int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
   const size_t smem_max = 227 * 1024;
@@ -340,6 +347,7 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   for (int64_t c = want; c <= want + clusters && c <= n_tiles; ++c) {
     if ((c * n_qpairs) % clusters == 0) { chunks = c; break; }
   }
+  if (force_chunks > 0) chunks = force_chunks;
   chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
   plan->mode = mode;
   plan->n_stages = stages;
@@ -354,7 +362,7 @@ int tc2_box_rows() { return kHalfRows; }
 
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               cudaStream_t stream) {
+               const SweepSeed& seed, cudaStream_t stream) {
   Tc2Args a;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
@@ -367,6 +375,11 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.q_stages = plan.q_stages;
   a.part_s = part_s;
   a.part_i = part_i;
+  a.seed = seed.values;
+  a.seed_stride = seed.stride;
+  a.seed_off = seed.off;
+  a.n_queries = seed.n_queries;
+  a.max_out = seed.max_out;
   a.m_rows = 0;
   a.tau = 0.f;
   a.self_join = 0;
@@ -404,6 +417,9 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.q_stages = plan.q_stages;
   a.part_s = nullptr;
   a.part_i = nullptr;
+  a.seed = nullptr;
+  a.seed_stride = a.seed_off = a.n_queries = 0;
+  a.max_out = nullptr;
   a.m_rows = static_cast<int>(m_rows);
   a.tau = tau;
   a.self_join = self_join;

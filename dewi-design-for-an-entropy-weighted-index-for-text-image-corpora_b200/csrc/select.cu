@@ -53,8 +53,11 @@ __host__ __device__ inline int next_pow2(int v) {
 }
 
 // ---- merge_select -------------------------------------------------------------------------------
-// Streams the query's n_chunks*kc partial candidates through a shared-memory window, keeping the
-// running best kc_out (sorted).  Window = best list + a batch of new candidates, bitonic-sorted.
+// Streams the query's n_chunks*kc partial candidates through a shared-memory window that holds the
+// running best kc_out (sorted) plus newly admitted candidates.  Only candidates that beat the current
+// kc_out-th best are admitted (block-wide ballot compaction), so after the first window fills and is
+// sorted, later candidates trickle in and the number of bitonic sorts stays at one or two -- and a
+// sweep that ran with seeded thresholds, whose partial lists are mostly empty, needs a single small one.
 constexpr int kWindow = 2048;
 constexpr int kMergeThreads = 1024;  // one compare-exchange per thread per bitonic stage
 
@@ -63,30 +66,59 @@ merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ pa
                     int kc_out, int* __restrict__ cand_idx, float* __restrict__ cand_sim) {
   __shared__ unsigned long long key[kWindow];
   __shared__ int val[kWindow];
+  __shared__ int warp_base[kMergeThreads / 32];
+  __shared__ int fill_s;
   const int b = blockIdx.x;
   const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
   const int total = n_chunks * kc;
-  const int batch = kWindow - kc_out;
-  for (int t = threadIdx.x; t < kc_out; t += blockDim.x) { key[t] = 0ull; val[t] = -1; }
-  for (int base = 0; base < total; base += batch) {
-    const int m = min(batch, total - base);
-    const int p = next_pow2(kc_out + m);
-    for (int t = threadIdx.x; t < p - kc_out; t += blockDim.x) {
-      unsigned long long kk = 0ull;
-      int vv = -1;
-      if (t < m) {
-        const int e = base + t;
-        const int chunk = e / kc, k = e - chunk * kc;
-        const size_t off = ((static_cast<size_t>(chunk) * n_qb + qb) * kc + k) * kQueryBlock + ql;
-        const int idx = part_i[off];
-        if (idx >= 0) { kk = make_key(part_s[off], static_cast<uint32_t>(idx)); vv = idx; }
-      }
-      key[kc_out + t] = kk;
-      val[kc_out + t] = vv;
-    }
-    bitonic_sort_desc(key, val, p);
-  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = threadIdx.x; t < kWindow; t += blockDim.x) { key[t] = 0ull; val[t] = -1; }
+  if (threadIdx.x == 0) fill_s = kc_out;
   __syncthreads();
+  unsigned long long floor_key = 0ull;  // admission bar: the kc_out-th best key so far (0 = any valid key)
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    unsigned long long kk = 0ull;
+    int vv = -1;
+    if (e < total) {
+      const int chunk = e / kc, k = e - chunk * kc;
+      const size_t off = ((static_cast<size_t>(chunk) * n_qb + qb) * kc + k) * kQueryBlock + ql;
+      const int idx = part_i[off];
+      if (idx >= 0) { kk = make_key(part_s[off], static_cast<uint32_t>(idx)); vv = idx; }
+    }
+    const bool pass = kk > floor_key;
+    const unsigned int m = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) warp_base[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 32 warp counts
+      const int c = warp_base[lane];
+      int incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      warp_base[lane] = fill_s + incl - c;
+      if (lane == 31) fill_s += incl;
+    }
+    __syncthreads();
+    if (pass) {
+      const int slot = warp_base[warp] + __popc(m & ((1u << lane) - 1u));
+      key[slot] = kk;   // slot < kWindow: the window is sorted down whenever fewer than blockDim slots remain
+      val[slot] = vv;
+    }
+    __syncthreads();
+    const int fill = fill_s;
+    if (fill > kWindow - static_cast<int>(blockDim.x) || base + static_cast<int>(blockDim.x) >= total) {
+      const int p = next_pow2(fill);
+      bitonic_sort_desc(key, val, p);  // slots [fill, p) hold zeros
+      floor_key = key[kc_out - 1];
+      __syncthreads();
+      for (int t = kc_out + threadIdx.x; t < p; t += blockDim.x) { key[t] = 0ull; val[t] = -1; }
+      if (threadIdx.x == 0) fill_s = kc_out;
+      __syncthreads();
+    }
+  }
   for (int t = threadIdx.x; t < kc_out; t += blockDim.x) {
     const int idx = val[t];
     cand_idx[static_cast<size_t>(b) * kc_out + t] = idx;
@@ -96,6 +128,38 @@ merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ pa
       s = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
     }
     cand_sim[static_cast<size_t>(b) * kc_out + t] = s;
+  }
+}
+
+// ---- seed_from_maxima -----------------------------------------------------------------------------
+// Pre-pass result -> admission thresholds.  Every work item of the pre-pass reported the best score it
+// saw for the query; those maxima belong to distinct corpus rows, so the kc-th largest of them is a
+// lower bound of the query's kc-th best score over the corpus.
+__global__ void __launch_bounds__(kMergeThreads)
+seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb, int kc, float* __restrict__ seed) {
+  __shared__ unsigned long long key[kWindow];
+  __shared__ int val[kWindow];
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
+  const int p = next_pow2(n_chunks);
+  for (int t = threadIdx.x; t < p; t += blockDim.x) {
+    unsigned long long kk = 0ull;
+    if (t < n_chunks) {
+      const float v = maxima[(static_cast<size_t>(t) * n_qb + qb) * kQueryBlock + ql];
+      if (v > -INFINITY) kk = make_key(v, static_cast<uint32_t>(t));
+    }
+    key[t] = kk;
+    val[t] = t;
+  }
+  bitonic_sort_desc(key, val, p);
+  if (threadIdx.x == 0) {
+    const unsigned long long kk = key[kc - 1];
+    float s = -INFINITY;
+    if (kk != 0ull) {
+      const uint32_t o = static_cast<uint32_t>(kk >> 32);
+      s = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+    }
+    seed[b] = s;
   }
 }
 
@@ -248,6 +312,13 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
 }
 
 }  // namespace
+
+int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream) {
+  if (n_chunks < kc || n_chunks > kWindow) return fail("seed_from_maxima: item count outside [kc, 2048]");
+  seed_from_maxima_kernel<<<B, kMergeThreads, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream) {
   if (kc_out > kWindow / 2) return fail("candidate count too large for merge window");

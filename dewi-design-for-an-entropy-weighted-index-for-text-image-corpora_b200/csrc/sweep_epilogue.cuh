@@ -58,6 +58,22 @@ __device__ __forceinline__ void lane_prune(LaneList& l, int kc) {
   }
 }
 
+// Admission threshold seeded from a sample pre-pass (api.cu): `seed[b * stride + off]` is the kc-th best
+// score of query b over a sample of the corpus -- a lower bound of its kc-th best over the whole
+// corpus, so nothing at or above it may be dropped: start just below it (admission is strict `>`).
+// TMEM lane L of block qb holds query qb * 128 + (L % 32) * 4 + L / 32 (inverse of query_lane).
+__device__ __forceinline__ float seed_threshold(const float* seed, int stride, int off, int n_queries, int qb, int qlane) {
+  if (!seed) return -INFINITY;
+  const int b = qb * kQueryBlock + (qlane & 31) * 4 + (qlane >> 5);
+  if (b >= n_queries) return -INFINITY;
+  const float t = seed[static_cast<size_t>(b) * stride + off];
+  if (!(t > -INFINITY)) return -INFINITY;  // fewer than kc sample rows (or NaN): no seed
+  const unsigned int u = __float_as_uint(t);
+  if (t > 0.f) return __uint_as_float(u - 1u);
+  if (t < 0.f) return __uint_as_float(u + 1u);
+  return __uint_as_float(0x80000001u);  // just below zero
+}
+
 // Warp-cooperative prune of ONE lane's list (the steady state, where lanes overflow one at a time):
 // every entry's rank among the `cnt` entries is counted by all 32 lanes together (each lane owns up to
 // two entries and compares them with every entry, read as a shared-memory broadcast), the kc best
@@ -138,6 +154,25 @@ __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, in
       }
     }
   }
+}
+
+// Pre-pass epilogue: only the running maximum of the lane's scores over the item (no lists).
+template <int N_TILE>
+__device__ __forceinline__ float max_tile(float best, uint32_t tcol, int row_base, int n_rows) {
+#pragma unroll 1
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    float v[32];
+    ptx::tmem_ld_32x32(tcol + c * 32, v);
+    const int r0 = row_base + c * 32;
+    if (r0 + 32 > n_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (r0 + j >= n_rows) v[j] = -INFINITY;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) best = fmaxf(best, v[j]);
+  }
+  return best;
 }
 
 // End of a work item: keep the kc best and write them as [k][query] partials.

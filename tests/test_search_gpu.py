@@ -256,3 +256,32 @@ def test_cta_pair_sweep_matches_single_cta_sweep_and_oracle(dtype, b):
     else:
         assert recall_at_k(rid, ids2[:64]) >= 0.999 and recall_at_k(rid, ids1[:64]) >= 0.999
         assert recall_at_k(ids1, ids2) >= 0.999
+
+
+@pytest.mark.parametrize("b", [5, 200])
+def test_seeded_sweep_equals_unseeded_and_oracle(b):
+    """Large corpora run a sample pre-pass that seeds the admission thresholds (DEWI_FLAG_NO_SEED turns
+    it off).  Duplicated rows make exact score ties at the threshold: nothing at the seed may be lost."""
+    n, d, k = 700_000, 64, 10
+    emb, pay = make_corpus(n, d, seed=91)
+    emb[5000:5040] = emb[100]          # 41 identical rows, inside the sample
+    emb[600_000:600_020] = emb[100]    # ... and far outside it
+    queries = np.random.RandomState(92).standard_normal((b, d)).astype(np.float32)
+    queries[0] = emb[100] + 0.01 * queries[0]
+    ix = bulk_index(emb, pay)
+    ent = entropy_column(pay)
+    ids_s, sc_s = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    ids_u, sc_u = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_NO_SEED)
+    np.testing.assert_allclose(sc_s, sc_u, rtol=1e-6)
+    nq = min(b, 12)
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], ent, queries[:nq], k, 0.3, 0.5, True)
+    for q in range(1, nq):
+        check_topk(rid[q], rsc[q], ids_s[q], sc_s[q], what=f"seeded q{q}")
+    # query 0 sits on a 61-way exact tie at the top: the reference keeps an arbitrary 20 of the tied rows
+    # as candidates, so any tied rows are valid -- but they must BE tied rows, with the blended score
+    tied = {100, *range(5000, 5040), *range(600_000, 600_020)}
+    assert set(ids_s[0].tolist()) <= tied and set(ids_u[0].tolist()) <= tied
+    qn = queries[0] / np.linalg.norm(queries[0])
+    for i, s in zip(ids_s[0], sc_s[0]):
+        want = np.float32(0.7) * np.float32(emb[i] @ qn) + np.float32(0.3) * np.float32(pay[i, 0]) + np.float32(0.5) * np.float32(ent[i])
+        assert abs(s - want) <= 1e-5 * max(1.0, abs(want))
