@@ -59,6 +59,8 @@ SIGNATURES = {
     "dewi_index_sweep_ms": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]),
     "dewi_fit_stats": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p]),
     "dewi_score": (c_int, [c_void_p, c_int, c_int64, c_int64, POINTER(c_double), POINTER(c_double), POINTER(c_double), c_int, c_void_p, c_int, c_int, c_void_p]),
+    "dewi_local_weights": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "dewi_cluster_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
 }

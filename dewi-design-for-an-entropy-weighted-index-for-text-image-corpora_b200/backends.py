@@ -364,6 +364,24 @@ class CudaIndex(BaseIndex):
                                                            dh, _native.stream_ptr()))
             torch.cuda.current_stream().synchronize()
 
+    def set_payload_from_signals(self, signals, scorer, fit: bool = True, offset: int = 0):
+        """Bulk form of the README loop (README.md:94-110; pipelines.py:199-221): `signals` is a `[7, n]`
+        array / tensor in `SIGNAL_FIELDS` order for rows `[offset, offset + n)`.  Fits the scorer's robust
+        statistics (unless `fit=False`), scores every row on the device and writes `dewi` and
+        `(ht_mean + hi_mean) * 0.5` straight into the device payload columns -- no per-document Python.
+        Returns the dewi scores (CUDA float32 tensor)."""
+        torch = _torch()
+        sig = torch.as_tensor(signals).to(torch.device("cuda", self.device), torch.float32)
+        if sig.ndim != 2 or sig.shape[0] != 7:
+            raise ValueError("expected seven signal columns")
+        self._flush_pending()
+        if fit:
+            scorer.fit_stats_columns(sig)
+        dewi = scorer.score_batch(sig)
+        ent = ((sig[0].double() + sig[2].double()) * 0.5).float()  # backends.py:458
+        self.set_payload_columns(dewi, ent, offset=offset)
+        return dewi
+
     def reserve(self, rows: int) -> None:
         """Pre-size the device planes for `rows` rows (one allocation instead of geometric regrowth)."""
         torch = _torch()

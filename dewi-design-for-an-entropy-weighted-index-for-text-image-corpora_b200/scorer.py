@@ -31,8 +31,10 @@ def _device_index(device: Optional[int]) -> int:
     return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
 
-def _fit_columns(cols, device: int):
-    """cols: CUDA float32 tensor [F, N] (row c = one signal column).  Returns (med[F], mad[F]) as float64 arrays."""
+def _fit_columns(cols, device: int, zero_mad_as: float = 1e-8):
+    """cols: CUDA float32 tensor [F, N] (row c = one signal column).  Returns (med[F], mad[F]) as float64
+    arrays.  The library reports a zero MAD as 1e-8 (scorer.py:24); `zero_mad_as` maps it back for callers
+    with a different rule (robust.py:8-10 adds 1e-8 instead)."""
     torch = _torch()
     lib = _native.load_library()
     f, n = cols.shape
@@ -42,7 +44,10 @@ def _fit_columns(cols, device: int):
         rc = lib.dewi_fit_stats(ctypes.c_void_p(cols.data_ptr()), n, f, cols.stride(0), med, mad, device,
                                 _native.stream_ptr())
     _native.check(rc)
-    return np.array(med[:], dtype=np.float64), np.array(mad[:], dtype=np.float64)
+    mad_arr = np.array(mad[:], dtype=np.float64)
+    if zero_mad_as != 1e-8:
+        mad_arr[mad_arr == 1e-8] = zero_mad_as  # a float32 MAD is never 1e-8 exactly unless it was zero
+    return np.array(med[:], dtype=np.float64), mad_arr
 
 
 @dataclass

@@ -145,6 +145,16 @@ DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int
               float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
               int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
 
+/* ---- neighbours of the path that reuse its kernels -------------------------- */
+/* local_weights_from_surprisal (src/dewi/local_weights.py:5-26): float32 median / MAD (+1e-8), z-score,
+ * clip to +-5, softplus.  `s` and `out` are n floats on the device; the call synchronises the stream.  */
+DEWI_API int dewi_local_weights(const float* s, int64_t n, float* out, int device, void* stream);
+/* Connected components of a pair list (e.g. the join's near-duplicate pairs) over documents 0..n-1:
+ * labels[i] = smallest document index of i's cluster.  The clusters are what metrics.duplicate_rate /
+ * cluster_coverage consume (src/dewi/metrics.py:173-212).  Synchronises the stream.                    */
+DEWI_API int dewi_cluster_pairs(const int64_t* pair_i, const int64_t* pair_j, int64_t n_pairs, int64_t n, int32_t* labels,
+                       int device, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,53 @@ def redundancy_case(name, t, i, d, seed):
     return {"case": name, "t": t, "i": i, "d": d, "oracle_vs_torch_maxabs": err}
 
 
+def extras_case():
+    """robust.RobustStats.from_payloads / .z and local_weights_from_surprisal of the reference."""
+    from dewi.local_weights import local_weights_from_surprisal
+    from dewi.robust import RobustStats as PayloadStats
+
+    rng = np.random.RandomState(51)
+    pay = synth_payload_columns(rng, 777, "profile")
+    payloads = [Payload(**{f: float(pay[i, j]) for j, f in enumerate(PAYLOAD_FIELDS)}) for i in range(len(pay))]
+    st = PayloadStats.from_payloads(payloads)
+    keys = ["ht_mean", "hi_mean", "redundancy", "noise"]
+    probe = {k: float(np.float32(pay[5, PAYLOAD_FIELDS.index(k)])) for k in keys}
+    surpr = np.concatenate([rng.gamma(2.0, 1.5, 4099), [0.0, 50.0, -3.0]]).astype(np.float32)
+    const = np.full(17, 2.5, np.float32)  # MAD == 0 path
+    np.savez_compressed(
+        GOLD / "extras_robust_localweights.npz", payload=pay,
+        med=np.array([st.fields[k][0] for k in keys]), mad=np.array([st.fields[k][1] for k in keys]),
+        probe=np.array([probe[k] for k in keys]), z=np.array([st.z(k, probe[k]) for k in keys]),
+        surprisal=surpr, weights=local_weights_from_surprisal(surpr),
+        const=const, const_weights=local_weights_from_surprisal(const),
+    )
+    return {"case": "extras_robust_localweights"}
+
+
+def saved_index_case():
+    """A directory written by the reference's own DewiIndex.save (index.py:121-141 -> ExactIndex.save,
+    backends.py:483-515), to be loaded by the CUDA backend."""
+    import shutil
+
+    rng = np.random.RandomState(61)
+    n, d, k = 40, 16, 5
+    emb = rng.randn(n, d).astype(np.float32)
+    pay = synth_payload_columns(rng, n, "profile")
+    ref = DewiIndex(dim=d, space="cosine", use_ann=False, rerank_eta=0.3, entropy_pref=0.5)
+    for i in range(n):
+        ref.add(f"doc_{i:03d}", emb[i], Payload(**{f: float(pay[i, j]) for j, f in enumerate(PAYLOAD_FIELDS)}),
+                meta={"source": f"file_{i}.txt"})
+    ref.build()
+    out = GOLD / "reference_saved_index"
+    shutil.rmtree(out, ignore_errors=True)
+    ref.save(out)
+    q = rng.randn(3, d).astype(np.float32)
+    res = [ref.search(q[i], k=k) for i in range(3)]
+    np.savez_compressed(GOLD / "reference_saved_index_queries.npz", queries=q,
+                        ids=np.array([[r[0] for r in rr] for rr in res]), scores=np.array([[r[1] for r in rr] for rr in res]))
+    return {"case": "reference_saved_index", "n": n, "d": d}
+
+
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
     grid_full = [(e, p) for e in (0.0, 0.25, 0.5, 1.0) for p in (-1.0, 0.0, 0.5, 1.0)]
@@ -185,6 +232,8 @@ def main() -> None:
     m.append(scorer_degenerate())
     m.append(redundancy_case("t37_i53_d512", 37, 53, 512, 31))
     m.append(redundancy_case("t64_i64_d64", 64, 64, 64, 32))
+    m.append(extras_case())
+    m.append(saved_index_case())
     (GOLD / "MANIFEST.json").write_text(json.dumps(manifest, indent=1))
     print(json.dumps(manifest, indent=1))
 

@@ -18,8 +18,9 @@ SCORER_CASES = ["readme_n1001", "readme_n1000", "profile_n4096"]
 
 def test_manifest_lists_every_fixture():
     man = json.loads((GOLD / "MANIFEST.json").read_text())
-    assert len(man["cases"]) == 12
-    assert len(list(GOLD.glob("*.npz"))) == 12
+    assert len(man["cases"]) == 14
+    assert len(list(GOLD.glob("*.npz"))) == 14
+    assert (GOLD / "reference_saved_index" / "ann_index" / "embeddings.npy").exists()
 
 
 @pytest.mark.parametrize("name", SEARCH_CASES)
