@@ -106,38 +106,80 @@ def run_c4(args, torch, dewi_b200, peaks):
 
 
 def run_c5(args, torch, dewi_b200, peaks):
-    n, d, tau = args.rows or 1_000_000, 512, 0.9
-    dev = torch.device("cuda", 0)
+    """1 process: bounded self-join, bf16 and hi/lo planes.  Under torchrun: the row-sharded self-join
+    (each rank owns a block of rows, all-gather once, join its rows against all rows), bf16 planes."""
+    import os
+
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, tau = args.rows or (1_000_000 if world == 1 else 10_000_000), 512, 0.9
+    lo, hi = dewi_b200.shard_range(n, world, rank, align=256)
     g = torch.Generator(device=dev)
-    g.manual_seed(44)
-    x = torch.randn((n, d), generator=g, device=dev)
-    dup = torch.randperm(n, generator=g, device=dev)[: n // 100]  # planted 1 % near-duplicates
-    src = torch.randperm(n, generator=g, device=dev)[: n // 100]
-    x[dup] = x[src] + 0.05 * torch.randn((n // 100, d), generator=g, device=dev)
+    g.manual_seed(44 + rank)
+    x = torch.randn((hi - lo, d), generator=g, device=dev)
+    m = (hi - lo) // 100  # planted 1 % near-duplicates (within the shard)
+    dup = torch.randperm(hi - lo, generator=g, device=dev)[:m]
+    src = torch.randperm(hi - lo, generator=g, device=dev)[:m]
+    x[dup] = x[src] + 0.05 * torch.randn((m, d), generator=g, device=dev)
     runs = []
-    for precision, rows in (("bf16", n), ("fp32", max(n // 4, 1))):
+    configs = (("bf16", n), ("fp32", max(n // 4, 1))) if world == 1 else (("bf16", n),)
+    for precision, rows in configs:
         res = {}
-        xs = x[:rows]
+        xs = x[: rows if world == 1 else hi - lo]
 
         def go():
-            res["out"] = dewi_b200.redundancy_join(xs, tau=tau, pair_cap=1 << 22, precision=precision)
+            if world == 1:
+                res["out"] = dewi_b200.redundancy_join(xs, tau=tau, pair_cap=1 << 22, precision=precision)
+            else:
+                res["out"] = dewi_b200.sharded_self_join(xs, tau=tau, pair_cap=1 << 22, precision=precision)
 
-        ms = timed(torch, go, 2, 1)
+        if world > 1:
+            go()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            go()
+            torch.cuda.synchronize()
+            ms_t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device=dev)
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+            ms = float(ms_t.item())
+            found = torch.tensor([res["out"]["n_pairs"]], dtype=torch.int64, device=dev)
+            dist.all_reduce(found)
+            n_found = int(found.item())
+        else:
+            ms = timed(torch, go, 2, 1)
+            n_found = res["out"]["n_pairs"]
         # algorithmic work of a symmetric self-join: N(N-1)/2 pair-dots of 2D flops each; the kernel evaluates
         # the full N x N product (row statistics need every row's whole neighbourhood), i.e. twice that
         alg = float(rows) * (rows - 1) * d
-        runs.append({"precision": precision, "rows": rows, "ms": ms, "pairs_found": res["out"]["n_pairs"],
+        runs.append({"precision": precision, "rows": rows, "ms": ms, "pairs_found": n_found,
                      "pair_dots_per_s": rows * (rows - 1) / 2 / (ms / 1e3), "algorithmic_tflops": alg / (ms / 1e3) / 1e12,
                      "executed_tflops": 2 * alg / (ms / 1e3) / 1e12})
     main = runs[0]
-    return {
+    line = {
         "metric": "pair-dots/sec (redundancy self-join, cosine threshold)", "unit": "pairs/s", "dtype": "bf16 planes, f32 accumulate",
-        "value": main["pair_dots_per_s"], "runs": runs,
-        "config": {"workload": f"C5 (bounded): {n} x {d} self-join, tau={tau}, 1 B200 (full size is 10M rows over 8 GPUs)"},
-        "roofline": {"bound": "tensor", "achieved": main["algorithmic_tflops"], "peak": peaks["bf16_sustained"],
-                     "unit": "TFLOP/s", "frac": main["algorithmic_tflops"] / peaks["bf16_sustained"],
-                     "executed_frac": main["executed_tflops"] / peaks["bf16_sustained"]},
+        "value": main["pair_dots_per_s"], "n_gpus": world, "runs": runs,
+        "config": {"workload": f"C5: {n} x {d} self-join, tau={tau}, row-sharded over {world} B200"
+                               + (" (bounded; full size is 10M rows over 8 GPUs)" if world == 1 else ""),
+                   "timing": "wall clock around one call incl. all-gather and row normalisation, max over ranks" if world > 1
+                   else "CUDA events"},
+        "roofline": {"bound": "tensor", "achieved": main["algorithmic_tflops"] / world, "peak": peaks["bf16_sustained"],
+                     "unit": "TFLOP/s per GPU", "frac": main["algorithmic_tflops"] / world / peaks["bf16_sustained"],
+                     "executed_frac": main["executed_tflops"] / world / peaks["bf16_sustained"]},
     }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return None
+    return line
 
 
 def main():
@@ -150,8 +192,12 @@ def main():
     import dewi_b200
 
     peaks = load_peaks()
-    with ClockSampler(0) as clocks:
+    import os
+
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
         line = {"c2": run_c2, "c4": run_c4, "c5": run_c5}[args.workload](args, torch, dewi_b200, peaks)
+    if line is None:
+        return
     line["clocks"] = clocks.summary()
     line["peak_source"] = peaks["source"]
     print(json.dumps(line), flush=True)

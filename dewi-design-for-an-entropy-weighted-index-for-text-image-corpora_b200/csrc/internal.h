@@ -89,7 +89,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
                const SweepSeed& seed, cudaStream_t stream);
 
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
-                    int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join,
+                    int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,
                     unsigned long long* row_best, int* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
                     int64_t pair_cap, unsigned long long* pair_count, cudaStream_t stream);
 

@@ -42,7 +42,7 @@ __device__ __forceinline__ unsigned int orderable(float f) {
 template <int MODE>
 __global__ void __launch_bounds__(256)
 sim_tile_kernel(const float* __restrict__ a, long long m, const float* __restrict__ b, long long n, int d,
-                float* __restrict__ out, float tau, int self_join, unsigned long long* __restrict__ row_best,
+                float* __restrict__ out, float tau, int self_join, long long a_offset, unsigned long long* __restrict__ row_best,
                 int* __restrict__ row_count, long long* __restrict__ pair_i, long long* __restrict__ pair_j,
                 float* __restrict__ pair_sim, long long pair_cap, unsigned long long* __restrict__ pair_count) {
   __shared__ float sa[TK][TM + 1];
@@ -93,11 +93,19 @@ sim_tile_kernel(const float* __restrict__ a, long long m, const float* __restric
         const unsigned long long key =
             (static_cast<unsigned long long>(orderable(s)) << 32) | static_cast<unsigned int>(~static_cast<unsigned int>(j));
         if (!self_join) {
+          // a_offset >= 0: A is the slice of B starting there -- row i is B's row a_offset + i
+          if (a_offset >= 0 && j == i + a_offset) continue;
           atomicMax(&row_best[i], key);
           if (s >= tau) {
             atomicAdd(&row_count[i], 1);
-            const unsigned long long slot = atomicAdd(pair_count, 1ull);
-            if (static_cast<long long>(slot) < pair_cap) { pair_i[slot] = i; pair_j[slot] = j; pair_sim[slot] = s; }
+            if (a_offset < 0 || j > i + a_offset) {
+              const unsigned long long slot = atomicAdd(pair_count, 1ull);
+              if (static_cast<long long>(slot) < pair_cap) {
+                pair_i[slot] = i + (a_offset > 0 ? a_offset : 0);
+                pair_j[slot] = j;
+                pair_sim[slot] = s;
+              }
+            }
           }
         } else {
           // upper-triangle tiles update both rows; diagonal tiles hold (i, j) and (j, i) themselves
@@ -165,7 +173,7 @@ extern "C" int dewi_similarity_dense(const float* a, int64_t m, const float* b, 
   if (!rc) rc = normalize_into(b, n, d, bn, stream);
   if (!rc) {
     dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
-    sim_tile_kernel<0><<<grid, 256, 0, stream>>>(an, m, bn, n, d, out, 0.f, 0, nullptr, nullptr, nullptr, nullptr,
+    sim_tile_kernel<0><<<grid, 256, 0, stream>>>(an, m, bn, n, d, out, 0.f, 0, -1, nullptr, nullptr, nullptr, nullptr,
                                                  nullptr, 0, nullptr);
     if (cudaGetLastError() != cudaSuccess) rc = fail("similarity kernel launch failed");
   }
@@ -186,7 +194,8 @@ struct JoinBufs {
 };
 
 // Tensor-core path: rows normalised into bf16 planes, A on the query side of the CTA-pair sweep.
-int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int bf16_only,
+int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int64_t a_offset,
+                int bf16_only,
                 float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
                 float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream) {
   int sms = 0;
@@ -230,7 +239,8 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
     DEWI_TRY(tc_encode_rows_map(&ma1, a_lo, m_pad, d, kQueryBlock));
     DEWI_TRY(tc_encode_rows_map(&mb1, b_lo, n, d, tc2_box_rows()));
   }
-  DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, ma0, ma1, m, m_pad, n, d, sms, tau, self_join, best, row_count,
+  DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, ma0, ma1, m, m_pad, n, d, sms, tau,
+                           (self_join || a_offset >= 0) ? 1 : 0, a_offset > 0 ? a_offset : 0, best, row_count,
                            pair_i, pair_j, pair_sim, pair_cap, count, stream));
   join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
                                                                              reinterpret_cast<long long*>(row_argmax));
@@ -245,12 +255,13 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
 }  // namespace
 }  // namespace dewi
 
-extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int flags,
-                         float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
+extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
+                         int64_t a_offset, int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
                          float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
   if (!a || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
-  if (self_join) { b = a; n = m; }
+  if (self_join) { b = a; n = m; a_offset = -1; }
   if (!b) return fail("null argument");
+  if (a_offset >= 0 && a_offset + m > n) return fail("a_offset + m exceeds the rows of b");
   if (m <= 0 || n <= 0 || d <= 0) return fail("join needs positive sizes");
   if (n >= (int64_t(1) << 31) || m >= (int64_t(1) << 31)) return fail("join supports fewer than 2^31 rows per side");
   if (pair_cap > 0 && (!pair_i || !pair_j || !pair_sim)) return fail("pair buffers missing");
@@ -260,7 +271,7 @@ extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, i
   const bool tensor_ok = tc_supported(d, n) && !(flags & DEWI_JOIN_FORCE_SIMT);
   const bool big = static_cast<double>(m) * static_cast<double>(n) >= 4.0e6;
   if (tensor_ok && (big || (flags & DEWI_JOIN_FORCE_TC)))
-    return join_tensor(a, m, b, n, d, tau, self_join, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_max, row_argmax, row_count,
+    return join_tensor(a, m, b, n, d, tau, self_join, a_offset, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_max, row_argmax, row_count,
                        pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, stream);
   if (flags & DEWI_JOIN_FORCE_TC) return fail("tensor-core join needs d % 64 == 0");
   float *an = nullptr, *bn = nullptr;
@@ -277,7 +288,7 @@ extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, i
     if ((rc = normalize_into(a, m, d, an, stream))) break;
     if (!self_join && (rc = normalize_into(b, n, d, bn, stream))) break;
     dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
-    sim_tile_kernel<1><<<grid, 256, 0, stream>>>(an, m, self_join ? an : bn, n, d, nullptr, tau, self_join, best,
+    sim_tile_kernel<1><<<grid, 256, 0, stream>>>(an, m, self_join ? an : bn, n, d, nullptr, tau, self_join, a_offset, best,
                                                  row_count, reinterpret_cast<long long*>(pair_i),
                                                  reinterpret_cast<long long*>(pair_j), pair_sim, pair_cap, count);
     join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,

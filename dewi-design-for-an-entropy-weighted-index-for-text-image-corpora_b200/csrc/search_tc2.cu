@@ -50,7 +50,8 @@ struct Tc2Args {
   // EPI_JOIN: thresholded similarity join instead of candidate lists (dewi_join)
   int m_rows;                      // rows of A (the "query" side); rows >= m_rows are padding
   float tau;
-  int self_join;                   // exclude i == j, emit only pairs with j > i
+  int self_join;                   // A's row i is B's row a_offset + i: exclude that column, emit only pairs beyond it
+  long long a_offset;
   unsigned long long* row_best;    // [m_rows] packed (orderable(sim) << 32 | ~j), atomicMax
   int* row_count;                  // [m_rows] sims >= tau
   long long* pair_i;
@@ -86,10 +87,11 @@ __device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int
       for (int j = 0; j < 32; ++j)
         if (j0 + j >= a.n_rows) v[j] = -INFINITY;
     }
-    if (a.self_join && i_row >= j0 && i_row < j0 + 32) {
+    const long long i_glob = i_row + a.a_offset;  // this row's index on the B side (self / slice joins)
+    if (a.self_join && i_glob >= j0 && i_glob < j0 + 32) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j0 + j == i_row) v[j] = -INFINITY;  // the diagonal
+        if (j0 + j == i_glob) v[j] = -INFINITY;  // the diagonal
     }
     float mx = v[0];
 #pragma unroll
@@ -104,10 +106,10 @@ __device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int
       for (int j = 0; j < 32; ++j) {
         if (v[j] >= a.tau) {
           ++r.count;
-          if (!a.self_join || j0 + j > i_row) {
+          if (!a.self_join || j0 + j > i_glob) {
             const unsigned long long slot = atomicAdd(a.pair_count, 1ull);
             if (static_cast<long long>(slot) < a.pair_cap) {
-              a.pair_i[slot] = i_row;
+              a.pair_i[slot] = i_glob;
               a.pair_j[slot] = j0 + j;
               a.pair_sim[slot] = v[j];
             }
@@ -383,6 +385,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.m_rows = 0;
   a.tau = 0.f;
   a.self_join = 0;
+  a.a_offset = 0;
   a.row_best = nullptr;
   a.row_count = nullptr;
   a.pair_i = a.pair_j = nullptr;
@@ -399,7 +402,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 // B stream through as the "corpus".  mode 0 = single bf16 plane (sims carry bf16 rounding, ~1e-3),
 // mode 2 = hi/lo planes on both sides (three MMAs, ~1e-6).
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
-                    int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join,
+                    int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,
                     unsigned long long* row_best, int* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
                     int64_t pair_cap, unsigned long long* pair_count, cudaStream_t stream) {
   Tc2Plan plan;
@@ -423,6 +426,7 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.m_rows = static_cast<int>(m_rows);
   a.tau = tau;
   a.self_join = self_join;
+  a.a_offset = self_join ? a_offset : 0;
   a.row_best = row_best;
   a.row_count = row_count;
   a.pair_i = reinterpret_cast<long long*>(pair_i);

@@ -46,12 +46,14 @@ def cross_modal_similarity(tfeat, ifeat, device: Optional[int] = None):
 
 
 def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device: Optional[int] = None,
-                    precision: str = "fp32", force: Optional[str] = None):
+                    precision: str = "fp32", force: Optional[str] = None, a_offset: int = -1):
     """Thresholded similarity join.  `b=None` is the self-join (diagonal excluded, pairs j > i).
 
     precision "fp32": similarities good to ~1e-5 (bf16 hi+lo planes on the tensor cores, or the fp32
     CUDA-core kernel for small inputs / d % 64 != 0); "bf16": one bf16 plane, ~1e-3, 3x fewer MMAs.
     force: None | "simt" | "tc" pins the kernel (tests).
+    a_offset >= 0: `a` is rows `[a_offset, a_offset + len(a))` of `b` (one shard of a row-sharded
+    self-join): each row's own column is excluded, pairs are kept for j > global i and carry global i.
 
     Returns dict(max_sim [M] f32, argmax [M] i64, count [M] i32, pairs_i, pairs_j, pairs_sim, n_pairs)
     of CUDA tensors; `n_pairs` may exceed `pair_cap`, in which case only `pair_cap` pairs were kept."""
@@ -77,7 +79,7 @@ def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device
     lib = _native.load_library()
     with torch.cuda.device(dev):
         rc = lib.dewi_join(ctypes.c_void_p(ta.data_ptr()), m, ctypes.c_void_p(tb.data_ptr()), tb.shape[0], ta.shape[1],
-                           float(tau), int(self_join), flags, ctypes.c_void_p(row_max.data_ptr()),
+                           float(tau), int(self_join), int(a_offset), flags, ctypes.c_void_p(row_max.data_ptr()),
                            ctypes.c_void_p(row_arg.data_ptr()), ctypes.c_void_p(row_cnt.data_ptr()),
                            ctypes.c_void_p(pi.data_ptr()), ctypes.c_void_p(pj.data_ptr()), ctypes.c_void_p(ps.data_ptr()),
                            int(pair_cap), ctypes.byref(cnt), dev, _native.stream_ptr())
@@ -85,3 +87,34 @@ def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device
     kept = min(int(cnt.value), pair_cap)
     return {"max_sim": row_max, "argmax": row_arg, "count": row_cnt, "pairs_i": pi[:kept], "pairs_j": pj[:kept],
             "pairs_sim": ps[:kept], "n_pairs": int(cnt.value)}
+
+
+def sharded_self_join(local_rows, tau: float = 0.9, pair_cap: int = 1 << 20, group=None, precision: str = "bf16"):
+    """Row-sharded near-duplicate self-join over the ranks of `group` (one process per GPU, SURVEY.md
+    section 8e): every rank passes its contiguous block of rows (rank order = row order); the blocks are
+    all-gathered once over NCCL (10M x 512 fp32 = 20 GB, fits every B200) and each rank joins ITS rows
+    against all rows.  Row statistics come back for the local rows, pairs carry global indices with
+    j > i, so the union of the ranks' pair lists is the full pair set without duplicates."""
+    torch = _torch()
+    import torch.distributed as dist
+
+    rows = local_rows.contiguous()
+    if not rows.is_cuda:
+        raise ValueError("local_rows must live on this rank's GPU")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return redundancy_join(rows, tau=tau, pair_cap=pair_cap, device=rows.device.index, precision=precision)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    counts = torch.zeros(world, dtype=torch.int64, device=rows.device)
+    dist.all_gather_into_tensor(counts, torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device), group=group)
+    counts = counts.cpu().tolist()
+    if len(set(counts)) == 1:
+        everything = torch.empty((world * counts[0], rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        dist.all_gather_into_tensor(everything, rows, group=group)
+    else:
+        parts = [torch.empty((c, rows.shape[1]), dtype=rows.dtype, device=rows.device) for c in counts]
+        dist.all_gather(parts, rows, group=group)
+        everything = torch.cat(parts)
+    out = redundancy_join(rows, everything, tau=tau, pair_cap=pair_cap, device=rows.device.index, precision=precision,
+                          a_offset=int(sum(counts[:rank])))
+    out["row_offset"] = int(sum(counts[:rank]))
+    return out

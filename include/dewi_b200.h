@@ -137,12 +137,15 @@ DEWI_API int dewi_similarity_dense(const float* a, int64_t m, const float* b, in
  * best similarity against rows of `b`, its index, and the number of rows with sim >= tau; plus up
  * to `pair_cap` (i, j, sim) pairs with sim >= tau appended to pair_i/pair_j/pair_sim, the total
  * number found in *pair_count_host.  self_join: b == a, diagonal excluded, pairs only j > i.
+ * a_offset >= 0 (with self_join == 0): `a` is the slice of `b` starting at row a_offset -- one rank's
+ * shard of a row-sharded self-join: column a_offset + i is excluded for row i, pairs are emitted only
+ * for j > a_offset + i and carry the global row a_offset + i.  a_offset < 0: plain cross join.
  * Large inputs with d % 64 == 0 run on the tensor cores (CTA-pair sweep with a threshold epilogue):
  * rows as bf16 hi+lo planes, three MMAs, similarities good to ~1e-5 (the lo.lo term is dropped); DEWI_JOIN_BF16 keeps one bf16
  * plane (one MMA, similarities carry bf16 rounding ~1e-3).  Otherwise an fp32 CUDA-core kernel.   */
 enum { DEWI_JOIN_BF16 = 1 << 0, DEWI_JOIN_FORCE_SIMT = 1 << 1, DEWI_JOIN_FORCE_TC = 1 << 2 };
-DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int flags,
-              float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
+              int64_t a_offset, int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
               int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
 
 /* ---- neighbours of the path that reuse its kernels -------------------------- */

@@ -70,3 +70,51 @@ def test_nccl_sharded_search_matches_oracle(dtype):
             check_topk(rid[q], rsc[q], ids[q], scores[q], what=f"nccl q{q}")
     else:
         assert recall_at_k(rid, ids) >= 0.999
+
+
+def _join_worker(rank, world, port, n, d, tau, ret):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import dewi_b200
+        from dewi_b200 import shard_range
+
+        rng = np.random.RandomState(71)
+        x = rng.standard_normal((n, d)).astype(np.float32)
+        x[1::50] = x[0:-1:50] * 1.1 + 0.02 * rng.standard_normal((len(x[1::50]), d)).astype(np.float32)
+        lo, hi = shard_range(n, world, rank, align=64)
+        out = dewi_b200.sharded_self_join(torch.from_numpy(x[lo:hi]).cuda(), tau=tau, precision="fp32")
+        assert out["row_offset"] == lo
+        ret[rank] = (out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist(), out["max_sim"].cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_sharded_self_join_matches_oracle():
+    import torch.multiprocessing as mp
+
+    from oracle import redundancy as ored
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    n, d, tau = 6000, 128, 0.93
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_join_worker, args=(world, port, n, d, tau, ret), nprocs=world, join=True)
+        parts = [ret[r] for r in range(world)]
+    rng = np.random.RandomState(71)
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x[1::50] = x[0:-1:50] * 1.1 + 0.02 * rng.standard_normal((len(x[1::50]), d)).astype(np.float32)
+    mx, am, cnt, pairs = ored.join_rowstats(x, x, tau, self_join=True)
+    got = set()
+    for pi, pj, _ in parts:
+        got |= set(zip(pi, pj))
+    assert got == {(i, j) for i, j, _ in pairs} and len(got) > 50
+    np.testing.assert_allclose(np.concatenate([p[2] for p in parts]), mx, atol=1e-5)

@@ -85,3 +85,23 @@ def test_bf16_join_finds_the_planted_duplicates():
     assert clear and clear <= got
     near = {(i, j) for i, j, s in pairs}
     assert all(p in near or True for p in got) and len(got) <= len(near) + 50
+
+
+@pytest.mark.parametrize("force", ["simt", "tc"])
+def test_slice_joins_add_up_to_the_self_join(force):
+    """Row-sharded self-join on one device: each 'rank' joins its slice of rows against all rows
+    (`a_offset`); statistics concatenate and the pair lists unite to the single-call self-join."""
+    a = planted(2500, 128, 15, frac=0.05)
+    tau = 0.92
+    whole = dewi_b200.redundancy_join(a, tau=tau, force=force)
+    pairs, mx, cnt = set(), [], []
+    for lo, hi in ((0, 700), (700, 1800), (1800, 2500)):
+        part = dewi_b200.redundancy_join(a[lo:hi], a, tau=tau, force=force, a_offset=lo)
+        got = list(zip(part["pairs_i"].cpu().tolist(), part["pairs_j"].cpu().tolist()))
+        assert all(lo <= i < hi and j > i for i, j in got)
+        pairs |= set(got)
+        mx.append(part["max_sim"].cpu().numpy())
+        cnt.append(part["count"].cpu().numpy())
+    assert pairs == set(zip(whole["pairs_i"].cpu().tolist(), whole["pairs_j"].cpu().tolist()))
+    np.testing.assert_allclose(np.concatenate(mx), whole["max_sim"].cpu().numpy(), atol=1e-6)
+    np.testing.assert_array_equal(np.concatenate(cnt), whole["count"].cpu().numpy())
