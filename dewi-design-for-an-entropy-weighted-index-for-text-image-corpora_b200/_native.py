@@ -25,6 +25,7 @@ FLAG_PRECISE_QUERY = 1 << 4
 FLAG_SCOPE_FULL = 1 << 5
 FLAG_NO_PAIR = 1 << 6
 FLAG_NO_SEED = 1 << 7
+FLAG_NO_M64 = 1 << 8
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2

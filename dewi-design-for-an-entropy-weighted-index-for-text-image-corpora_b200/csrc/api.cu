@@ -353,8 +353,10 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
       use_pair = false;
     }
   }
+  // at most 64 queries: M = 64 MMAs (half the tensor work / power and half the query re-stream)
+  const int q_rows = (B <= 64 && !(flags & DEWI_FLAG_NO_M64)) ? 64 : kQueryBlock;
   if (use_tc && !use_pair) {
-    if (tc_make_plan(mode, dim, h->n, n_qb, kc, h->sm_count, &plan) != 0) {
+    if (tc_make_plan(mode, dim, h->n, n_qb, kc, h->sm_count, &plan, 0, q_rows) != 0) {
       if (flags & DEWI_FLAG_FORCE_TC) return 1;
       use_tc = false;
     }
@@ -368,7 +370,7 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   DEWI_TRY(h->q1.ensure(static_cast<size_t>(b_pad) * dim * 2));
   const int qnorm = (h->space == DEWI_SPACE_COSINE && !(flags & DEWI_FLAG_QUERY_NORMALIZED)) ? 1 : 0;
   DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
-                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/1));
+                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/(use_tc && !use_pair && q_rows == 64) ? 2 : 1));
   h->last_launches++;
 
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
@@ -380,8 +382,9 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
   if (use_tc) {
     DEWI_TRY(ensure_corpus_maps(h, use_pair ? tc2_box_rows() : plan.n_tile));
     CUtensorMap mq0, mq1;
-    DEWI_TRY(tc_encode_rows_map(&mq0, h->q0.p, b_pad, dim, kQueryBlock));
-    DEWI_TRY(tc_encode_rows_map(&mq1, h->q1.p, b_pad, dim, kQueryBlock));
+    const int q_box = use_pair ? kQueryBlock : plan.q_rows;
+    DEWI_TRY(tc_encode_rows_map(&mq0, h->q0.p, b_pad, dim, q_box));
+    DEWI_TRY(tc_encode_rows_map(&mq1, h->q1.p, b_pad, dim, q_box));
     {  // size the partial-list buffers for the main sweep up front: growing them later would cudaFree
        // (a device-wide synchronisation) between the pre-pass and the main sweep
       const size_t main_items = static_cast<size_t>(use_pair ? plan2.n_chunks : plan.n_chunks) * n_qb;
@@ -421,7 +424,7 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
         // a tight bound (at least one tile each)
         const int want = static_cast<int>(std::min<int64_t>(std::max<int64_t>(workers, 4 * kc), 2048));
         const int rc = use_pair ? tc2_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s2, want)
-                                : tc_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s1, want);
+                                : tc_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s1, want, q_rows);
         const int s_chunks = use_pair ? s2.n_chunks : s1.n_chunks;
         if (rc == 0 && s_chunks >= kc && s_chunks <= 2048) {
           DEWI_TRY(h->seed_max.ensure(static_cast<size_t>(s_chunks) * n_qb * kQueryBlock * 4));

@@ -59,6 +59,7 @@ struct SweepSeed {
 // mode 0: S = Q0.E0 ; mode 1: S = (Q0+Q1).E0 ; mode 2: S = Q0.E0 + Q1.E0 + Q0.E1
 struct TcPlan {
   int mode;
+  int q_rows;    // query rows per MMA (M): 128, or 64 for batches of at most 64 queries
   int n_tile;    // corpus rows per MMA (N): 128 or 256
   int n_stages;  // corpus ring depth
   int q_stages;  // query ring depth
@@ -67,7 +68,8 @@ struct TcPlan {
   size_t smem_bytes;
 };
 int tc_supported(int dim, int64_t n_rows);
-int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks = 0);
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks = 0,
+                 int q_rows = 128);
 int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
@@ -116,7 +118,8 @@ int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const 
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
                        __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream);
 // queries fp32 [B, dim] -> qn fp32 [b_pad, dim] (natural order), q hi/lo bf16 [b_pad, dim] (rows >= B
-// zeroed).  lane_order: plane row of query b is (b / 128) * 128 + query_lane(b % 128).
+// zeroed).  lane_order 1: plane row of query b is (b / 128) * 128 + query_lane(b % 128) (M = 128 sweeps);
+// lane_order 2 (b < 64 only): row (b & 3) * 16 + (b >> 2), the A-row whose M = 64 accumulator lane is query_lane(b).
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
                         __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0);
 

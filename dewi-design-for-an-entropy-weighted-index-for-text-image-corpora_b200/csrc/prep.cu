@@ -29,7 +29,9 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
   for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n_out; row += warps) {
     const size_t off = static_cast<size_t>(row) * dim;
     // bf16 planes may use the TMEM-lane order of the sweep (internal.h: query_lane)
-    const long long prow = lane_order ? (row / kQueryBlock) * kQueryBlock + query_lane(static_cast<int>(row % kQueryBlock)) : row;
+    long long prow = row;
+    if (lane_order == 1) prow = (row / kQueryBlock) * kQueryBlock + query_lane(static_cast<int>(row % kQueryBlock));
+    if (lane_order == 2 && row < 64) prow = (row & 3) * 16 + (row >> 2);
     const size_t poff = static_cast<size_t>(prow) * dim;
     if (row >= n) {  // zero padding rows (query block padding)
       for (int d = lane; d < dim; d += 32) {

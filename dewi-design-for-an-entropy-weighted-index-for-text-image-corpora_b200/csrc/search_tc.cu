@@ -54,18 +54,21 @@ struct TcArgs {
   float* max_out;     // pre-pass mode: [item][128] maximum score per query, no candidate lists
 };
 
-template <int MODE, int N_TILE>
+template <int MODE, int N_TILE, int Q_ROWS>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                  const TcArgs a) {
   using T = ModeTraits<MODE>;
   constexpr uint32_t kEPlaneBytes = N_TILE * 128;
-  constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
+  // Q_ROWS = 64: a batch of at most 64 queries runs M = 64 MMAs (half the tensor work and half the query
+  // re-stream of M = 128).  The accumulator then lives in TMEM lanes 0-15 of each 32-lane quarter (rows
+  // 16q .. 16q+15 -> lanes 32q .. 32q+15), which is exactly where query_lane() puts queries 0..63.
+  constexpr uint32_t kQPlaneBytes = Q_ROWS * 128;
   constexpr uint32_t kEStageBytes = T::PE * kEPlaneBytes;
   constexpr uint32_t kQStageBytes = T::PQ * kQPlaneBytes;
   constexpr uint32_t kTmemCols = 2 * N_TILE;
-  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(kQueryBlock, N_TILE);
+  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(Q_ROWS, N_TILE);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B operand tiles.
@@ -159,7 +162,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
             if (ptx::elect_one()) {
               uint8_t* sqp = ring_q + static_cast<size_t>(sq) * kQStageBytes;
               ptx::mbar_arrive_expect_tx(&bar_q_full[sq], kQStageBytes);
-              ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);
+              ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock, ptx::kEvictLast);  // Q_ROWS-row box
               if (T::PQ > 1)
                 ptx::tma_load_2d(sqp + kQPlaneBytes, &map_q1, &bar_q_full[sq], kb * kKBlock, qb * kQueryBlock,
                                  ptx::kEvictLast);
@@ -232,6 +235,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
       tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
       l.cnt = 0;
       l.thr = seed_threshold(a.seed, a.seed_stride, a.seed_off, a.n_queries, item % a.n_qb, qlane);
+      if (Q_ROWS == 64 && lane >= 16) l.thr = INFINITY;  // these TMEM lanes hold no accumulator row
       float best = -INFINITY;
       for (int t = t0; t < t1; ++t) {
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
@@ -280,16 +284,16 @@ EncodeTiledFn get_encode_fn() {
 }
 
 size_t e_stage_bytes(int mode, int n_tile) { return static_cast<size_t>((mode == 2) ? 2 : 1) * n_tile * 128; }
-size_t q_stage_bytes(int mode) { return static_cast<size_t>((mode == 0) ? 1 : 2) * kQueryBlock * 128; }
+size_t q_stage_bytes(int mode, int q_rows) { return static_cast<size_t>((mode == 0) ? 1 : 2) * q_rows * 128; }
 size_t fixed_bytes(int kc) {
   return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
          1024 /*alignment slack*/;
 }
 
-template <int MODE, int N_TILE>
+template <int MODE, int N_TILE, int Q_ROWS>
 int launch_one(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, const TcArgs& args, cudaStream_t stream) {
-  auto kern = search_tc_kernel<MODE, N_TILE>;
+  auto kern = search_tc_kernel<MODE, N_TILE, Q_ROWS>;
   DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
   kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
   DEWI_CUDA(cudaGetLastError());
@@ -302,7 +306,8 @@ int tc_supported(int dim, int64_t n_rows) {
   return dim % kKBlock == 0 && dim >= kKBlock && dim <= 8192 && n_rows >= 1 && n_rows < (int64_t(1) << 31);
 }
 
-int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks) {
+int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks,
+                 int q_rows) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   const size_t smem_max = 227 * 1024;
   int n_tile = (mode == 2) ? 128 : 256;
@@ -310,7 +315,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   const int q_stages = 2;
   int stages = 0;
   for (;;) {
-    const size_t used = fixed + q_stages * q_stage_bytes(mode);
+    const size_t used = fixed + q_stages * q_stage_bytes(mode, q_rows);
     stages = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode, n_tile)) : 0;
     if (stages >= 3 || n_tile == 128) break;
     n_tile = 128;
@@ -330,12 +335,13 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   if (force_chunks > 0) chunks = force_chunks;
   chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
   plan->mode = mode;
+  plan->q_rows = q_rows;
   plan->n_tile = n_tile;
   plan->n_stages = stages;
   plan->q_stages = q_stages;
   plan->n_chunks = static_cast<int>(chunks);
   plan->grid = static_cast<int>(std::min<int64_t>(grid, chunks * n_qb));
-  plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode, n_tile) + q_stages * q_stage_bytes(mode);
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode, n_tile) + q_stages * q_stage_bytes(mode, q_rows);
   return 0;
 }
 
@@ -373,11 +379,17 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
   a.seed_off = seed.off;
   a.n_queries = seed.n_queries;
   a.max_out = seed.max_out;
-  if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 0 && plan.n_tile == 128) return launch_one<0, 128>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 1 && plan.n_tile == 128) return launch_one<1, 128>(plan, e0, e1, q0, q1, a, stream);
-  if (plan.mode == 2 && plan.n_tile == 128) return launch_one<2, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.q_rows == 64) {
+    if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256, 64>(plan, e0, e1, q0, q1, a, stream);
+    if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256, 64>(plan, e0, e1, q0, q1, a, stream);
+    if (plan.mode == 2 && plan.n_tile == 128) return launch_one<2, 128, 64>(plan, e0, e1, q0, q1, a, stream);
+    return fail("unsupported tcgen05 sweep configuration (M = 64)");
+  }
+  if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 0 && plan.n_tile == 128) return launch_one<0, 128, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 1 && plan.n_tile == 128) return launch_one<1, 128, 128>(plan, e0, e1, q0, q1, a, stream);
+  if (plan.mode == 2 && plan.n_tile == 128) return launch_one<2, 128, 128>(plan, e0, e1, q0, q1, a, stream);
   return fail("unsupported tcgen05 sweep configuration");
 }
 

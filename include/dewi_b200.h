@@ -53,7 +53,8 @@ enum {
   DEWI_FLAG_PRECISE_QUERY = 1 << 4,    /* bf16 corpus: hi+lo query planes (2 MMAs) not 1 + rescore */
   DEWI_FLAG_SCOPE_FULL = 1 << 5,       /* (non-reference) blend over the whole corpus; unsupported */
   DEWI_FLAG_NO_PAIR = 1 << 6,          /* B > 128: keep the 1-CTA sweep instead of the CTA-pair one  */
-  DEWI_FLAG_NO_SEED = 1 << 7           /* skip the sample pre-pass that seeds admission thresholds    */
+  DEWI_FLAG_NO_SEED = 1 << 7,          /* skip the sample pre-pass that seeds admission thresholds    */
+  DEWI_FLAG_NO_M64 = 1 << 8            /* B <= 64: keep M = 128 MMAs instead of M = 64                */
 };
 
 /* ---- library ------------------------------------------------------------------------------ */

@@ -285,3 +285,23 @@ def test_seeded_sweep_equals_unseeded_and_oracle(b):
     for i, s in zip(ids_s[0], sc_s[0]):
         want = np.float32(0.7) * np.float32(emb[i] @ qn) + np.float32(0.3) * np.float32(pay[i, 0]) + np.float32(0.5) * np.float32(ent[i])
         assert abs(s - want) <= 1e-5 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_m64_and_m128_sweeps_agree(dtype):
+    """B <= 64 runs M = 64 MMAs (accumulator rows on TMEM lanes 0-15 of each quarter); DEWI_FLAG_NO_M64
+    keeps M = 128.  Same results either way, and both match the oracle."""
+    n, d, b, k = 90_000, 192, 64, 10
+    emb, pay = make_corpus(n, d, seed=61)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    queries = np.random.RandomState(62).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    ids64, sc64 = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    ids128, sc128 = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_NO_M64)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries, k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for q in range(b):
+            check_topk(rid[q], rsc[q], ids64[q], sc64[q], what=f"M64 q{q}")
+            check_topk(rid[q], rsc[q], ids128[q], sc128[q], what=f"M128 q{q}")
+    else:
+        assert recall_at_k(rid, ids64) >= 0.999 and recall_at_k(rid, ids128) >= 0.999
