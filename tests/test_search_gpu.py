@@ -305,3 +305,16 @@ def test_m64_and_m128_sweeps_agree(dtype):
             check_topk(rid[q], rsc[q], ids128[q], sc128[q], what=f"M128 q{q}")
     else:
         assert recall_at_k(rid, ids64) >= 0.999 and recall_at_k(rid, ids128) >= 0.999
+
+
+def test_precise_query_small_batch():
+    """bf16 corpus, hi+lo query planes (mode 1), B <= 64 (M = 64 MMAs)."""
+    n, d, b, k = 60_000, 256, 40, 10
+    emb, pay = make_corpus(n, d, seed=71)
+    emb16 = bf16_round(emb)
+    queries = np.random.RandomState(72).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype="bf16", precise_query=True)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    rid, rsc = osearch.exact_search_batch(emb16, pay[:, 0], entropy_column(pay), queries, k, 0.3, 0.5, True)
+    for q in range(b):  # with both query planes the sweep is as exact as the fp32 one
+        check_topk(rid[q], rsc[q], ids[q], sc[q], what=f"q{q}")
