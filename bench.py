@@ -232,6 +232,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # stdout carries exactly one JSON line: anything libraries print there meanwhile (NCCL's version
+    # banner at communicator creation, for one) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
@@ -391,6 +395,8 @@ def main():
             "dtype": args.dtype, "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(), "batch_sweep": batch_sweep,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -194,12 +194,17 @@ def main():
     peaks = load_peaks()
     import os
 
+    real_stdout = os.dup(1)  # stdout carries exactly one JSON line (NCCL prints a banner there)
+    os.dup2(2, 1)
+
     with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
         line = {"c2": run_c2, "c4": run_c4, "c5": run_c5}[args.workload](args, torch, dewi_b200, peaks)
     if line is None:
         return
     line["clocks"] = clocks.summary()
     line["peak_source"] = peaks["source"]
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)
 
 
