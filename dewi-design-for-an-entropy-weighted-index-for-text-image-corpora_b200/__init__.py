@@ -12,13 +12,14 @@ from .types import Payload, Signals, Weights  # noqa: F401
 from .backends import BaseIndex, CudaIndex, IndexBackend  # noqa: F401
 from .index import DewiIndex  # noqa: F401
 from .scorer import DewiScorer, RobustStats  # noqa: F401
-from .redundancy import cross_modal_similarity, redundancy_join, sharded_self_join  # noqa: F401
+from .redundancy import (combine_range_stats, cross_modal_similarity, redundancy_join, self_join_range,  # noqa: F401
+                         sharded_self_join)
 from .sharded import ShardedDewiIndex, shard_range  # noqa: F401
 from .robust import (PayloadRobustStats, cluster_coverage, cluster_pairs, clusters_from_labels, duplicate_rate,  # noqa: F401
                      local_weights_from_surprisal)
 
 __all__ = [
     "__version__", "DewiIndex", "BaseIndex", "CudaIndex", "IndexBackend", "Payload", "Signals", "Weights",
-    "DewiScorer", "RobustStats", "cross_modal_similarity", "redundancy_join", "sharded_self_join", "ShardedDewiIndex", "shard_range", "PayloadRobustStats", "local_weights_from_surprisal",
+    "DewiScorer", "RobustStats", "cross_modal_similarity", "redundancy_join", "self_join_range", "combine_range_stats", "sharded_self_join", "ShardedDewiIndex", "shard_range", "PayloadRobustStats", "local_weights_from_surprisal",
     "cluster_pairs", "clusters_from_labels", "duplicate_rate", "cluster_coverage",
 ]

@@ -29,6 +29,7 @@ FLAG_NO_M64 = 1 << 8
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2
+JOIN_NO_SYMMETRY = 1 << 3
 
 
 class NativeUnavailable(ImportError):
@@ -63,6 +64,7 @@ SIGNATURES = {
     "dewi_local_weights": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "dewi_cluster_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
+    "dewi_self_join_range": (c_int, [c_void_p, c_int64, c_int, c_float, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
     "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
 }
 

@@ -194,8 +194,10 @@ struct JoinBufs {
 };
 
 // Tensor-core path: rows normalised into bf16 planes, A on the query side of the CTA-pair sweep.
+// sym_lo >= 0: the symmetric self-join of `a` (= b, m = n) restricted to the row blocks [sym_lo, sym_hi): the
+// outputs then cover ALL n rows (partial statistics when the range is not the whole matrix).
 int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int64_t a_offset,
-                int bf16_only,
+                int bf16_only, int64_t sym_lo, int64_t sym_hi,
                 float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
                 float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream) {
   int sms = 0;
@@ -239,9 +241,17 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
     DEWI_TRY(tc_encode_rows_map(&ma1, a_lo, m_pad, d, kQueryBlock));
     DEWI_TRY(tc_encode_rows_map(&mb1, b_lo, n, d, tc2_box_rows()));
   }
-  DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, ma0, ma1, m, m_pad, n, d, sms, tau,
-                           (self_join || a_offset >= 0) ? 1 : 0, a_offset > 0 ? a_offset : 0, best, row_count,
-                           pair_i, pair_j, pair_sim, pair_cap, count, stream));
+  if (sym_lo >= 0) {
+    // A is the row range of the same planes: the kernel offsets its query rows by sym_lo
+    const int64_t rows = sym_hi - sym_lo;
+    if (rows > 0)
+      DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, mb0, mb1, rows, round_up(rows, 2 * kQueryBlock), n, d, sms, tau, 1,
+                               sym_lo, 1, best, row_count, pair_i, pair_j, pair_sim, pair_cap, count, stream));
+  } else {
+    DEWI_TRY(tc2_join_launch(bf16_only ? 0 : 2, mb0, mb1, ma0, ma1, m, m_pad, n, d, sms, tau,
+                             (self_join || a_offset >= 0) ? 1 : 0, a_offset > 0 ? a_offset : 0, 0, best, row_count,
+                             pair_i, pair_j, pair_sim, pair_cap, count, stream));
+  }
   join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
                                                                              reinterpret_cast<long long*>(row_argmax));
   DEWI_CUDA(cudaGetLastError());
@@ -271,7 +281,8 @@ extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, i
   const bool tensor_ok = tc_supported(d, n) && !(flags & DEWI_JOIN_FORCE_SIMT);
   const bool big = static_cast<double>(m) * static_cast<double>(n) >= 4.0e6;
   if (tensor_ok && (big || (flags & DEWI_JOIN_FORCE_TC)))
-    return join_tensor(a, m, b, n, d, tau, self_join, a_offset, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_max, row_argmax, row_count,
+    return join_tensor(a, m, b, n, d, tau, self_join, a_offset, (flags & DEWI_JOIN_BF16) ? 1 : 0,
+                       (self_join && !(flags & DEWI_JOIN_NO_SYMMETRY)) ? 0 : -1, m, row_max, row_argmax, row_count,
                        pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, stream);
   if (flags & DEWI_JOIN_FORCE_TC) return fail("tensor-core join needs d % 64 == 0");
   float *an = nullptr, *bn = nullptr;
@@ -307,4 +318,21 @@ extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, i
   cudaFree(best);
   cudaFree(count);
   return rc;
+}
+
+extern "C" int dewi_self_join_range(const float* x, int64_t n, int d, float tau, int64_t row_lo, int64_t row_hi, int flags,
+                                    float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
+                                    float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
+  if (!x || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
+  if (n <= 0 || d <= 0) return fail("join needs positive sizes");
+  if (n >= (int64_t(1) << 31)) return fail("join supports fewer than 2^31 rows per side");
+  if (row_lo < 0 || row_hi < row_lo || row_hi > n) return fail("row range outside the matrix");
+  if (row_lo % 256 != 0 || (row_hi % 256 != 0 && row_hi != n))
+    return fail("row range must start and end on multiples of 256 (or at the last row)");
+  if (pair_cap > 0 && (!pair_i || !pair_j || !pair_sim)) return fail("pair buffers missing");
+  if (!tc_supported(d, n)) return fail("the symmetric range join runs on the tensor cores: needs d % 64 == 0");
+  DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
+  DEWI_CUDA(cudaSetDevice(device));
+  return join_tensor(x, n, x, n, d, tau, 1, -1, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_lo, row_hi, row_max, row_argmax, row_count,
+                     pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, static_cast<cudaStream_t>(stream_));
 }

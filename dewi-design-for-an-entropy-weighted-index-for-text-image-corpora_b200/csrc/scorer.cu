@@ -239,109 +239,139 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, const S
 }
 
 // THE full pass of the windowed path: count keys below the window, collect the keys inside it.
-// 16 elements per thread per iteration (four 128-bit loads in flight); window hits (~0.8 % of the
-// keys) go to a per-block shared buffer through one warp-aggregated shared atomic, flushed to the
-// global window with one global atomic every kFlushEvery iterations.
-constexpr int kWinBuf = 6144;
-constexpr int kWinThreads = 512;
+//
+// The pass is a pure HBM stream, so the per-element instruction count is what has to stay small:
+// the window bounds are turned back into floats and every element costs four instructions --
+// `p = x >= lo` (FSETP), `below += !p`, `q = p && x <= hi` (FSETP.AND), `mask |= q << e`.  Window hits
+// are ~0.8 % of the keys, i.e. ~4 per warp per 16-element tile, so nearly every warp has SOME lane with
+// a hit: the hit path must be short too.  Lanes with a non-zero mask walk its set bits, re-read the
+// element (an L1 / L2 hit), and append its order-preserving key to a per-block shared buffer with one
+// shared atomic each; the buffer goes to the global window with one global atomic when it is half full.
+// Float order and key order differ only in (-0, +0) and NaNs: counting and collecting use the SAME float
+// predicates and the selection inside the window uses key order (a refinement of float order), so the
+// selected VALUE is exact.  The [column][row] space is flattened into 4096-element tiles and cut into
+// one contiguous tile range per block, so a grid of exactly (SMs x resident blocks) is one balanced wave
+// for any column count.
+constexpr int kWinBuf = 3072;
+constexpr int kWinThreads = 256;
 constexpr int kWinPerThread = 16;
-constexpr int kFlushEvery = 8;
+constexpr int kWinTile = kWinThreads * kWinPerThread;
+constexpr int kFlushCheckEvery = 8;   // tiles between two looks at the buffer fill (8 tiles add ~260 keys)
+constexpr int kWinBlocksPerSm = 8;
 
 template <int SRC>
-__global__ void __launch_bounds__(kWinThreads)
-window_kernel(const float* __restrict__ cols, long long n, long long ld, SelState* st, unsigned int* __restrict__ wkeys,
-              unsigned int window_cap) {
+__global__ void __launch_bounds__(kWinThreads, kWinBlocksPerSm)
+window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, SelState* st,
+              unsigned int* __restrict__ wkeys, unsigned int window_cap) {
   __shared__ unsigned int buf[kWinBuf];
   __shared__ unsigned int buf_n, flush_base;
   __shared__ unsigned long long below_blk;
-  const int c = blockIdx.y;
-  const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
-  const unsigned int lo = st->lo[c], hi = st->hi[c];
-  const float* col = cols + static_cast<size_t>(c) * ld;
-  unsigned int* out = wkeys + static_cast<size_t>(c) * window_cap;
   const int lane = threadIdx.x & 31;
-  const bool aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
+  const long long tiles_per_col = (n + kWinTile - 1) / kWinTile;
+  const long long total_tiles = tiles_per_col * f;
+  const long long t_begin = (total_tiles * blockIdx.x) / gridDim.x;
+  const long long t_end = (total_tiles * (blockIdx.x + 1)) / gridDim.x;
   if (threadIdx.x == 0) { buf_n = 0u; below_blk = 0ull; }
   __syncthreads();
+
+  int c = -1;
+  float med = 0.f, lo_f = 0.f, hi_f = 0.f;
+  const float* col = nullptr;
+  unsigned int* out = nullptr;
+  bool aligned = false;
   unsigned int below = 0u;
-  auto flush = [&]() {  // block-uniform
+  int since_check = 0;
+
+  auto flush = [&](unsigned int min_fill) {  // block-uniform
     __syncthreads();
     const unsigned int cnt = min(buf_n, static_cast<unsigned int>(kWinBuf));
-    if (cnt) {
+    if (cnt > min_fill) {
       if (threadIdx.x == 0) flush_base = atomicAdd(&st->wcnt[c], cnt);
       __syncthreads();
       for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
         if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
       __syncthreads();
       if (threadIdx.x == 0) buf_n = 0u;
+      __syncthreads();
     }
+    since_check = 0;
+  };
+  auto commit_column = [&]() {  // block-uniform: hand this column's counts over before switching
+    flush(0u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0 && below) atomicAdd(&below_blk, static_cast<unsigned long long>(below));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (below_blk) atomicAdd(&st->below[c], below_blk);
+      below_blk = 0ull;
+    }
+    below = 0u;
     __syncthreads();
   };
-  const long long per_iter = static_cast<long long>(kWinThreads) * kWinPerThread;
-  const long long stride = static_cast<long long>(gridDim.x) * per_iter;
-  int it = 0;
-  for (long long base = static_cast<long long>(blockIdx.x) * per_iter; base < n; base += stride, ++it) {
-    float v[kWinPerThread];
-    bool ok[kWinPerThread];
-    // element e of this thread: base + (e / 4) * (threads * 4) + tid * 4 + (e % 4)  (coalesced 128-bit loads)
-#pragma unroll
-    for (int q = 0; q < kWinPerThread / 4; ++q) {
-      const long long i0 = base + static_cast<long long>(q) * kWinThreads * 4 + static_cast<long long>(threadIdx.x) * 4;
-      if (aligned && i0 + 3 < n) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(col + i0));
-        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
-        ok[4 * q] = ok[4 * q + 1] = ok[4 * q + 2] = ok[4 * q + 3] = true;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          ok[4 * q + j] = i0 + j < n;
-          v[4 * q + j] = ok[4 * q + j] ? __ldg(col + i0 + j) : 0.f;
-        }
-      }
+  auto push = [&](float v) {  // v lies in the window
+    const unsigned int key = orderable(v);
+    const unsigned int slot = atomicAdd(&buf_n, 1u);
+    if (slot < kWinBuf) buf[slot] = key;
+    else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
+      const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
+      if (g < window_cap) out[g] = key;
     }
-    unsigned int keys[kWinPerThread];
-    unsigned int inside = 0u;  // bit e: element e lies in the window
-#pragma unroll
-    for (int e = 0; e < kWinPerThread; ++e) {
-      float x = v[e];
-      if (SRC == SRC_DEV) x = fabsf(__fsub_rn(x, med));
-      keys[e] = orderable(x);
-      below += (ok[e] && keys[e] < lo) ? 1u : 0u;
-      inside |= (ok[e] && keys[e] >= lo && keys[e] <= hi) ? (1u << e) : 0u;
+  };
+
+  for (long long t = t_begin; t < t_end; ++t) {
+    const int tc = static_cast<int>(t / tiles_per_col);
+    if (tc != c) {
+      if (c >= 0) commit_column();
+      c = tc;
+      med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
+      lo_f = from_orderable(st->lo[c]);
+      hi_f = from_orderable(st->hi[c]);
+      col = cols + static_cast<size_t>(c) * ld;
+      out = wkeys + static_cast<size_t>(c) * window_cap;
+      aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
     }
-    if (__any_sync(0xffffffffu, inside != 0u)) {
-      // one shared atomic per warp: exclusive prefix of the lanes' hit counts
-      const unsigned int mine = __popc(inside);
-      unsigned int incl = mine;
+    const long long base = (t - static_cast<long long>(c) * tiles_per_col) * kWinTile;
+    if (aligned && base + kWinTile <= n) {
+      // element e of this thread: base + (e / 4) * (threads * 4) + tid * 4 + (e % 4)  (coalesced 128-bit loads)
+      const float* p = col + base + threadIdx.x * 4;
+      float x[kWinPerThread];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
+      for (int q = 0; q < kWinPerThread / 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + q * kWinThreads * 4));
+        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
       }
-      unsigned int wbase = 0u;
-      if (lane == 31) wbase = atomicAdd(&buf_n, incl);
-      wbase = __shfl_sync(0xffffffffu, wbase, 31);
-      unsigned int slot = wbase + incl - mine;
+      unsigned int mask = 0u;
 #pragma unroll
       for (int e = 0; e < kWinPerThread; ++e) {
-        if (inside & (1u << e)) {
-          if (slot < kWinBuf) buf[slot] = keys[e];
-          else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
-            const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
-            if (g < window_cap) out[g] = keys[e];
-          }
-          ++slot;
+        float y = x[e];
+        if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
+        const bool ge = y >= lo_f;
+        below += ge ? 0u : 1u;
+        mask |= (ge && y <= hi_f) ? (1u << e) : 0u;
+      }
+      while (mask) {  // rare per lane; the element is re-read (cache hit) instead of indexing registers dynamically
+        const int e = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        float y = p[(e >> 2) * (kWinThreads * 4) + (e & 3)];
+        if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
+        push(y);
+      }
+    } else {  // ragged last tile of a column, or a column that is not 16-byte aligned
+      for (int e = 0; e < kWinPerThread; ++e) {
+        const long long i = base + static_cast<long long>(e >> 2) * kWinThreads * 4 + threadIdx.x * 4 + (e & 3);
+        if (i < n) {
+          float y = __ldg(col + i);
+          if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
+          const bool ge = y >= lo_f;
+          below += ge ? 0u : 1u;
+          if (ge && y <= hi_f) push(y);
         }
       }
     }
-    if ((it + 1) % kFlushEvery == 0) flush();
+    if (++since_check == kFlushCheckEvery) flush(kWinBuf / 2);
   }
-  flush();
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
-  if (lane == 0 && below) atomicAdd(&below_blk, static_cast<unsigned long long>(below));
-  __syncthreads();
-  if (threadIdx.x == 0 && below_blk) atomicAdd(&st->below[c], below_blk);
+  if (c >= 0) commit_column();
 }
 
 struct ScoreParams {
@@ -394,6 +424,7 @@ struct FitWork {
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
   size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0;
+  int sm_count = 148;
 };
 std::mutex g_fit_mu;
 FitWork g_fit_work[64];
@@ -439,8 +470,7 @@ void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsi
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
   select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_WINDOW, f, n, cap, w.st);
-  const int bx = std::max(1, 148 * 4 / f);
-  window_kernel<SRC><<<dim3(bx, f), kWinThreads, 0, stream>>>(cols, n, ld, w.st, w.wkeys, cap);
+  window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_INSIDE, f, n, cap, w.st);
   select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(final_op, f, n, cap, w.st);
@@ -457,7 +487,8 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   if (n <= 0) return fail("fit_stats needs at least one row");
   if (f <= 0 || f > kMaxCols) return fail("fit_stats supports 1..32 columns");
   if (ld < n) return fail("ld must be >= n");
-  DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
+  int sms = 148;
+  DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
   DEWI_CUDA(cudaSetDevice(device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool windowed = n >= kWindowMinRows;
@@ -466,6 +497,7 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   if (device >= 64) return fail("device ordinal out of range");
   std::lock_guard<std::mutex> lock(g_fit_mu);
   FitWork& w = g_fit_work[device];
+  w.sm_count = sms;
   if (!w.st) DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
   DEWI_TRY(ensure_buf(&w.ghist, &w.ghist_bytes, static_cast<size_t>(kMaxCols) * 2 * kBins * 4));
   if (windowed) {

@@ -52,6 +52,12 @@ struct Tc2Args {
   float tau;
   int self_join;                   // A's row i is B's row a_offset + i: exclude that column, emit only pairs beyond it
   long long a_offset;
+  // Symmetric self-join (sym = 1): A is rows [a_offset, a_offset + m_rows) of B, a_offset % 256 == 0.  Row block
+  // ig (256 rows) meets only the tiles ig, ig+1, ..., ig+L-1 (mod n_tiles) -- the circulant half, L ~ n_tiles / 2 --
+  // and every off-diagonal tile also updates the statistics of its COLUMNS (rows of the other block), so each
+  // unordered block pair is multiplied once.  row_best / row_count are then indexed by GLOBAL row.
+  int sym;
+  int blk0;                        // a_offset / 256
   unsigned long long* row_best;    // [m_rows] packed (orderable(sim) << 32 | ~j), atomicMax
   int* row_count;                  // [m_rows] sims >= tau
   long long* pair_i;
@@ -117,6 +123,146 @@ __device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int
         }
       }
     }
+  }
+}
+
+// The tiles of one work item: offsets [o0, o1) from tile `tbase` (wrapping at n_tiles).
+__device__ __forceinline__ void item_span(const Tc2Args& a, int item, int& qpair, int& o0, int& o1, int& tbase) {
+  qpair = item % a.n_qpairs;
+  const int chunk = item / a.n_qpairs;
+  if (!a.sym) {
+    tile_range(chunk, a.n_chunks, a.n_tiles, o0, o1);
+    tbase = 0;
+    return;
+  }
+  const int ig = a.blk0 + qpair;
+  const int T = a.n_tiles;
+  // block pairs at distance d <= (T-1)/2 belong to the lower block; for even T the distance T/2 is met
+  // from both sides and belongs to the block in the first half
+  const int L = 1 + (T - 1) / 2 + ((((T & 1) == 0) && ig < T / 2) ? 1 : 0);
+  tile_range(chunk, a.n_chunks, L, o0, o1);
+  tbase = ig;
+}
+__device__ __forceinline__ int tile_at(const Tc2Args& a, int tbase, int o) {
+  const int t = tbase + o;
+  return t >= a.n_tiles ? t - a.n_tiles : t;
+}
+
+__device__ __forceinline__ unsigned long long pack_best(float sim, long long idx) {
+  return (static_cast<unsigned long long>(orderable_u32(sim)) << 32) |
+         static_cast<unsigned int>(~static_cast<unsigned int>(idx));
+}
+__device__ __forceinline__ float best_sim(unsigned long long key) {
+  if (key == 0ull) return -INFINITY;
+  const unsigned int o = static_cast<unsigned int>(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// Column direction of an off-diagonal tile of the symmetric join: column j0 + c is row j0 + c of the matrix,
+// and the 32 rows this warp holds may contain its best match.  `cur` is row_best[j0 + lane] read a little
+// earlier (it only ever grows, so a stale value merely costs a useless atomic).  Almost every group is
+// rejected by the gate -- no element of the 32 x 32 block beats the weakest of the 32 columns' current
+// bests; otherwise a transposed butterfly (31 shuffles) leaves lane c with column c's maximum over the
+// warp's rows and the improved columns publish (sim, row) with one 64-bit atomicMax each.
+__device__ __forceinline__ void join_column_update(const float (&v)[32], float mx, unsigned long long cur, int j0,
+                                                   long long i_glob, int lane, const Tc2Args& a) {
+  const float cur_s = (j0 + lane < a.n_rows) ? best_sim(cur) : INFINITY;
+  float lb = cur_s;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
+  if (!__any_sync(0xffffffffu, mx > lb)) return;
+  float w16[16], w8[8], w4[4], w2[2];
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const float send = b4 ? v[k] : v[k + 16], keep = b4 ? v[k + 16] : v[k];
+    w16[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float send = b3 ? w16[k] : w16[k + 8], keep = b3 ? w16[k + 8] : w16[k];
+    w8[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 8));
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = b2 ? w8[k] : w8[k + 4], keep = b2 ? w8[k + 4] : w8[k];
+    w4[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 4));
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = b1 ? w4[k] : w4[k + 2], keep = b1 ? w4[k + 2] : w4[k];
+    w2[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 2));
+  }
+  const float send = b0 ? w2[0] : w2[1], keep = b0 ? w2[1] : w2[0];
+  const float m = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));  // column j0 + lane over the warp's 32 rows
+  const unsigned int improved = __ballot_sync(0xffffffffu, m > cur_s);
+  if (!improved) return;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (improved & (1u << c)) {  // warp-uniform
+      const float mc = __shfl_sync(0xffffffffu, m, c);
+      const unsigned int who = __ballot_sync(0xffffffffu, v[c] == mc);
+      if (who && lane == c) atomicMax(&a.row_best[j0 + c], pack_best(mc, i_glob - lane + (__ffs(who) - 1)));
+    }
+  }
+}
+
+// Symmetric self-join epilogue for one tile.  Diagonal tile (the block against itself): every row sees its
+// whole 256-column neighbourhood, so only the row direction runs, own column excluded, pairs for j > i.
+// Off-diagonal tile: row direction as usual, every sim >= tau also counts for row j and is emitted once as
+// (min, max); the column direction updates the other block's best matches.
+template <int N_TILE>
+__device__ __forceinline__ void join_scan_tile_sym(JoinRow& r, const Tc2Args& a, long long i_glob, int lane, uint32_t tcol,
+                                                   int col_base, bool diag) {
+  const bool row_ok = i_glob < a.n_rows;
+#pragma unroll 1
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    const int j0 = col_base + c * 32;
+    unsigned long long cur = 0ull;
+    if (!diag && j0 + lane < a.n_rows) cur = __ldcg(a.row_best + j0 + lane);  // issued ahead of the TMEM load
+    float v[32];
+    ptx::tmem_ld_32x32(tcol + c * 32, v);
+    if (!row_ok) {  // padding rows of the last block: zero vectors, must not win any column
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
+    } else if (j0 + 32 > a.n_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j0 + j >= a.n_rows) v[j] = -INFINITY;
+    }
+    if (diag && i_glob >= j0 && i_glob < j0 + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j0 + j == i_glob) v[j] = -INFINITY;
+    }
+    float mx = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+    if (mx > r.best) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (v[j] > r.best) { r.best = v[j]; r.best_j = j0 + j; }
+    }
+    if (mx >= a.tau) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (v[j] >= a.tau) {
+          ++r.count;
+          const long long jj = j0 + j;
+          if (!diag) atomicAdd(&a.row_count[jj], 1);
+          if (!diag || jj > i_glob) {
+            const unsigned long long slot = atomicAdd(a.pair_count, 1ull);
+            if (static_cast<long long>(slot) < a.pair_cap) {
+              a.pair_i[slot] = i_glob < jj ? i_glob : jj;
+              a.pair_j[slot] = i_glob < jj ? jj : i_glob;
+              a.pair_sim[slot] = v[j];
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (!diag) join_column_update(v, mx, cur, j0, i_glob, lane, a);
   }
 }
 
@@ -186,11 +332,11 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     // chunk: leave it in L2 at normal priority unless this is the only pair
     const uint64_t e_policy = a.n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-      const int qrow = ((item % a.n_qpairs) * 2 + static_cast<int>(rank)) * kQueryBlock;
-      int t0, t1;
-      tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
-      for (int t = t0; t < t1; ++t) {
-        const int row0 = t * kNTile + static_cast<int>(rank) * kHalfRows;
+      int qpair, t0, t1, tbase;
+      item_span(a, item, qpair, t0, t1, tbase);
+      const int qrow = (qpair * 2 + static_cast<int>(rank)) * kQueryBlock + (a.sym ? static_cast<int>(a.a_offset) : 0);
+      for (int o = t0; o < t1; ++o) {
+        const int row0 = tile_at(a, tbase, o) * kNTile + static_cast<int>(rank) * kHalfRows;
         for (int kb = 0; kb < a.n_kb; ++kb) {
           ptx::mbar_wait(&bar_empty[st], ph ^ 1);
           if (ptx::elect_one()) {
@@ -217,8 +363,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       uint32_t acc_phase = 0;
       const uint32_t ring_addr = ptx::smem_u32(ring);
       for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-        int t0, t1;
-        tile_range(item / a.n_qpairs, a.n_chunks, a.n_tiles, t0, t1);
+        int qpair, t0, t1, tbase;
+        item_span(a, item, qpair, t0, t1, tbase);
         for (int t = t0; t < t1; ++t) {
           ptx::mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
           ptx::tc_fence_after();
@@ -264,20 +410,22 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {
       const int chunk = item / a.n_qpairs;
-      const int qb = (item % a.n_qpairs) * 2 + static_cast<int>(rank);
-      int t0, t1;
-      tile_range(chunk, a.n_chunks, a.n_tiles, t0, t1);
+      int qpair, t0, t1, tbase;
+      item_span(a, item, qpair, t0, t1, tbase);
+      const int qb = qpair * 2 + static_cast<int>(rank);
       l.cnt = 0;
       l.thr = seed_threshold(a.seed, a.seed_stride, a.seed_off, a.n_queries, qb, qlane);
       float best = -INFINITY;
       JoinRow jr = {-INFINITY, -1, 0};
       const int i_row = qb * kQueryBlock + qlane;
-      for (int t = t0; t < t1; ++t) {
+      for (int o = t0; o < t1; ++o) {
+        const int t = tile_at(a, tbase, o);
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * kNTile);
         if (EPI == EPI_TOPK && a.max_out) best = max_tile<kNTile>(best, tcol, t * kNTile, a.n_rows);
         else if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
+        else if (a.sym) join_scan_tile_sym<kNTile>(jr, a, i_row + a.a_offset, lane, tcol, t * kNTile, o == 0);
         else join_scan_tile<kNTile>(jr, a, i_row, tcol, t * kNTile);
         ptx::tc_fence_before();
         __syncwarp();
@@ -291,10 +439,9 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
         const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
         flush_item(l, kc, a.part_s + slot, a.part_i + slot);
       } else if (i_row < a.m_rows) {
-        if (jr.best_j >= 0)
-          atomicMax(&a.row_best[i_row], (static_cast<unsigned long long>(orderable_u32(jr.best)) << 32) |
-                                            static_cast<unsigned int>(~static_cast<unsigned int>(jr.best_j)));
-        if (jr.count) atomicAdd(&a.row_count[i_row], jr.count);
+        const long long i_out = a.sym ? i_row + a.a_offset : i_row;
+        if (jr.best_j >= 0) atomicMax(&a.row_best[i_out], pack_best(jr.best, jr.best_j));
+        if (jr.count) atomicAdd(&a.row_count[i_out], jr.count);
       }
     }
   }
@@ -329,7 +476,8 @@ int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 
 }  // namespace
 
-int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks) {
+int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks,
+                  int64_t tiles_per_item) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
   const size_t smem_max = 227 * 1024;
@@ -338,7 +486,8 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   if (const char* env = getenv("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));
   if (stages < 2) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
   stages = std::min(stages, kMaxStages);
-  const int64_t n_tiles = ceil_div(n_rows, kNTile);
+  // tiles one query-block pair meets: the whole corpus, or the circulant half of a symmetric self-join
+  const int64_t n_tiles = tiles_per_item > 0 ? tiles_per_item : ceil_div(n_rows, kNTile);
   const int n_qpairs = n_qb / 2;
   const int max_clusters = std::max(1, sm_count / 2);
   const int clusters = static_cast<int>(std::min<int64_t>(max_clusters, n_tiles * n_qpairs));
@@ -386,6 +535,8 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.tau = 0.f;
   a.self_join = 0;
   a.a_offset = 0;
+  a.sym = 0;
+  a.blk0 = 0;
   a.row_best = nullptr;
   a.row_count = nullptr;
   a.pair_i = a.pair_j = nullptr;
@@ -403,12 +554,16 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 // mode 2 = hi/lo planes on both sides (three MMAs, ~1e-6).
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
                     int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,
-                    unsigned long long* row_best, int* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+                    int sym, unsigned long long* row_best, int* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
                     int64_t pair_cap, unsigned long long* pair_count, cudaStream_t stream) {
   Tc2Plan plan;
   const int n_qb = static_cast<int>(m_pad / kQueryBlock);
-  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan));
+  const int64_t all_tiles = ceil_div(n_rows, kNTile);
+  if (sym && (a_offset % kNTile) != 0) return fail("symmetric join: the row range must start on a multiple of 256");
+  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, 0, sym ? all_tiles / 2 + 1 : 0));
   Tc2Args a;
+  a.sym = sym ? 1 : 0;
+  a.blk0 = sym ? static_cast<int>(a_offset / kNTile) : 0;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
   a.n_kb = dim / kKBlock;
@@ -426,7 +581,7 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.m_rows = static_cast<int>(m_rows);
   a.tau = tau;
   a.self_join = self_join;
-  a.a_offset = self_join ? a_offset : 0;
+  a.a_offset = (self_join || sym) ? a_offset : 0;
   a.row_best = row_best;
   a.row_count = row_count;
   a.pair_i = reinterpret_cast<long long*>(pair_i);

@@ -143,10 +143,25 @@ DEWI_API int dewi_similarity_dense(const float* a, int64_t m, const float* b, in
  * for j > a_offset + i and carry the global row a_offset + i.  a_offset < 0: plain cross join.
  * Large inputs with d % 64 == 0 run on the tensor cores (CTA-pair sweep with a threshold epilogue):
  * rows as bf16 hi+lo planes, three MMAs, similarities good to ~1e-5 (the lo.lo term is dropped); DEWI_JOIN_BF16 keeps one bf16
- * plane (one MMA, similarities carry bf16 rounding ~1e-3).  Otherwise an fp32 CUDA-core kernel.   */
-enum { DEWI_JOIN_BF16 = 1 << 0, DEWI_JOIN_FORCE_SIMT = 1 << 1, DEWI_JOIN_FORCE_TC = 1 << 2 };
+ * plane (one MMA, similarities carry bf16 rounding ~1e-3).  Otherwise an fp32 CUDA-core kernel.
+ * A self-join on the tensor cores multiplies every unordered pair of 256-row blocks ONCE (circulant
+ * half of the block grid; an off-diagonal tile updates the statistics of its rows and of its columns);
+ * DEWI_JOIN_NO_SYMMETRY evaluates the full M x N product instead (tests / comparison).             */
+enum { DEWI_JOIN_BF16 = 1 << 0, DEWI_JOIN_FORCE_SIMT = 1 << 1, DEWI_JOIN_FORCE_TC = 1 << 2, DEWI_JOIN_NO_SYMMETRY = 1 << 3 };
 DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
               int64_t a_offset, int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+              int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
+
+/* One rank's share of a row-sharded SYMMETRIC self-join of x[n, d] (every rank holds all rows): the row
+ * blocks of [row_lo, row_hi) (multiples of 256, or ending at n) against their half of the block grid --
+ * block I meets blocks I .. I + (T-1)/2 (mod T), T = ceil(n / 256), plus I + T/2 for I < T/2 when T is
+ * even -- so contiguous ranges of equal length carry equal work and the ranges of all ranks cover every
+ * unordered row pair exactly once.  row_max / row_argmax / row_count have n entries and hold the
+ * contribution of this range only (-inf / -1 / 0 where it has none): combine ranks with max (ties: any
+ * argmax) and sum.  Each pair with sim >= tau is emitted once, as (min, max).  Tensor cores only
+ * (d % 64 == 0); flags: DEWI_JOIN_BF16.  [row_lo, row_hi) = [0, n) is the whole self-join.            */
+DEWI_API int dewi_self_join_range(const float* x, int64_t n, int d, float tau, int64_t row_lo, int64_t row_hi, int flags,
+              float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
               int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
 
 /* ---- neighbours of the path that reuse its kernels -------------------------- */

@@ -53,17 +53,66 @@ def test_cross_join_vs_oracle(m, n, d, force):
     assert out["n_pairs"] == len(got)
 
 
-@pytest.mark.parametrize("force", ["simt", "tc"])
-def test_self_join_vs_oracle(force):
-    a = planted(3000, 128, 5, frac=0.05)
+def _check_self_join(out, a, tau, mx, cnt, pairs, tol=1e-5):
+    np.testing.assert_allclose(out["max_sim"].cpu().numpy(), mx, atol=tol)
+    sim = ored.cross_modal_similarity(a, a)
+    np.fill_diagonal(sim, -np.inf)
+    am = out["argmax"].cpu().numpy()
+    assert np.all((am >= 0) & (am < len(a)) & (am != np.arange(len(a))))
+    assert np.all(sim[np.arange(len(a)), am] >= mx - tol)  # an index that attains the maximum
+    np.testing.assert_array_equal(out["count"].cpu().numpy(), cnt)
+    got = list(zip(out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist()))
+    assert len(got) == len(set(got)) == out["n_pairs"]
+    assert set(got) == {(i, j) for i, j, _ in pairs} and all(i < j for i, j in got)
+
+
+@pytest.mark.parametrize("force,symmetric", [("simt", True), ("tc", True), ("tc", False)])
+@pytest.mark.parametrize("n", [3000, 2700, 300, 200])  # 12 / 11 / 2 / 1 tiles of 256 rows: even, odd, tiny grids
+def test_self_join_vs_oracle(force, symmetric, n):
+    """The tensor-core self-join multiplies each unordered pair of 256-row blocks once (circulant half,
+    column-direction statistics); `symmetric=False` is the full product.  Both must equal the oracle."""
+    a = planted(n, 128, 5, frac=0.05)
     tau = 0.92
     mx, am, cnt, pairs = ored.join_rowstats(a, a, tau, self_join=True)
-    out = dewi_b200.redundancy_join(a, tau=tau, force=force)
-    np.testing.assert_allclose(out["max_sim"].cpu().numpy(), mx, atol=1e-5)
-    np.testing.assert_array_equal(out["count"].cpu().numpy(), cnt)
-    got = set(zip(out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist()))
-    assert got == {(i, j) for i, j, _ in pairs} and all(i < j for i, j in got)
+    out = dewi_b200.redundancy_join(a, tau=tau, force=force, symmetric=symmetric)
+    _check_self_join(out, a, tau, mx, cnt, pairs)
     assert out["n_pairs"] == len(pairs) > 0
+
+
+@pytest.mark.parametrize("n,cuts", [(2500, (0, 768, 1792, 2500)), (5000, (0, 1280, 2560, 3840, 5000)), (700, (0, 256, 700))])
+def test_range_joins_add_up_to_the_self_join(n, cuts):
+    """The sharded symmetric join on one device: each 'rank' evaluates its row range against the circulant
+    half of the block grid; statistics combine with max / sum, pair lists unite without duplicates."""
+    a = planted(n, 128, 17, frac=0.05)
+    tau = 0.92
+    mx, am, cnt, pairs = ored.join_rowstats(a, a, tau, self_join=True)
+    parts = [dewi_b200.self_join_range(a, lo, hi, tau=tau) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    cmx, carg, ccnt = dewi_b200.combine_range_stats(parts)
+    import torch
+    merged = {"max_sim": cmx, "argmax": carg, "count": ccnt,
+              "pairs_i": torch.cat([p["pairs_i"] for p in parts]), "pairs_j": torch.cat([p["pairs_j"] for p in parts]),
+              "n_pairs": sum(p["n_pairs"] for p in parts)}
+    _check_self_join(merged, a, tau, mx, cnt, pairs)
+
+
+def test_symmetric_join_duplicate_heavy_rows():
+    """Many exact duplicates: every row's best match is 1.0 with ties everywhere, counts are large and the
+    column direction fires on every tile."""
+    rng = np.random.RandomState(3)
+    base = rng.standard_normal((40, 64)).astype(np.float32)
+    a = base[rng.randint(0, 40, size=1500)]
+    tau = 0.99
+    mx, am, cnt, pairs = ored.join_rowstats(a, a, tau, self_join=True)
+    out = dewi_b200.redundancy_join(a, tau=tau, force="tc", pair_cap=1 << 17)
+    _check_self_join(out, a, tau, mx, cnt, pairs, tol=2e-5)
+
+
+def test_range_join_rejects_unaligned_ranges():
+    a = planted(1000, 64, 1)
+    with pytest.raises(ValueError):
+        dewi_b200.self_join_range(a, 100, 612)
+    with pytest.raises(ValueError):
+        dewi_b200.self_join_range(a, 0, 500)
 
 
 def test_pair_cap_overflow_is_reported():
