@@ -64,8 +64,9 @@ SIGNATURES = {
     "dewi_local_weights": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "dewi_cluster_pairs": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "dewi_similarity_dense": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int, c_void_p]),
-    "dewi_self_join_range": (c_int, [c_void_p, c_int64, c_int, c_float, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
-    "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_int, c_void_p]),
+    "dewi_join_workspace_bytes": (c_int64, [c_int64, c_int64, c_int, c_int, c_int]),
+    "dewi_self_join_range": (c_int, [c_void_p, c_int64, c_int, c_float, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64, c_int, c_void_p]),
+    "dewi_join": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_float, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, POINTER(c_int64), c_void_p, c_int64, c_int, c_void_p]),
 }
 
 _lib = None

@@ -10,6 +10,8 @@
 // This translation unit is the fp32 CUDA-core implementation (64x64 tiles, 4x4 register blocking,
 // shared-memory staged).  It is exact to fp32 rounding and serves as the small-size path.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -186,12 +188,37 @@ extern "C" int dewi_similarity_dense(const float* a, int64_t m, const float* b, 
 namespace dewi {
 namespace {
 
-struct JoinBufs {
-  void* p[8] = {};
-  ~JoinBufs() {
-    for (void* q : p) cudaFree(q);
+// Scratch memory of one join call: carved out of the caller's workspace (the Python wrapper hands in a
+// torch tensor, so repeated calls cost no cudaMalloc / cudaFree -- those dominated the wall time of a
+// join by far: a cudaFree of the GB-sized operand planes synchronises and returns the pages to the
+// driver), or, with no workspace, allocated here and freed on return.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, used = 0;
+  bool dry = false;             // only add up the sizes (dewi_join_workspace_bytes)
+  void* owned[8] = {};
+  int n_owned = 0;
+  void* take(size_t bytes) {
+    bytes = static_cast<size_t>(round_up(static_cast<int64_t>(std::max<size_t>(bytes, 1)), 256));
+    if (dry) { used += bytes; return reinterpret_cast<void*>(uintptr_t(256)); }
+    if (base) {
+      if (used + bytes > cap) return nullptr;
+      void* p = base + used;
+      used += bytes;
+      return p;
+    }
+    void* p = nullptr;
+    if (n_owned >= 8 || cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    owned[n_owned++] = p;
+    return p;
+  }
+  ~Arena() {
+    for (int i = 0; i < n_owned; ++i) cudaFree(owned[i]);
   }
 };
+#define DEWI_TAKE(var, type, arena, bytes)                                              \
+  type var = static_cast<type>((arena).take(bytes));                                    \
+  if (!var) return fail("join: workspace too small or cudaMalloc failed")
 
 // Tensor-core path: rows normalised into bf16 planes, A on the query side of the CTA-pair sweep.
 // sym_lo >= 0: the symmetric self-join of `a` (= b, m = n) restricted to the row blocks [sym_lo, sym_hi): the
@@ -199,36 +226,31 @@ struct JoinBufs {
 int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int64_t a_offset,
                 int bf16_only, int64_t sym_lo, int64_t sym_hi,
                 float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
-                float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream) {
-  int sms = 0;
-  DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
+                float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream, Arena& w) {
+  int sms = 148;
+  if (!w.dry) DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
   const int64_t m_pad = round_up(m, 2 * kQueryBlock);
   const size_t plane_a = static_cast<size_t>(m_pad) * d * 2, plane_b = static_cast<size_t>(n) * d * 2;
-  JoinBufs w;
-  __nv_bfloat16 *a_hi, *a_lo = nullptr, *b_hi, *b_lo = nullptr;
-  DEWI_CUDA(cudaMalloc(&w.p[0], plane_a));
-  a_hi = static_cast<__nv_bfloat16*>(w.p[0]);
+  DEWI_TAKE(a_hi, __nv_bfloat16*, w, plane_a);
+  __nv_bfloat16 *a_lo = nullptr, *b_hi = a_hi, *b_lo = nullptr;
   if (!bf16_only) {
-    DEWI_CUDA(cudaMalloc(&w.p[1], plane_a));
-    a_lo = static_cast<__nv_bfloat16*>(w.p[1]);
+    DEWI_TAKE(p, __nv_bfloat16*, w, plane_a);
+    a_lo = b_lo = p;
   }
-  DEWI_TRY(launch_prep_queries(a, static_cast<int>(m), static_cast<int>(m_pad), d, 1, nullptr, a_hi, a_lo, stream));
-  if (self_join) {
-    b_hi = a_hi;
-    b_lo = a_lo;
-  } else {
-    DEWI_CUDA(cudaMalloc(&w.p[2], plane_b));
-    b_hi = static_cast<__nv_bfloat16*>(w.p[2]);
+  if (!self_join) {
+    DEWI_TAKE(p, __nv_bfloat16*, w, plane_b);
+    b_hi = p;
     if (!bf16_only) {
-      DEWI_CUDA(cudaMalloc(&w.p[3], plane_b));
-      b_lo = static_cast<__nv_bfloat16*>(w.p[3]);
+      DEWI_TAKE(q, __nv_bfloat16*, w, plane_b);
+      b_lo = q;
     }
-    DEWI_TRY(launch_prep_queries(b, static_cast<int>(n), static_cast<int>(n), d, 1, nullptr, b_hi, b_lo, stream));
   }
-  DEWI_CUDA(cudaMalloc(&w.p[4], static_cast<size_t>(m) * 8));
-  DEWI_CUDA(cudaMalloc(&w.p[5], 8));
-  unsigned long long* best = static_cast<unsigned long long*>(w.p[4]);
-  unsigned long long* count = static_cast<unsigned long long*>(w.p[5]);
+  DEWI_TAKE(best, unsigned long long*, w, static_cast<size_t>(m) * 8);
+  DEWI_TAKE(count, unsigned long long*, w, 8);
+  if (w.dry) return 0;
+  DEWI_TRY(launch_prep_queries(a, static_cast<int>(m), static_cast<int>(m_pad), d, 1, nullptr, a_hi, a_lo, stream));
+  if (!self_join)
+    DEWI_TRY(launch_prep_queries(b, static_cast<int>(n), static_cast<int>(n), d, 1, nullptr, b_hi, b_lo, stream));
   DEWI_CUDA(cudaMemsetAsync(best, 0, static_cast<size_t>(m) * 8, stream));
   DEWI_CUDA(cudaMemsetAsync(count, 0, 8, stream));
   DEWI_CUDA(cudaMemsetAsync(row_count, 0, static_cast<size_t>(m) * 4, stream));
@@ -241,6 +263,14 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
     DEWI_TRY(tc_encode_rows_map(&ma1, a_lo, m_pad, d, kQueryBlock));
     DEWI_TRY(tc_encode_rows_map(&mb1, b_lo, n, d, tc2_box_rows()));
   }
+  // DEWI_JOIN_TIMING=1: CUDA-event time of the join kernel alone on stderr (profiling / bench_paths.py)
+  const bool timing = getenv("DEWI_JOIN_TIMING") != nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (timing) {
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
+  }
   if (sym_lo >= 0) {
     // A is the row range of the same planes: the kernel offsets its query rows by sym_lo
     const int64_t rows = sym_hi - sym_lo;
@@ -252,6 +282,59 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
                              (self_join || a_offset >= 0) ? 1 : 0, a_offset > 0 ? a_offset : 0, 0, best, row_count,
                              pair_i, pair_j, pair_sim, pair_cap, count, stream));
   }
+  if (timing) cudaEventRecord(ev1, stream);
+  join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
+                                                                             reinterpret_cast<long long*>(row_argmax));
+  DEWI_CUDA(cudaGetLastError());
+  unsigned long long cnt = 0;
+  DEWI_CUDA(cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, stream));
+  DEWI_CUDA(cudaStreamSynchronize(stream));
+  *pair_count_host = static_cast<int64_t>(cnt);
+  if (timing) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    fprintf(stderr, "[dewi_join] kernel %.3f ms (m=%lld n=%lld d=%d %s%s)\n", ms, static_cast<long long>(m),
+            static_cast<long long>(n), d, bf16_only ? "bf16" : "hi/lo", sym_lo >= 0 ? " symmetric" : "");
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace dewi
+
+namespace dewi {
+namespace {
+
+bool join_uses_tensor_cores(int64_t m, int64_t n, int d, int flags) {
+  const bool tensor_ok = tc_supported(d, n) && !(flags & DEWI_JOIN_FORCE_SIMT);
+  const bool big = static_cast<double>(m) * static_cast<double>(n) >= 4.0e6;
+  return tensor_ok && (big || (flags & DEWI_JOIN_FORCE_TC));
+}
+
+// fp32 CUDA-core join (small inputs, d % 64 != 0).
+int join_simt(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int64_t a_offset,
+              float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
+              int64_t pair_cap, int64_t* pair_count_host, cudaStream_t stream, Arena& w) {
+  DEWI_TAKE(an, float*, w, static_cast<size_t>(m) * d * 4);
+  float* bn = an;
+  if (!self_join) {
+    DEWI_TAKE(p, float*, w, static_cast<size_t>(n) * d * 4);
+    bn = p;
+  }
+  DEWI_TAKE(best, unsigned long long*, w, static_cast<size_t>(m) * 8);
+  DEWI_TAKE(count, unsigned long long*, w, 8);
+  if (w.dry) return 0;
+  DEWI_CUDA(cudaMemsetAsync(best, 0, static_cast<size_t>(m) * 8, stream));
+  DEWI_CUDA(cudaMemsetAsync(count, 0, 8, stream));
+  DEWI_CUDA(cudaMemsetAsync(row_count, 0, static_cast<size_t>(m) * 4, stream));
+  DEWI_TRY(normalize_into(a, m, d, an, stream));
+  if (!self_join) DEWI_TRY(normalize_into(b, n, d, bn, stream));
+  dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
+  sim_tile_kernel<1><<<grid, 256, 0, stream>>>(an, m, bn, n, d, nullptr, tau, self_join, a_offset, best, row_count,
+                                               reinterpret_cast<long long*>(pair_i), reinterpret_cast<long long*>(pair_j),
+                                               pair_sim, pair_cap, count);
   join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
                                                                              reinterpret_cast<long long*>(row_argmax));
   DEWI_CUDA(cudaGetLastError());
@@ -262,12 +345,37 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
   return 0;
 }
 
+int join_dispatch(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join, int64_t a_offset,
+                  int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
+                  float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, cudaStream_t stream, Arena& w) {
+  if (join_uses_tensor_cores(m, n, d, flags))
+    return join_tensor(a, m, b, n, d, tau, self_join, a_offset, (flags & DEWI_JOIN_BF16) ? 1 : 0,
+                       (self_join && !(flags & DEWI_JOIN_NO_SYMMETRY)) ? 0 : -1, m, row_max, row_argmax, row_count,
+                       pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, stream, w);
+  if (flags & DEWI_JOIN_FORCE_TC) return fail("tensor-core join needs d % 64 == 0");
+  return join_simt(a, m, b, n, d, tau, self_join, a_offset, row_max, row_argmax, row_count, pair_i, pair_j, pair_sim, pair_cap,
+                   pair_count_host, stream, w);
+}
+
 }  // namespace
 }  // namespace dewi
 
+extern "C" int64_t dewi_join_workspace_bytes(int64_t m, int64_t n, int d, int self_join, int flags) {
+  if (self_join) n = m;
+  if (m <= 0 || n <= 0 || d <= 0) return 0;
+  Arena w;
+  w.dry = true;
+  int64_t dummy = 0;
+  if (join_dispatch(nullptr, m, nullptr, n, d, 0.f, self_join, -1, flags, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                    &dummy, 0, nullptr, w) != 0)
+    return 0;
+  return static_cast<int64_t>(w.used);
+}
+
 extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
                          int64_t a_offset, int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
-                         float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
+                         float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, void* workspace, int64_t workspace_bytes,
+                         int device, void* stream_) {
   if (!a || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
   if (self_join) { b = a; n = m; a_offset = -1; }
   if (!b) return fail("null argument");
@@ -277,52 +385,17 @@ extern "C" int dewi_join(const float* a, int64_t m, const float* b, int64_t n, i
   if (pair_cap > 0 && (!pair_i || !pair_j || !pair_sim)) return fail("pair buffers missing");
   DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
   DEWI_CUDA(cudaSetDevice(device));
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const bool tensor_ok = tc_supported(d, n) && !(flags & DEWI_JOIN_FORCE_SIMT);
-  const bool big = static_cast<double>(m) * static_cast<double>(n) >= 4.0e6;
-  if (tensor_ok && (big || (flags & DEWI_JOIN_FORCE_TC)))
-    return join_tensor(a, m, b, n, d, tau, self_join, a_offset, (flags & DEWI_JOIN_BF16) ? 1 : 0,
-                       (self_join && !(flags & DEWI_JOIN_NO_SYMMETRY)) ? 0 : -1, m, row_max, row_argmax, row_count,
-                       pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, stream);
-  if (flags & DEWI_JOIN_FORCE_TC) return fail("tensor-core join needs d % 64 == 0");
-  float *an = nullptr, *bn = nullptr;
-  unsigned long long *best = nullptr, *count = nullptr;
-  int rc = 0;
-  do {
-    if (cudaMalloc(&an, static_cast<size_t>(m) * d * 4) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
-    if (!self_join && cudaMalloc(&bn, static_cast<size_t>(n) * d * 4) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
-    if (cudaMalloc(&best, static_cast<size_t>(m) * 8) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
-    if (cudaMalloc(&count, 8) != cudaSuccess) { rc = fail("cudaMalloc failed"); break; }
-    cudaMemsetAsync(best, 0, static_cast<size_t>(m) * 8, stream);
-    cudaMemsetAsync(count, 0, 8, stream);
-    cudaMemsetAsync(row_count, 0, static_cast<size_t>(m) * 4, stream);
-    if ((rc = normalize_into(a, m, d, an, stream))) break;
-    if (!self_join && (rc = normalize_into(b, n, d, bn, stream))) break;
-    dim3 grid(static_cast<unsigned>(ceil_div(n, TN)), static_cast<unsigned>(ceil_div(m, TM)));
-    sim_tile_kernel<1><<<grid, 256, 0, stream>>>(an, m, self_join ? an : bn, n, d, nullptr, tau, self_join, a_offset, best,
-                                                 row_count, reinterpret_cast<long long*>(pair_i),
-                                                 reinterpret_cast<long long*>(pair_j), pair_sim, pair_cap, count);
-    join_finish_kernel<<<static_cast<int>(ceil_div(m, 256)), 256, 0, stream>>>(best, m, row_max,
-                                                                               reinterpret_cast<long long*>(row_argmax));
-    if (cudaGetLastError() != cudaSuccess) { rc = fail("join kernel launch failed"); break; }
-    unsigned long long cnt = 0;
-    if (cudaMemcpyAsync(&cnt, count, 8, cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
-        cudaStreamSynchronize(stream) != cudaSuccess) {
-      rc = fail(std::string("join: ") + cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
-    *pair_count_host = static_cast<int64_t>(cnt);
-  } while (0);
-  cudaFree(an);
-  cudaFree(bn);
-  cudaFree(best);
-  cudaFree(count);
-  return rc;
+  Arena w;
+  w.base = static_cast<char*>(workspace);
+  w.cap = workspace ? static_cast<size_t>(std::max<int64_t>(workspace_bytes, 0)) : 0;
+  return join_dispatch(a, m, b, n, d, tau, self_join, a_offset, flags, row_max, row_argmax, row_count, pair_i, pair_j, pair_sim,
+                       pair_cap, pair_count_host, device, static_cast<cudaStream_t>(stream_), w);
 }
 
 extern "C" int dewi_self_join_range(const float* x, int64_t n, int d, float tau, int64_t row_lo, int64_t row_hi, int flags,
                                     float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j,
-                                    float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, int device, void* stream_) {
+                                    float* pair_sim, int64_t pair_cap, int64_t* pair_count_host, void* workspace,
+                                    int64_t workspace_bytes, int device, void* stream_) {
   if (!x || !row_max || !row_argmax || !row_count || !pair_count_host) return fail("null argument");
   if (n <= 0 || d <= 0) return fail("join needs positive sizes");
   if (n >= (int64_t(1) << 31)) return fail("join supports fewer than 2^31 rows per side");
@@ -333,6 +406,9 @@ extern "C" int dewi_self_join_range(const float* x, int64_t n, int d, float tau,
   if (!tc_supported(d, n)) return fail("the symmetric range join runs on the tensor cores: needs d % 64 == 0");
   DEWI_TRY(dewi_device_check(device, nullptr, nullptr, nullptr));
   DEWI_CUDA(cudaSetDevice(device));
+  Arena w;
+  w.base = static_cast<char*>(workspace);
+  w.cap = workspace ? static_cast<size_t>(std::max<int64_t>(workspace_bytes, 0)) : 0;
   return join_tensor(x, n, x, n, d, tau, 1, -1, (flags & DEWI_JOIN_BF16) ? 1 : 0, row_lo, row_hi, row_max, row_argmax, row_count,
-                     pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, static_cast<cudaStream_t>(stream_));
+                     pair_i, pair_j, pair_sim, pair_cap, pair_count_host, device, static_cast<cudaStream_t>(stream_), w);
 }

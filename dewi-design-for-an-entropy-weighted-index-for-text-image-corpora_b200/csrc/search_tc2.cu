@@ -28,7 +28,11 @@ namespace {
 
 using namespace sweep;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;            // 2 role warps + 4 epilogue warps (top-k epilogue)
+// The join epilogue is the longer one (row and column direction per tile) and sets the pace of the MMAs when a
+// single warp per TMEM lane quarter has to walk all 256 columns: it runs TWO warps per quarter, 128 columns each.
+constexpr int kJoinEpiWarps = 8;
+constexpr int kJoinThreads = 64 + 32 * kJoinEpiWarps;
 constexpr int kNTile = 256;           // corpus rows per MMA (N); each CTA stages kNTile / 2
 constexpr int kHalfRows = kNTile / 2;
 
@@ -58,6 +62,7 @@ struct Tc2Args {
   // unordered block pair is multiplied once.  row_best / row_count are then indexed by GLOBAL row.
   int sym;
   int blk0;                        // a_offset / 256
+  int rotate;                      // align the clusters' tile walks (item_span)
   unsigned long long* row_best;    // [m_rows] packed (orderable(sim) << 32 | ~j), atomicMax
   int* row_count;                  // [m_rows] sims >= tau
   long long* pair_i;
@@ -126,22 +131,41 @@ __device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int
   }
 }
 
-// The tiles of one work item: offsets [o0, o1) from tile `tbase` (wrapping at n_tiles).
-__device__ __forceinline__ void item_span(const Tc2Args& a, int item, int& qpair, int& o0, int& o1, int& tbase) {
-  qpair = item % a.n_qpairs;
+// The tiles of one work item: `len` offsets starting at o0 from tile `tbase` (wrapping at n_tiles), walked in
+// the rotated order o0 + (s + rot) % len.  Symmetric join: the clusters running concurrently hold consecutive
+// row blocks I0 + cluster_id whose tile ranges are shifted by one tile each; rotating cluster k's walk by
+// (n_clusters - 1 - k) makes all of them read tile I0 + n_clusters - 1 + o0 + s at step s -- one DRAM read
+// feeds every cluster through L2, exactly as in the plain sweep -- and leaves each cluster its private
+// leftovers (n_clusters - 1 tiles, the diagonal among them) for the end of the item.
+struct ItemSpan {
+  int qpair, o0, len, rot, tbase;
+};
+__device__ __forceinline__ ItemSpan item_span(const Tc2Args& a, int item, int cluster_id, int n_clusters) {
+  ItemSpan sp;
+  sp.qpair = item % a.n_qpairs;
   const int chunk = item / a.n_qpairs;
+  int o1;
   if (!a.sym) {
-    tile_range(chunk, a.n_chunks, a.n_tiles, o0, o1);
-    tbase = 0;
-    return;
+    tile_range(chunk, a.n_chunks, a.n_tiles, sp.o0, o1);
+    sp.len = o1 - sp.o0;
+    sp.rot = 0;
+    sp.tbase = 0;
+    return sp;
   }
-  const int ig = a.blk0 + qpair;
+  const int ig = a.blk0 + sp.qpair;
   const int T = a.n_tiles;
   // block pairs at distance d <= (T-1)/2 belong to the lower block; for even T the distance T/2 is met
   // from both sides and belongs to the block in the first half
   const int L = 1 + (T - 1) / 2 + ((((T & 1) == 0) && ig < T / 2) ? 1 : 0);
-  tile_range(chunk, a.n_chunks, L, o0, o1);
-  tbase = ig;
+  tile_range(chunk, a.n_chunks, L, sp.o0, o1);
+  sp.len = o1 - sp.o0;
+  sp.rot = (a.rotate && sp.len > 0) ? (n_clusters - 1 - cluster_id) % sp.len : 0;
+  sp.tbase = ig;
+  return sp;
+}
+__device__ __forceinline__ int span_offset(const ItemSpan& sp, int s) {
+  const int o = sp.o0 + s + sp.rot;
+  return o >= sp.o0 + sp.len ? o - sp.len : o;
 }
 __device__ __forceinline__ int tile_at(const Tc2Args& a, int tbase, int o) {
   const int t = tbase + o;
@@ -159,23 +183,46 @@ __device__ __forceinline__ float best_sim(unsigned long long key) {
 }
 
 // Column direction of an off-diagonal tile of the symmetric join: column j0 + c is row j0 + c of the matrix,
-// and the 32 rows this warp holds may contain its best match.  `cur` is row_best[j0 + lane] read a little
-// earlier (it only ever grows, so a stale value merely costs a useless atomic).  Almost every group is
-// rejected by the gate -- no element of the 32 x 32 block beats the weakest of the 32 columns' current
-// bests; otherwise a transposed butterfly (31 shuffles) leaves lane c with column c's maximum over the
-// warp's rows and the improved columns publish (sim, row) with one 64-bit atomicMax each.
-__device__ __forceinline__ void join_column_update(const float (&v)[32], float mx, unsigned long long cur, int j0,
-                                                   long long i_glob, int lane, const Tc2Args& a) {
-  const float cur_s = (j0 + lane < a.n_rows) ? best_sim(cur) : INFINITY;
-  float lb = cur_s;
+// and the 32 rows this warp holds may contain its best match.  Almost every 32 x 32 group is rejected by the
+// GATE -- no element beats the weakest current best of the group's 32 columns.  The gate values of a tile are
+// fetched one tile ahead (row_best only ever grows, so a stale value merely lets a useless group through):
+// lane c of `lbv` holds the minimum over group c's columns.
+template <int N_TILE>
+__device__ __forceinline__ void gate_prefetch(unsigned long long (&raw)[N_TILE / 32], const Tc2Args& a, int col_base, int lane) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) lb = fminf(lb, __shfl_xor_sync(0xffffffffu, lb, o));
-  if (!__any_sync(0xffffffffu, mx > lb)) return;
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    const int j = col_base + c * 32 + lane;
+    raw[c] = (j < a.n_rows) ? __ldcg(a.row_best + j) : ~0ull;  // ~0: padding column, never improved
+  }
+}
+// `cache` (shared memory, one copy per epilogue warp) keeps the per-column values for the groups that pass.
+template <int N_TILE>
+__device__ __forceinline__ float gate_reduce(const unsigned long long (&raw)[N_TILE / 32], int lane, float* cache) {
+  float lbv = INFINITY;
+  __syncwarp();
+#pragma unroll
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    float s = (raw[c] == ~0ull) ? INFINITY : best_sim(raw[c]);
+    cache[c * 32 + lane] = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = fminf(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if (lane == c) lbv = s;
+  }
+  __syncwarp();
+  return lbv;
+}
+
+// A group passed the gate: a transposed butterfly (31 shuffles) leaves lane c with column c's maximum over
+// the warp's rows; the columns that beat their current best publish (sim, row) with one 64-bit atomicMax.
+__device__ __forceinline__ void join_column_update(const float (&v)[32], bool row_ok, float cur_s, int j0, long long i_glob,
+                                                   int lane, const Tc2Args& a) {
   float w16[16], w8[8], w4[4], w2[2];
   const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
 #pragma unroll
   for (int k = 0; k < 16; ++k) {
-    const float send = b4 ? v[k] : v[k + 16], keep = b4 ? v[k + 16] : v[k];
+    // padding rows of the last block are zero vectors: they must not win any column
+    const float lo = row_ok ? v[k] : -INFINITY, hi = row_ok ? v[k + 16] : -INFINITY;
+    const float send = b4 ? lo : hi, keep = b4 ? hi : lo;
     w16[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 16));
   }
 #pragma unroll
@@ -201,7 +248,7 @@ __device__ __forceinline__ void join_column_update(const float (&v)[32], float m
   for (int c = 0; c < 32; ++c) {
     if (improved & (1u << c)) {  // warp-uniform
       const float mc = __shfl_sync(0xffffffffu, m, c);
-      const unsigned int who = __ballot_sync(0xffffffffu, v[c] == mc);
+      const unsigned int who = __ballot_sync(0xffffffffu, row_ok && v[c] == mc);
       if (who && lane == c) atomicMax(&a.row_best[j0 + c], pack_best(mc, i_glob - lane + (__ffs(who) - 1)));
     }
   }
@@ -213,19 +260,14 @@ __device__ __forceinline__ void join_column_update(const float (&v)[32], float m
 // (min, max); the column direction updates the other block's best matches.
 template <int N_TILE>
 __device__ __forceinline__ void join_scan_tile_sym(JoinRow& r, const Tc2Args& a, long long i_glob, int lane, uint32_t tcol,
-                                                   int col_base, bool diag) {
+                                                   int col_base, bool diag, float lbv, const float* cache) {
   const bool row_ok = i_glob < a.n_rows;
 #pragma unroll 1
   for (int c = 0; c < N_TILE / 32; ++c) {
     const int j0 = col_base + c * 32;
-    unsigned long long cur = 0ull;
-    if (!diag && j0 + lane < a.n_rows) cur = __ldcg(a.row_best + j0 + lane);  // issued ahead of the TMEM load
     float v[32];
     ptx::tmem_ld_32x32(tcol + c * 32, v);
-    if (!row_ok) {  // padding rows of the last block: zero vectors, must not win any column
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = -INFINITY;
-    } else if (j0 + 32 > a.n_rows) {
+    if (j0 + 32 > a.n_rows) {  // ragged last tile (warp-uniform)
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j0 + j >= a.n_rows) v[j] = -INFINITY;
@@ -238,7 +280,8 @@ __device__ __forceinline__ void join_scan_tile_sym(JoinRow& r, const Tc2Args& a,
     float mx = v[0];
 #pragma unroll
     for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-    if (mx > r.best) {
+    if (!row_ok) mx = -INFINITY;  // padding rows of the last block take no part (their sims are all 0)
+    if (mx > r.best) {  // rare: r.best starts from the row's best so far (see the item prologue)
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (v[j] > r.best) { r.best = v[j]; r.best_j = j0 + j; }
@@ -262,12 +305,16 @@ __device__ __forceinline__ void join_scan_tile_sym(JoinRow& r, const Tc2Args& a,
       }
     }
     __syncwarp();
-    if (!diag) join_column_update(v, mx, cur, j0, i_glob, lane, a);
+    if (!diag) {
+      const float lb = __shfl_sync(0xffffffffu, lbv, c);
+      // cache[]: the columns' bests as of one tile ago (+inf for padding columns) -- stale values only cost atomics
+      if (__any_sync(0xffffffffu, mx > lb)) join_column_update(v, row_ok, cache[c * 32 + lane], j0, i_glob, lane, a);
+    }
   }
 }
 
 template <int MODE, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EPI == 1) ? kJoinThreads : kThreads, 1)
 search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                   const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
                   const Tc2Args a) {
@@ -277,6 +324,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   constexpr uint32_t kEBytes = T::PE * kEPlaneBytes;
   constexpr uint32_t kStageBytes = kEBytes + T::PQ * kQPlaneBytes;   // [corpus half planes | query planes]
   constexpr uint32_t kTmemCols = 2 * kNTile;
+  constexpr int kEpiWarps = (EPI == EPI_JOIN) ? kJoinEpiWarps : 4;
+  constexpr int kColsPerWarp = kNTile * 4 / kEpiWarps;   // columns of a tile one epilogue warp walks
   constexpr uint32_t kIdesc = ptx::make_idesc_bf16(2 * kQueryBlock, kNTile);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -311,7 +360,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&bar_acc_full[b], 1);
-      ptx::mbar_init(&bar_acc_empty[b], 8);  // 4 epilogue warps x 2 CTAs
+      ptx::mbar_init(&bar_acc_empty[b], 2 * kEpiWarps);  // every epilogue warp of both CTAs
     }
     ptx::fence_mbar_init();
   }
@@ -332,11 +381,10 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     // chunk: leave it in L2 at normal priority unless this is the only pair
     const uint64_t e_policy = a.n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-      int qpair, t0, t1, tbase;
-      item_span(a, item, qpair, t0, t1, tbase);
-      const int qrow = (qpair * 2 + static_cast<int>(rank)) * kQueryBlock + (a.sym ? static_cast<int>(a.a_offset) : 0);
-      for (int o = t0; o < t1; ++o) {
-        const int row0 = tile_at(a, tbase, o) * kNTile + static_cast<int>(rank) * kHalfRows;
+      const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
+      const int qrow = (sp.qpair * 2 + static_cast<int>(rank)) * kQueryBlock + (a.sym ? static_cast<int>(a.a_offset) : 0);
+      for (int step = 0; step < sp.len; ++step) {
+        const int row0 = tile_at(a, sp.tbase, span_offset(sp, step)) * kNTile + static_cast<int>(rank) * kHalfRows;
         for (int kb = 0; kb < a.n_kb; ++kb) {
           ptx::mbar_wait(&bar_empty[st], ph ^ 1);
           if (ptx::elect_one()) {
@@ -363,9 +411,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       uint32_t acc_phase = 0;
       const uint32_t ring_addr = ptx::smem_u32(ring);
       for (int item = cluster_id; item < a.n_items; item += n_clusters) {
-        int qpair, t0, t1, tbase;
-        item_span(a, item, qpair, t0, t1, tbase);
-        for (int t = t0; t < t1; ++t) {
+        const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
+        for (int step = 0; step < sp.len; ++step) {
           ptx::mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kNTile);
@@ -410,23 +457,47 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {
       const int chunk = item / a.n_qpairs;
-      int qpair, t0, t1, tbase;
-      item_span(a, item, qpair, t0, t1, tbase);
-      const int qb = qpair * 2 + static_cast<int>(rank);
+      const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
+      const int qb = sp.qpair * 2 + static_cast<int>(rank);
       l.cnt = 0;
       l.thr = seed_threshold(a.seed, a.seed_stride, a.seed_off, a.n_queries, qb, qlane);
       float best = -INFINITY;
       JoinRow jr = {-INFINITY, -1, 0};
       const int i_row = qb * kQueryBlock + qlane;
-      for (int o = t0; o < t1; ++o) {
-        const int t = tile_at(a, tbase, o);
+      if (EPI == EPI_JOIN && i_row < a.m_rows) {
+        // Start from the best this row has met so far (other items of the same rows, and -- symmetric join -- the
+        // column direction of other blocks): the warp then takes the "new best" path only for real improvements
+        // instead of ~32 ln(groups) times per item.
+        jr.best = best_sim(__ldcg(a.row_best + (a.sym ? i_row + a.a_offset : i_row)));
+      }
+      const int col0 = ((warp - 2) >> 2) * kColsPerWarp;   // this warp's first column inside a tile
+      unsigned long long gate_raw[kColsPerWarp / 32];  // symmetric join: current bests of the NEXT tile's columns
+      float* col_cache = list_s + (warp - 2) * kColsPerWarp;  // the join keeps no candidate lists: their memory is free
+      if (EPI == EPI_JOIN && a.sym && sp.len > 0)
+        gate_prefetch<kColsPerWarp>(gate_raw, a, tile_at(a, sp.tbase, span_offset(sp, 0)) * kNTile + col0, lane);
+      for (int step = 0; step < sp.len; ++step) {
+        const int o = span_offset(sp, step);
+        const int t = tile_at(a, sp.tbase, o);
+        float lbv = INFINITY;
+        if (EPI == EPI_JOIN && a.sym) {
+          if (o > 0) lbv = gate_reduce<kColsPerWarp>(gate_raw, lane, col_cache);  // (the diagonal tile has no column direction)
+          if (step + 1 < sp.len)
+            gate_prefetch<kColsPerWarp>(gate_raw, a, tile_at(a, sp.tbase, span_offset(sp, step + 1)) * kNTile + col0, lane);
+        }
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * kNTile);
         if (EPI == EPI_TOPK && a.max_out) best = max_tile<kNTile>(best, tcol, t * kNTile, a.n_rows);
         else if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
-        else if (a.sym) join_scan_tile_sym<kNTile>(jr, a, i_row + a.a_offset, lane, tcol, t * kNTile, o == 0);
-        else join_scan_tile<kNTile>(jr, a, i_row, tcol, t * kNTile);
+        else if (a.sym)
+          join_scan_tile_sym<kColsPerWarp>(jr, a, i_row + a.a_offset, lane, tcol + col0, t * kNTile + col0, o == 0, lbv, col_cache);
+        else join_scan_tile<kColsPerWarp>(jr, a, i_row, tcol + col0, t * kNTile + col0);
+        if (EPI == EPI_JOIN && (step & 31) == 31 && jr.best_j >= 0 && i_row < a.m_rows) {
+          // publish the row's running best every 32 tiles, not only at the end of a (possibly very long) item: the
+          // column-direction gates of the OTHER blocks read row_best, and the sooner it is tight the fewer groups pass
+          atomicMax(&a.row_best[a.sym ? i_row + a.a_offset : i_row], pack_best(jr.best, jr.best_j));
+          jr.best_j = -1;
+        }
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_leader(&bar_acc_empty[acc]);
@@ -469,7 +540,7 @@ int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
                const CUtensorMap& q1, const Tc2Args& args, cudaStream_t stream) {
   auto kern = search_tc2_kernel<MODE, EPI>;
   DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
-  kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
+  kern<<<plan.grid, EPI == EPI_JOIN ? kJoinThreads : kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -537,6 +608,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.a_offset = 0;
   a.sym = 0;
   a.blk0 = 0;
+  a.rotate = 0;
   a.row_best = nullptr;
   a.row_count = nullptr;
   a.pair_i = a.pair_j = nullptr;
@@ -560,10 +632,27 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   const int n_qb = static_cast<int>(m_pad / kQueryBlock);
   const int64_t all_tiles = ceil_div(n_rows, kNTile);
   if (sym && (a_offset % kNTile) != 0) return fail("symmetric join: the row range must start on a multiple of 256");
-  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, 0, sym ? all_tiles / 2 + 1 : 0));
+  int sym_chunks = 0;
+  if (sym) {
+    // Items are dealt chunk-major (all row blocks walk their first chunk of tiles, then the second, ...), so a
+    // handful of chunks per row block lets every row publish a tight running best early -- the column-direction
+    // gates of all blocks read those -- while items stay long enough (>= 64 tiles) to hide their prologue.
+    // Measured at 1M x 512 (B200, power-capped): 1 chunk 470 ms, 8 chunks 405 ms, 32 chunks 465 ms.
+    const int64_t clusters = std::max(1, sm_count / 2), qpairs = n_qb / 2, per_item = all_tiles / 2 + 1;
+    const int64_t want = std::max<int64_t>(1, std::min<int64_t>(8, per_item / 64));
+    for (int64_t c = want; c <= per_item; ++c) {  // ... and at most 2 % of the cluster-rounds idle
+      const int64_t items = c * qpairs, rounds = ceil_div(items, clusters);
+      sym_chunks = static_cast<int>(c);
+      if (static_cast<double>(items) >= 0.98 * static_cast<double>(rounds * clusters)) break;
+    }
+    if (const char* env = getenv("DEWI_JOIN_CHUNKS")) sym_chunks = std::max(1, atoi(env));  // experiments
+  }
+  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, sym_chunks, sym ? all_tiles / 2 + 1 : 0));
   Tc2Args a;
   a.sym = sym ? 1 : 0;
   a.blk0 = sym ? static_cast<int>(a_offset / kNTile) : 0;
+  a.rotate = 1;
+  if (const char* env = getenv("DEWI_JOIN_ROTATE")) a.rotate = atoi(env) != 0;  // experiments
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
   a.n_kb = dim / kKBlock;

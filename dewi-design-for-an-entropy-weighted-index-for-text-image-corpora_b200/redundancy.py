@@ -82,11 +82,15 @@ def redundancy_join(a, b=None, tau: float = 0.9, pair_cap: int = 1 << 20, device
         (0 if symmetric else _native.JOIN_NO_SYMMETRY)
     lib = _native.load_library()
     with torch.cuda.device(dev):
+        # scratch (operand planes, packed statistics) comes from torch's caching allocator: no cudaMalloc / cudaFree per call
+        ws_bytes = int(lib.dewi_join_workspace_bytes(m, tb.shape[0], ta.shape[1], int(self_join), flags))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=tdev)
         rc = lib.dewi_join(ctypes.c_void_p(ta.data_ptr()), m, ctypes.c_void_p(tb.data_ptr()), tb.shape[0], ta.shape[1],
                            float(tau), int(self_join), int(a_offset), flags, ctypes.c_void_p(row_max.data_ptr()),
                            ctypes.c_void_p(row_arg.data_ptr()), ctypes.c_void_p(row_cnt.data_ptr()),
                            ctypes.c_void_p(pi.data_ptr()), ctypes.c_void_p(pj.data_ptr()), ctypes.c_void_p(ps.data_ptr()),
-                           int(pair_cap), ctypes.byref(cnt), dev, _native.stream_ptr())
+                           int(pair_cap), ctypes.byref(cnt), ctypes.c_void_p(ws.data_ptr()), ws_bytes, dev, _native.stream_ptr())
+        del ws
     _native.check(rc)
     kept = min(int(cnt.value), pair_cap)
     return {"max_sim": row_max, "argmax": row_arg, "count": row_cnt, "pairs_i": pi[:kept], "pairs_j": pj[:kept],
@@ -121,11 +125,14 @@ def self_join_range(x, row_lo: int, row_hi: int, tau: float = 0.9, pair_cap: int
     flags = _native.JOIN_BF16 if precision in ("bf16", "bfloat16") else 0
     lib = _native.load_library()
     with torch.cuda.device(dev):
+        ws_bytes = int(lib.dewi_join_workspace_bytes(n, n, tx.shape[1], 1, flags | _native.JOIN_FORCE_TC))
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=tdev)
         rc = lib.dewi_self_join_range(ctypes.c_void_p(tx.data_ptr()), n, tx.shape[1], float(tau), int(row_lo), int(row_hi),
                                       flags, ctypes.c_void_p(row_max.data_ptr()), ctypes.c_void_p(row_arg.data_ptr()),
                                       ctypes.c_void_p(row_cnt.data_ptr()), ctypes.c_void_p(pi.data_ptr()),
                                       ctypes.c_void_p(pj.data_ptr()), ctypes.c_void_p(ps.data_ptr()), int(pair_cap),
-                                      ctypes.byref(cnt), dev, _native.stream_ptr())
+                                      ctypes.byref(cnt), ctypes.c_void_p(ws.data_ptr()), ws_bytes, dev, _native.stream_ptr())
+        del ws
     _native.check(rc)
     kept = min(int(cnt.value), pair_cap)
     return {"max_sim": row_max, "argmax": row_arg, "count": row_cnt, "pairs_i": pi[:kept], "pairs_j": pj[:kept],

@@ -148,9 +148,14 @@ DEWI_API int dewi_similarity_dense(const float* a, int64_t m, const float* b, in
  * half of the block grid; an off-diagonal tile updates the statistics of its rows and of its columns);
  * DEWI_JOIN_NO_SYMMETRY evaluates the full M x N product instead (tests / comparison).             */
 enum { DEWI_JOIN_BF16 = 1 << 0, DEWI_JOIN_FORCE_SIMT = 1 << 1, DEWI_JOIN_FORCE_TC = 1 << 2, DEWI_JOIN_NO_SYMMETRY = 1 << 3 };
+/* Scratch memory (normalised operand planes, packed row statistics): `workspace` is a device buffer of at
+ * least dewi_join_workspace_bytes(...) bytes owned by the caller -- the Python wrapper passes a torch tensor,
+ * so repeated joins cost no cudaMalloc / cudaFree; NULL makes the call allocate and free its own.
+ * For dewi_self_join_range use dewi_join_workspace_bytes(n, n, d, 1, flags).                          */
+DEWI_API int64_t dewi_join_workspace_bytes(int64_t m, int64_t n, int d, int self_join, int flags);
 DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int d, float tau, int self_join,
               int64_t a_offset, int flags, float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
-              int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
+              int64_t pair_cap, int64_t* pair_count_host, void* workspace, int64_t workspace_bytes, int device, void* stream);
 
 /* One rank's share of a row-sharded SYMMETRIC self-join of x[n, d] (every rank holds all rows): the row
  * blocks of [row_lo, row_hi) (multiples of 256, or ending at n) against their half of the block grid --
@@ -162,7 +167,7 @@ DEWI_API int dewi_join(const float* a, int64_t m, const float* b, int64_t n, int
  * (d % 64 == 0); flags: DEWI_JOIN_BF16.  [row_lo, row_hi) = [0, n) is the whole self-join.            */
 DEWI_API int dewi_self_join_range(const float* x, int64_t n, int d, float tau, int64_t row_lo, int64_t row_hi, int flags,
               float* row_max, int64_t* row_argmax, int32_t* row_count, int64_t* pair_i, int64_t* pair_j, float* pair_sim,
-              int64_t pair_cap, int64_t* pair_count_host, int device, void* stream);
+              int64_t pair_cap, int64_t* pair_count_host, void* workspace, int64_t workspace_bytes, int device, void* stream);
 
 /* ---- neighbours of the path that reuse its kernels -------------------------- */
 /* local_weights_from_surprisal (src/dewi/local_weights.py:5-26): float32 median / MAD (+1e-8), z-score,

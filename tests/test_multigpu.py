@@ -72,7 +72,7 @@ def test_nccl_sharded_search_matches_oracle(dtype):
         assert recall_at_k(rid, ids) >= 0.999
 
 
-def _join_worker(rank, world, port, n, d, tau, ret):
+def _join_worker(rank, world, port, n, d, tau, align, ret):
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -85,15 +85,17 @@ def _join_worker(rank, world, port, n, d, tau, ret):
         rng = np.random.RandomState(71)
         x = rng.standard_normal((n, d)).astype(np.float32)
         x[1::50] = x[0:-1:50] * 1.1 + 0.02 * rng.standard_normal((len(x[1::50]), d)).astype(np.float32)
-        lo, hi = shard_range(n, world, rank, align=64)
+        lo, hi = shard_range(n, world, rank, align=align)
         out = dewi_b200.sharded_self_join(torch.from_numpy(x[lo:hi]).cuda(), tau=tau, precision="fp32")
         assert out["row_offset"] == lo
-        ret[rank] = (out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist(), out["max_sim"].cpu().numpy())
+        ret[rank] = (out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist(), out["max_sim"].cpu().numpy(),
+                     out["count"].cpu().numpy(), out["argmax"].cpu().numpy())
     finally:
         dist.destroy_process_group()
 
 
-def test_nccl_sharded_self_join_matches_oracle():
+@pytest.mark.parametrize("align", [256, 64])  # 256: symmetric range join + all-reduced statistics; 64: a_offset slices
+def test_nccl_sharded_self_join_matches_oracle(align):
     import torch.multiprocessing as mp
 
     from oracle import redundancy as ored
@@ -107,14 +109,21 @@ def test_nccl_sharded_self_join_matches_oracle():
         port = s.getsockname()[1]
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_join_worker, args=(world, port, n, d, tau, ret), nprocs=world, join=True)
+        mp.spawn(_join_worker, args=(world, port, n, d, tau, align, ret), nprocs=world, join=True)
         parts = [ret[r] for r in range(world)]
     rng = np.random.RandomState(71)
     x = rng.standard_normal((n, d)).astype(np.float32)
     x[1::50] = x[0:-1:50] * 1.1 + 0.02 * rng.standard_normal((len(x[1::50]), d)).astype(np.float32)
     mx, am, cnt, pairs = ored.join_rowstats(x, x, tau, self_join=True)
     got = set()
-    for pi, pj, _ in parts:
-        got |= set(zip(pi, pj))
-    assert got == {(i, j) for i, j, _ in pairs} and len(got) > 50
+    n_emitted = 0
+    for p in parts:
+        got |= set(zip(p[0], p[1]))
+        n_emitted += len(p[0])
+    assert got == {(i, j) for i, j, _ in pairs} and len(got) > 50 and n_emitted == len(got)
     np.testing.assert_allclose(np.concatenate([p[2] for p in parts]), mx, atol=1e-5)
+    np.testing.assert_array_equal(np.concatenate([p[3] for p in parts]), cnt)
+    sim = ored.cross_modal_similarity(x, x)
+    np.fill_diagonal(sim, -np.inf)
+    arg = np.concatenate([p[4] for p in parts])
+    assert np.all(sim[np.arange(n), arg] >= mx - 1e-5)
