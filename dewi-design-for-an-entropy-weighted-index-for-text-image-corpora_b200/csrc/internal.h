@@ -85,7 +85,7 @@ struct Tc2Plan {
   size_t smem_bytes;
 };
 int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks = 0,
-                  int64_t tiles_per_item = 0);
+                  int64_t tiles_per_item = 0, int a_resident = 0);
 int tc2_box_rows();
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,

@@ -313,7 +313,12 @@ __device__ __forceinline__ void join_scan_tile_sym(JoinRow& r, const Tc2Args& a,
   }
 }
 
-template <int MODE, int EPI>
+// ARES = 1 ("A resident", join only): the row block on the M side -- 128 rows x dim per CTA -- is loaded ONCE per
+// work item into its own shared-memory buffer instead of being re-streamed from L2 with every corpus tile; the
+// ring then carries only the corpus halves.  That halves the L2 -> SM operand traffic (at D = 512 the re-streamed
+// row block is half of the ~10 TB/s the sweep pulls through the crossbar), which is what the power-capped chip
+// converts into clock.  Needs 128 * dim * 2 * planes bytes next to a ring of >= 4 stages: bf16 planes up to dim 640.
+template <int MODE, int EPI, int ARES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((EPI == 1) ? kJoinThreads : kThreads, 1)
 search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                   const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
@@ -322,7 +327,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   constexpr uint32_t kEPlaneBytes = kHalfRows * 128;   // this CTA's half of a corpus k-block
   constexpr uint32_t kQPlaneBytes = kQueryBlock * 128;
   constexpr uint32_t kEBytes = T::PE * kEPlaneBytes;
-  constexpr uint32_t kStageBytes = kEBytes + T::PQ * kQPlaneBytes;   // [corpus half planes | query planes]
+  constexpr uint32_t kQBytes = T::PQ * kQPlaneBytes;
+  constexpr uint32_t kStageBytes = kEBytes + (ARES ? 0u : kQBytes);   // [corpus half planes | query planes]
   constexpr uint32_t kTmemCols = 2 * kNTile;
   constexpr int kEpiWarps = (EPI == EPI_JOIN) ? kJoinEpiWarps : 4;
   constexpr int kColsPerWarp = kNTile * 4 / kEpiWarps;   // columns of a tile one epilogue warp walks
@@ -332,7 +338,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // ONE ring: both operands of a k-block arrive from L2 at the same rate here, and one full / one empty
   // barrier per k-block keeps the single-threaded MMA issue loop short.
-  uint8_t* ring = smem;
+  uint8_t* a_buf = smem;                                   // ARES: [k-block][plane] row-block tiles, n_kb * kQBytes
+  uint8_t* ring = smem + (ARES ? static_cast<size_t>(a.n_kb) * kQBytes : 0);
   const int kl = a.kc + kPending;
   float* list_s = reinterpret_cast<float*>(ring + static_cast<size_t>(a.e_stages) * kStageBytes);
   int* list_i = reinterpret_cast<int*>(list_s + kl * kQueryBlock);
@@ -340,7 +347,9 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   uint64_t* bar_empty = bar_full + kMaxStages;
   uint64_t* bar_acc_full = bar_empty + kMaxStages;
   uint64_t* bar_acc_empty = bar_acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_a_full = bar_acc_empty + 2;    // ARES: the item's row block has landed (leader; both CTAs' bytes)
+  uint64_t* bar_a_empty = bar_a_full + 1;      // ARES: the item's last MMA has read it (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a_empty + 1);
 
   // warp-uniform role index (the shuffle tells the compiler so)
   const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -362,6 +371,8 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       ptx::mbar_init(&bar_acc_full[b], 1);
       ptx::mbar_init(&bar_acc_empty[b], 2 * kEpiWarps);  // every epilogue warp of both CTAs
     }
+    ptx::mbar_init(bar_a_full, 2);
+    ptx::mbar_init(bar_a_empty, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -380,22 +391,39 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     // a corpus tile is read again by the clusters working on the other query-block pairs of the same
     // chunk: leave it in L2 at normal priority unless this is the only pair
     const uint64_t e_policy = a.n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
+    uint32_t a_ph = 0;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {
       const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
       const int qrow = (sp.qpair * 2 + static_cast<int>(rank)) * kQueryBlock + (a.sym ? static_cast<int>(a.a_offset) : 0);
+      if (ARES && sp.len > 0) {
+        ptx::mbar_wait(bar_a_empty, a_ph ^ 1);   // the previous item's MMAs are done with the buffer
+        if (ptx::elect_one()) {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(bar_a_full, 2 * static_cast<uint32_t>(a.n_kb) * kQBytes);
+          else ptx::mbar_arrive_leader(bar_a_full);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            uint8_t* dst = a_buf + static_cast<size_t>(kb) * kQBytes;
+            ptx::tma_load_2d_pair(dst, &map_q0, bar_a_full, kb * kKBlock, qrow, ptx::kEvictFirst);
+            if (T::PQ > 1) ptx::tma_load_2d_pair(dst + kQPlaneBytes, &map_q1, bar_a_full, kb * kKBlock, qrow, ptx::kEvictFirst);
+          }
+        }
+        __syncwarp();
+        a_ph ^= 1;
+      }
       for (int step = 0; step < sp.len; ++step) {
         const int row0 = tile_at(a, sp.tbase, span_offset(sp, step)) * kNTile + static_cast<int>(rank) * kHalfRows;
         for (int kb = 0; kb < a.n_kb; ++kb) {
           ptx::mbar_wait(&bar_empty[st], ph ^ 1);
           if (ptx::elect_one()) {
-            uint8_t* sp = ring + static_cast<size_t>(st) * kStageBytes;
+            uint8_t* stg = ring + static_cast<size_t>(st) * kStageBytes;
             if (rank == 0) ptx::mbar_arrive_expect_tx(&bar_full[st], 2 * kStageBytes);
             else ptx::mbar_arrive_leader(&bar_full[st]);
-            ptx::tma_load_2d_pair(sp, &map_e0, &bar_full[st], kb * kKBlock, row0, e_policy);
-            if (T::PE > 1) ptx::tma_load_2d_pair(sp + kEPlaneBytes, &map_e1, &bar_full[st], kb * kKBlock, row0, e_policy);
-            ptx::tma_load_2d_pair(sp + kEBytes, &map_q0, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
-            if (T::PQ > 1)
-              ptx::tma_load_2d_pair(sp + kEBytes + kQPlaneBytes, &map_q1, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
+            ptx::tma_load_2d_pair(stg, &map_e0, &bar_full[st], kb * kKBlock, row0, e_policy);
+            if (T::PE > 1) ptx::tma_load_2d_pair(stg + kEPlaneBytes, &map_e1, &bar_full[st], kb * kKBlock, row0, e_policy);
+            if (!ARES) {
+              ptx::tma_load_2d_pair(stg + kEBytes, &map_q0, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
+              if (T::PQ > 1)
+                ptx::tma_load_2d_pair(stg + kEBytes + kQPlaneBytes, &map_q1, &bar_full[st], kb * kKBlock, qrow, ptx::kEvictLast);
+            }
           }
           __syncwarp();
           if (++st == a.e_stages) { st = 0; ph ^= 1; }
@@ -410,8 +438,15 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t ring_addr = ptx::smem_u32(ring);
+      const uint32_t a_addr = ptx::smem_u32(a_buf);
+      uint32_t a_full_ph = 0;
       for (int item = cluster_id; item < a.n_items; item += n_clusters) {
         const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
+        if (ARES && sp.len > 0) {
+          ptx::mbar_wait(bar_a_full, a_full_ph);   // the item's row block (both CTAs' halves of M) has landed
+          ptx::tc_fence_after();
+          a_full_ph ^= 1;
+        }
         for (int step = 0; step < sp.len; ++step) {
           ptx::mbar_wait(&bar_acc_empty[acc], acc_phase ^ 1);  // both CTAs' epilogues drained this accumulator
           ptx::tc_fence_after();
@@ -420,11 +455,12 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
             ptx::mbar_wait(&bar_full[st], ph);  // both CTAs' TMA bytes have landed
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-              const uint32_t sp = ring_addr + static_cast<uint32_t>(st) * kStageBytes;
-              const uint64_t de0 = ptx::make_desc_sw128(sp);
-              const uint64_t de1 = ptx::make_desc_sw128(sp + kEPlaneBytes);
-              const uint64_t dq0 = ptx::make_desc_sw128(sp + kEBytes);
-              const uint64_t dq1 = ptx::make_desc_sw128(sp + kEBytes + kQPlaneBytes);
+              const uint32_t stg = ring_addr + static_cast<uint32_t>(st) * kStageBytes;
+              const uint32_t qa = ARES ? a_addr + static_cast<uint32_t>(kb) * kQBytes : stg + kEBytes;
+              const uint64_t de0 = ptx::make_desc_sw128(stg);
+              const uint64_t de1 = ptx::make_desc_sw128(stg + kEPlaneBytes);
+              const uint64_t dq0 = ptx::make_desc_sw128(qa);
+              const uint64_t dq1 = ptx::make_desc_sw128(qa + kQPlaneBytes);
 #pragma unroll
               for (int k = 0; k < kKBlock / 16; ++k) {
                 const uint64_t adv = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 B = 2 x 16 B units
@@ -433,7 +469,10 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
                 if (MODE == 2) ptx::mma_bf16_ss_pair(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
               }
               ptx::mma_commit_pair(&bar_empty[st], 3);  // frees the slot in both CTAs
-              if (kb == a.n_kb - 1) ptx::mma_commit_pair(&bar_acc_full[acc], 3);
+              if (kb == a.n_kb - 1) {
+                ptx::mma_commit_pair(&bar_acc_full[acc], 3);
+                if (ARES && step == sp.len - 1) ptx::mma_commit_pair(bar_a_empty, 3);  // row block free for the next item
+              }
             }
             __syncwarp();
             if (++st == a.e_stages) { st = 0; ph ^= 1; }
@@ -527,18 +566,22 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   }
 }
 
-size_t stage_bytes(int mode) {
+size_t stage_bytes(int mode, bool a_resident = false) {
   const int pe = (mode == 2) ? 2 : 1, pq = (mode == 0) ? 1 : 2;
-  return static_cast<size_t>(pe) * kHalfRows * 128 + static_cast<size_t>(pq) * kQueryBlock * 128;
+  return static_cast<size_t>(pe) * kHalfRows * 128 + (a_resident ? 0 : static_cast<size_t>(pq) * kQueryBlock * 128);
+}
+size_t a_resident_bytes(int mode, int dim) {
+  const int pq = (mode == 0) ? 1 : 2;
+  return static_cast<size_t>(dim / kKBlock) * pq * kQueryBlock * 128;
 }
 size_t fixed_bytes(int kc) {
-  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 4) * 8 + 16 + 1024 /*alignment slack*/;
+  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 6) * 8 + 16 + 1024 /*alignment slack*/;
 }
 
-template <int MODE, int EPI>
+template <int MODE, int EPI, int ARES = 0>
 int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, const Tc2Args& args, cudaStream_t stream) {
-  auto kern = search_tc2_kernel<MODE, EPI>;
+  auto kern = search_tc2_kernel<MODE, EPI, ARES>;
   DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
   kern<<<plan.grid, EPI == EPI_JOIN ? kJoinThreads : kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
   DEWI_CUDA(cudaGetLastError());
@@ -548,12 +591,12 @@ int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 }  // namespace
 
 int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks,
-                  int64_t tiles_per_item) {
+                  int64_t tiles_per_item, int a_resident) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
   const size_t smem_max = 227 * 1024;
-  const size_t fixed = fixed_bytes(kc);
-  int stages = fixed < smem_max ? static_cast<int>((smem_max - fixed) / stage_bytes(mode)) : 0;
+  const size_t fixed = fixed_bytes(kc) + (a_resident ? a_resident_bytes(mode, dim) : 0);
+  int stages = fixed < smem_max ? static_cast<int>((smem_max - fixed) / stage_bytes(mode, a_resident != 0)) : 0;
   if (const char* env = getenv("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));
   if (stages < 2) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
   stages = std::min(stages, kMaxStages);
@@ -576,7 +619,7 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   plan->q_stages = 0;
   plan->n_chunks = static_cast<int>(chunks);
   plan->grid = 2 * static_cast<int>(std::min<int64_t>(clusters, chunks * n_qpairs));
-  plan->smem_bytes = fixed + static_cast<size_t>(stages) * stage_bytes(mode);
+  plan->smem_bytes = fixed + static_cast<size_t>(stages) * stage_bytes(mode, a_resident != 0);
   return 0;
 }
 
@@ -647,7 +690,10 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
     }
     if (const char* env = getenv("DEWI_JOIN_CHUNKS")) sym_chunks = std::max(1, atoi(env));  // experiments
   }
-  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, sym_chunks, sym ? all_tiles / 2 + 1 : 0));
+  // row block resident in shared memory when it fits next to a ring of at least 4 stages
+  bool a_res = fixed_bytes(0) + a_resident_bytes(mode, dim) + 4 * stage_bytes(mode, true) <= 227 * 1024;
+  if (const char* env = getenv("DEWI_JOIN_ARES")) a_res = a_res && atoi(env) != 0;  // experiments
+  DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, sym_chunks, sym ? all_tiles / 2 + 1 : 0, a_res ? 1 : 0));
   Tc2Args a;
   a.sym = sym ? 1 : 0;
   a.blk0 = sym ? static_cast<int>(a_offset / kNTile) : 0;
@@ -678,6 +724,8 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.pair_sim = pair_sim;
   a.pair_cap = pair_cap;
   a.pair_count = pair_count;
+  if (mode == 0 && a_res) return launch_one<0, EPI_JOIN, 1>(plan, b0, b1, a0, a1, a, stream);
+  if (mode == 2 && a_res) return launch_one<2, EPI_JOIN, 1>(plan, b0, b1, a0, a1, a, stream);
   if (mode == 0) return launch_one<0, EPI_JOIN>(plan, b0, b1, a0, a1, a, stream);
   if (mode == 2) return launch_one<2, EPI_JOIN>(plan, b0, b1, a0, a1, a, stream);
   return fail("unsupported join precision mode");
