@@ -10,6 +10,7 @@
 //   in float64 with one rounding per operation (no FMA contraction), so results match the reference's
 //   Python-float arithmetic; HBM-bound: 7 fp32 loads and one store per row.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -68,14 +69,19 @@ __device__ __forceinline__ unsigned int load_key(const void* col, long long i, f
   return orderable(v);
 }
 
-// Histogram of the current digit over the keys whose higher digits match a slot's prefix.  Real
-// signal columns put most keys into a handful of bins, so equal bins are combined inside the warp
-// (match.any) before the shared-memory atomic; one global atomic per non-empty bin at the end.
+__device__ void pick_column(int pass, int c, SelState* st, unsigned int* ghist, unsigned long long* cum,
+                            unsigned long long* wsum);
+
+// Histogram of the current digit over the keys whose higher digits match a slot's prefix: block-private
+// shared-memory histograms (per-thread run-length combining in front of the shared atomics), one global
+// atomic per non-empty bin at the end; the last block of a column then picks the bins (pick_column).
 template <int SRC>
 __global__ void __launch_bounds__(512)
 hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* __restrict__ n_dev, long long ld, int pass,
-            const SelState* __restrict__ st, unsigned int* __restrict__ ghist) {
-  __shared__ unsigned int sh[2 * kBins];
+            SelState* st, unsigned int* __restrict__ ghist, unsigned int* __restrict__ done) {
+  __shared__ __align__(8) unsigned int sh[2 * kBins];   // two slot histograms; reused as 2048 x u64 by pick_column
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned int ticket;
   const int c = blockIdx.y;
   int shift, nbins;
   unsigned int himask;
@@ -87,35 +93,64 @@ hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* 
   const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
   const long long n = n_dev ? static_cast<long long>(min(static_cast<long long>(n_dev[c]), n_host)) : n_host;
   const char* col = static_cast<const char*>(src) + static_cast<size_t>(c) * ld * 4;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   const unsigned int binmask = static_cast<unsigned int>(nbins - 1);
-  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < n; base += stride) {
-    const long long i = base + threadIdx.x;  // whole warps iterate together (base is warp-uniform)
-    unsigned int tgt = 0xFFFFFFFFu;
-    if (i < n) {
-      const unsigned int key = load_key<SRC>(col, i, med);
-      const unsigned int hi = key & himask;
-      const unsigned int bin = (key >> shift) & binmask;
-      if (hi == p0) tgt = bin;
-      else if (!same && hi == p1) tgt = kBins + bin;
+  // kHistUnroll independent loads per thread are issued before any of them is consumed: the passes over the
+  // small L2-resident key buffers (sample, window) are latency-bound otherwise (one dependent
+  // load -> match -> atomic chain per key).  Whole warps iterate together (base is warp-uniform).
+  constexpr int kHistUnroll = 8;
+  unsigned int run_bin = 0xFFFFFFFFu, run_cnt = 0u;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * kHistUnroll;
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x * kHistUnroll; base < n; base += stride) {
+    unsigned int key[kHistUnroll];
+    bool ok[kHistUnroll];
+#pragma unroll
+    for (int u = 0; u < kHistUnroll; ++u) {
+      const long long i = base + static_cast<long long>(u) * blockDim.x + threadIdx.x;
+      ok[u] = i < n;
+      key[u] = ok[u] ? load_key<SRC>(col, i, med) : 0u;
     }
-    const unsigned int peers = __match_any_sync(0xffffffffu, tgt);
-    if (tgt != 0xFFFFFFFFu && (__ffs(peers) - 1) == (threadIdx.x & 31)) atomicAdd(&sh[tgt], __popc(peers));
+#pragma unroll
+    for (int u = 0; u < kHistUnroll; ++u) {
+      unsigned int tgt = 0xFFFFFFFFu;
+      if (ok[u]) {
+        const unsigned int hi = key[u] & himask;
+        const unsigned int bin = (key[u] >> shift) & binmask;
+        if (hi == p0) tgt = bin;
+        else if (!same && hi == p1) tgt = kBins + bin;
+      }
+      // run-length combining per thread: real signal columns put most keys of a pass into a handful of bins
+      // (pass 0 sees 11 leading bits), so consecutive keys of a thread usually share their bin and cost no atomic
+      if (tgt != run_bin) {
+        if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
+        run_bin = tgt;
+        run_cnt = 0u;
+      }
+      ++run_cnt;
+    }
   }
+  if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
   __syncthreads();
   unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) {
     const unsigned int v = sh[i];
     if (v) atomicAdd(&g[i], v);
   }
+  // the last block to finish a column picks its bins (threadfence reduction pattern)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&done[c], 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  pick_column(pass, c, st, ghist, reinterpret_cast<unsigned long long*>(sh), wsum);
+  if (threadIdx.x == 0) done[c] = 0u;
 }
 
-// One block per column: locate the bin holding each slot's rank, extend the prefix, clear the histogram.
-__global__ void __launch_bounds__(1024)
-pick_kernel(int pass, SelState* st, unsigned int* ghist) {
-  __shared__ unsigned long long cum[kBins];
-  __shared__ unsigned long long wsum[32];
-  const int c = blockIdx.x;
+// Locate the bin holding each slot's rank, extend the prefix, clear the histogram.  Runs in the LAST block
+// of hist_kernel to finish a column (all of the block's threads; `cum` is the block's histogram memory
+// reused, `wsum` 32 more words), so a selection pass is one launch.
+__device__ void pick_column(int pass, int c, SelState* st, unsigned int* ghist, unsigned long long* cum,
+                            unsigned long long* wsum) {
   int shift, nbins;
   unsigned int himask;
   pass_bits(pass, shift, nbins, himask);
@@ -123,15 +158,18 @@ pick_kernel(int pass, SelState* st, unsigned int* ghist) {
   const int nslots = was_same ? 1 : 2;
   // ranks are read by every thread up front: the thread that finds the bin rewrites them below
   const unsigned long long rank_in[2] = {st->rank[c][0], st->rank[c][1]};
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per = kBins / T;  // consecutive bins per thread (T divides kBins)
   __syncthreads();
   for (int s = 0; s < nslots; ++s) {
     unsigned int* g = ghist + (static_cast<size_t>(c) * 2 + s) * kBins;
-    // inclusive scan of nbins (<= 2048) counts with 1024 threads, two bins per thread
-    const int t = threadIdx.x;
-    const unsigned long long a = (2 * t < nbins) ? g[2 * t] : 0ull;
-    const unsigned long long b = (2 * t + 1 < nbins) ? g[2 * t + 1] : 0ull;
-    unsigned long long x = a + b;
-    const int lane = t & 31, w = t >> 5;
+    unsigned long long mine[8];
+    unsigned long long x = 0ull;
+    for (int i = 0; i < per; ++i) {
+      const int bin = t * per + i;
+      mine[i] = (bin < nbins) ? __ldcg(g + bin) : 0u;
+      x += mine[i];
+    }
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
@@ -140,7 +178,7 @@ pick_kernel(int pass, SelState* st, unsigned int* ghist) {
     if (lane == 31) wsum[w] = x;
     __syncthreads();
     if (w == 0) {
-      unsigned long long y = wsum[lane];
+      unsigned long long y = (lane < T / 32) ? wsum[lane] : 0ull;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long z = __shfl_up_sync(0xffffffffu, y, o);
@@ -149,15 +187,17 @@ pick_kernel(int pass, SelState* st, unsigned int* ghist) {
       wsum[lane] = y;
     }
     __syncthreads();
-    const unsigned long long base = (w > 0) ? wsum[w - 1] : 0ull;
-    cum[2 * t] = base + x - b;   // inclusive up to bin 2t
-    cum[2 * t + 1] = base + x;   // inclusive up to bin 2t+1
+    unsigned long long run = ((w > 0) ? wsum[w - 1] : 0ull) + x;  // inclusive up to this thread's last bin
+    for (int i = per - 1; i >= 0; --i) {
+      cum[t * per + i] = run;
+      run -= mine[i];
+    }
     __syncthreads();
     // slots that share this histogram
     const int s_end = was_same ? 2 : s + 1;
     for (int ss = s; ss < s_end; ++ss) {
       const unsigned long long r = rank_in[ss];
-      for (int bin = threadIdx.x; bin < nbins; bin += blockDim.x) {
+      for (int bin = t; bin < nbins; bin += T) {
         const unsigned long long lo = (bin > 0) ? cum[bin - 1] : 0ull;
         if (r >= lo && r < cum[bin]) {
           st->prefix[c][ss] = (st->prefix[c][ss] & himask) | (static_cast<unsigned int>(bin) << shift);
@@ -166,10 +206,12 @@ pick_kernel(int pass, SelState* st, unsigned int* ghist) {
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) g[i] = 0u;
+    for (int i = t; i < kBins; i += T) g[i] = 0u;
     __syncthreads();
   }
-  if (threadIdx.x == 0 && was_same && st->prefix[c][0] != st->prefix[c][1]) st->same[c] = 0;
+  __threadfence();
+  __syncthreads();
+  if (t == 0 && was_same && st->prefix[c][0] != st->prefix[c][1]) st->same[c] = 0;
 }
 
 // The two middle ranks of n sorted values (equal when n is odd): np.median averages them in fp32.
@@ -423,6 +465,7 @@ struct FitWork {
   unsigned int* ghist = nullptr;
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
+  unsigned int* done = nullptr;   // per-column block tickets of hist_kernel (self-resetting)
   size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0;
   int sm_count = 148;
 };
@@ -441,23 +484,22 @@ int ensure_buf(unsigned int** p, size_t* have, size_t need) {
 
 template <int SRC>
 void select3(const void* src, long long n_host, const unsigned int* n_dev, long long ld, int f, SelState* st,
-             unsigned int* ghist, cudaStream_t stream) {
+             unsigned int* ghist, unsigned int* done, cudaStream_t stream) {
   const int threads = 512;
-  int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * 8), std::max(1, 148 * 4 / f)));
+  const int per_thread = 8;  // (64 keys per thread on the small key buffers measured slower: 43 vs 30 us per pass)
+  int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * per_thread), std::max(1, 148 * 4 / f)));
   dim3 grid(std::max(bx, 1), f);
-  for (int pass = 0; pass < 3; ++pass) {
-    hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist);
-    pick_kernel<<<f, 1024, 0, stream>>>(pass, st, ghist);
-  }
+  for (int pass = 0; pass < 3; ++pass)
+    hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist, done);
 }
 
 // Exact radix selection over the whole column: 3 full passes per statistic.
 void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, cudaStream_t stream) {
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_FULL, f, n, 0u, w.st);
-  select3<SRC_RAW>(cols, n, nullptr, ld, f, w.st, w.ghist, stream);
+  select3<SRC_RAW>(cols, n, nullptr, ld, f, w.st, w.ghist, w.done, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(FINAL_MED, f, n, 0u, w.st);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_FULL, f, n, 0u, w.st);
-  select3<SRC_DEV>(cols, n, nullptr, ld, f, w.st, w.ghist, stream);
+  select3<SRC_DEV>(cols, n, nullptr, ld, f, w.st, w.ghist, w.done, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(FINAL_MAD, f, n, 0u, w.st);
 }
 
@@ -466,13 +508,13 @@ void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, c
 template <int SRC>
 void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsigned int cap, FitWork& w, int final_op,
                        cudaStream_t stream) {
-  sample_kernel<SRC><<<dim3(64, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys);
+  sample_kernel<SRC><<<dim3(512, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
-  select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, stream);
+  select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, w.done, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_WINDOW, f, n, cap, w.st);
   window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_INSIDE, f, n, cap, w.st);
-  select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, stream);
+  select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, w.done, stream);
   glue_kernel<<<1, kMaxCols, 0, stream>>>(final_op, f, n, cap, w.st);
 }
 
@@ -499,6 +541,10 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   FitWork& w = g_fit_work[device];
   w.sm_count = sms;
   if (!w.st) DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
+  if (!w.done) {
+    DEWI_CUDA(cudaMalloc(&w.done, kMaxCols * sizeof(unsigned int)));
+    DEWI_CUDA(cudaMemsetAsync(w.done, 0, kMaxCols * sizeof(unsigned int), stream));
+  }
   DEWI_TRY(ensure_buf(&w.ghist, &w.ghist_bytes, static_cast<size_t>(kMaxCols) * 2 * kBins * 4));
   if (windowed) {
     DEWI_TRY(ensure_buf(&w.skeys, &w.skeys_bytes, static_cast<size_t>(f) * kSample * 4));
