@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--sweep", default="1,8,256,1024,4096", help="extra batch sizes reported in `batch_sweep` ('' = none)")
     ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
+                    help="multi-GPU candidate exchange: fused peer stores (symmetric memory) or one NCCL all-gather per batch")
     return ap.parse_args()
 
 
@@ -261,7 +263,7 @@ def main():
 
     t_build = time.perf_counter()
     if world > 1:
-        index = dewi_b200.ShardedDewiIndex(args.dim, dtype=args.dtype, device=local_rank)
+        index = dewi_b200.ShardedDewiIndex(args.dim, dtype=args.dtype, device=local_rank, exchange=args.exchange)
         local = index.local
     else:
         index = local = dewi_b200.CudaIndex(args.dim, dtype=args.dtype, device=local_rank)
@@ -389,6 +391,9 @@ def main():
             cpu.pop("ms_per_step_sample", None)
         cfg = workload_config(args, world, rows)
         cfg.update({"build_s": round(t_build, 2), "parallelism": f"row-shard x{world}", "note": shrunk})
+        if world > 1:
+            cfg["exchange"] = ("fused peer stores over NVLink (symmetric memory), no collective on the search path"
+                               if index.exchange == "push" else "one NCCL all_gather_into_tensor per batch")
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -66,6 +66,8 @@ struct dewi_index {
   DevBuf stage, qraw, qn, q0, q1, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
       out_score;
   int last_launches = 0;
+  DevBuf push_ticket;               // block counter of the peer-push finalize kernel
+  bool push_ticket_zeroed = false;
   // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
   int profile = 0;
   int last_sweep_kind = 0;  // 1 = tcgen05 sweep, 2 = CUDA-core sweep
@@ -321,8 +323,45 @@ int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host) {
   return 0;
 }
 
+static int search_local_impl(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
+                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push);
+
 int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_) {
+  if (!out_sim || !out_id || !out_dewi || !out_ent) return fail("null output");
+  return search_local_impl(h, queries, B, kcand, flags, out_sim, out_id, out_dewi, out_ent, stream_, nullptr);
+}
+
+int dewi_index_search_local_push(dewi_index_t* h, const float* queries, int B, int kcand, int flags, int world, int my_rank,
+                                 const uint64_t* peer_bases, const uint64_t* peer_flags, int64_t block_stride_bytes,
+                                 uint32_t seq, void* stream_) {
+  if (!h) return fail("null handle");
+  if (!peer_bases || !peer_flags) return fail("null peer table");
+  if (world < 1 || world > kMaxPeers || my_rank < 0 || my_rank >= world) return fail("invalid world / rank");
+  if (block_stride_bytes < static_cast<int64_t>(B) * kcand * 20 || block_stride_bytes % 8 != 0)
+    return fail("block stride too small for [id i64 | sim | dewi | ent] x B x kcand, or not a multiple of 8");
+  DEWI_TRY(set_device(h));
+  DEWI_TRY(h->push_ticket.ensure(4));
+  if (!h->push_ticket_zeroed) {
+    DEWI_CUDA(cudaMemsetAsync(h->push_ticket.p, 0, 4, static_cast<cudaStream_t>(stream_)));
+    h->push_ticket_zeroed = true;
+  }
+  PeerPush push;
+  push.world = world;
+  push.my_rank = my_rank;
+  push.seq = seq;
+  push.block_stride = block_stride_bytes;
+  for (int r = 0; r < world; ++r) {
+    if (!peer_bases[r] || !peer_flags[r]) return fail("null peer pointer");
+    push.base[r] = peer_bases[r];
+    push.flags[r] = peer_flags[r];
+  }
+  push.ticket = h->push_ticket.as<unsigned int>();
+  return search_local_impl(h, queries, B, kcand, flags, nullptr, nullptr, nullptr, nullptr, stream_, &push);
+}
+
+static int search_local_impl(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
+                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push) {
   if (!h) return fail("null handle");
   if (B <= 0 || kcand <= 0) return fail("B and kcand must be positive");
   if (h->n <= 0) return fail("index is empty");
@@ -477,9 +516,25 @@ int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kc
     h->last_launches++;
   }
   DEWI_TRY(launch_finalize_local(h->cand_idx.as<int>(), h->cand_sim.as<float>(), B, kc, kcand, h->id_base, h->dewi_col,
-                                 h->ent_col, out_sim, out_id, out_dewi, out_ent, stream));
+                                 h->ent_col, out_sim, out_id, out_dewi, out_ent, stream, push));
   h->last_launches++;
   return 0;
+}
+
+int dewi_rerank_gathered(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int n_shards,
+                         int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
+                         int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, int device,
+                         void* stream_) {
+  if (!sim || !id || !dewi_v || !ent_v || !out_id || !out_score || !ready_flags) return fail("null argument");
+  if (B <= 0 || n_shards <= 0 || kcand <= 0 || k <= 0) return fail("B, n_shards, kcand and k must be positive");
+  if (shard_stride_bytes % 8 != 0) return fail("shard stride must be a multiple of 8 bytes");
+  const int64_t ncand = static_cast<int64_t>(n_shards) * kcand;
+  if (cand_count > ncand) cand_count = static_cast<int>(ncand);
+  if (k > cand_count) return fail("k exceeds the number of candidates (k > N)");
+  DEWI_CUDA(cudaSetDevice(device));
+  return launch_rerank(sim, id, dewi_v, ent_v, B, n_shards, kcand, shard_stride_bytes, cand_count, k,
+                       static_cast<float>(1.0 - eta), static_cast<float>(eta), static_cast<float>(entropy_pref),
+                       entropy_pref != 0.0 ? 1 : 0, out_id, out_score, static_cast<cudaStream_t>(stream_), ready_flags, seq);
 }
 
 int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int n_shards,

@@ -107,12 +107,27 @@ int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, 
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
 int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
                    float* cand_sim, cudaStream_t stream);
+// Fused exchange of the multi-GPU search (one process per GPU, peers' buffers mapped through symmetric memory):
+// finalize_local writes this rank's candidate block `[id i64 | sim | dewi | ent]` straight into EVERY rank's gather
+// buffer with peer stores over NVLink (slot `my_rank`), and the last block releases `flags[r][my_rank] = seq` on
+// every rank; the re-rank kernel of rank r acquires all `world` flags of its own buffer before it reads.
+constexpr int kMaxPeers = 16;
+struct PeerPush {
+  int world = 0;                       // 0: plain local output
+  int my_rank = 0;
+  unsigned int seq = 0;
+  long long block_stride = 0;          // bytes between two ranks' blocks in a gather buffer
+  unsigned long long base[kMaxPeers];  // rank r's gather buffer (as mapped in THIS process)
+  unsigned long long flags[kMaxPeers]; // rank r's ready flags, uint32[world]
+  unsigned int* ticket = nullptr;      // local block counter (self-resetting)
+};
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
-                          float* out_ent, cudaStream_t stream);
+                          float* out_ent, cudaStream_t stream, const PeerPush* push = nullptr);
 int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
                   int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
-                  int64_t* out_id, float* out_score, cudaStream_t stream);
+                  int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags = nullptr,
+                  unsigned int seq = 0);
 
 // ---- operand preparation (prep.cu) -----------------------------------------------------------
 // rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.

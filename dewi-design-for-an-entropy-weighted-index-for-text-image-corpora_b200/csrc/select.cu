@@ -206,12 +206,25 @@ __global__ void rescore_kernel(const RowT* __restrict__ rows, int dim, const flo
 }
 
 // ---- finalize_local -----------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// PUSH = 1: the block is not written to out_* but to slot `my_rank` of every rank's gather buffer (peer stores over
+// NVLink, fire-and-forget), then the last block to finish publishes the ready flags -- finalize and all-gather in one kernel.
+template <int PUSH>
 __global__ void __launch_bounds__(kSelThreads)
 finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict__ cand_sim, int kc_in, int kcand,
                       long long id_base, const float* __restrict__ dewi, const float* __restrict__ ent,
                       float* __restrict__ out_sim, long long* __restrict__ out_id, float* __restrict__ out_dewi,
-                      float* __restrict__ out_ent) {
+                      float* __restrict__ out_ent, const PeerPush push) {
   extern __shared__ unsigned long long sh[];
+  __shared__ unsigned int ticket;
   const int p = next_pow2(kc_in);
   unsigned long long* key = sh;
   int* val = reinterpret_cast<int*>(sh + p);
@@ -227,20 +240,46 @@ finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict_
     val[t] = vv;
   }
   bitonic_sort_desc(key, val, p);
+  const size_t bk = static_cast<size_t>(gridDim.x) * kcand;   // elements per section of a block
   for (int t = threadIdx.x; t < kcand; t += blockDim.x) {
     const size_t o = static_cast<size_t>(b) * kcand + t;
     const int slot = (t < p) ? val[t] : -1;
+    float v_sim = -INFINITY, v_dewi = 0.f, v_ent = 0.f;
+    long long v_id = -1;
     if (slot >= 0) {
       const int idx = cand_idx[static_cast<size_t>(b) * kc_in + slot];
-      out_sim[o] = cand_sim[static_cast<size_t>(b) * kc_in + slot];
-      out_id[o] = id_base + idx;
-      out_dewi[o] = dewi[idx];
-      out_ent[o] = ent[idx];
+      v_sim = cand_sim[static_cast<size_t>(b) * kc_in + slot];
+      v_id = id_base + idx;
+      v_dewi = dewi[idx];
+      v_ent = ent[idx];
+    }
+    if (!PUSH) {
+      out_sim[o] = v_sim;
+      out_id[o] = v_id;
+      out_dewi[o] = v_dewi;
+      out_ent[o] = v_ent;
     } else {
-      out_sim[o] = -INFINITY;
-      out_id[o] = -1;
-      out_dewi[o] = 0.f;
-      out_ent[o] = 0.f;
+      for (int r = 0; r < push.world; ++r) {  // block layout: [id i64 bk | sim bk | dewi bk | ent bk]
+        char* blk = reinterpret_cast<char*>(push.base[r]) + static_cast<long long>(push.my_rank) * push.block_stride;
+        reinterpret_cast<long long*>(blk)[o] = v_id;
+        reinterpret_cast<float*>(blk + 8 * bk)[o] = v_sim;
+        reinterpret_cast<float*>(blk + 12 * bk)[o] = v_dewi;
+        reinterpret_cast<float*>(blk + 16 * bk)[o] = v_ent;
+      }
+    }
+  }
+  if (PUSH) {
+    // every block's stores are fenced at system scope before its ticket; the block that draws the last ticket
+    // therefore publishes flags that cover all of them (threadfence reduction pattern, system-wide)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(push.ticket, 1u);
+    __syncthreads();
+    if (ticket == gridDim.x - 1) {
+      __threadfence_system();
+      if (threadIdx.x < push.world)
+        st_release_sys(reinterpret_cast<unsigned int*>(push.flags[threadIdx.x]) + push.my_rank, push.seq);
+      if (threadIdx.x == 0) *push.ticket = 0u;
     }
   }
 }
@@ -252,16 +291,28 @@ finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict_
 template <typename T>
 __device__ __forceinline__ T shard_at(const T* base, int c, int b, int kcand, long long shard_stride) {
   const int g = c / kcand, j = c - g * kcand;
+  // (L2 loads: in the fused exchange these blocks are written by peer GPUs while the kernel waits)
   const char* p = reinterpret_cast<const char*>(base) + static_cast<long long>(g) * shard_stride;
-  return reinterpret_cast<const T*>(p)[static_cast<size_t>(b) * kcand + j];
+  return __ldcg(reinterpret_cast<const T*>(p) + static_cast<size_t>(b) * kcand + j);
 }
 
 __global__ void __launch_bounds__(kSelThreads)
 rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, const float* __restrict__ dewi,
               const float* __restrict__ ent, int n_shards, int kcand, long long shard_stride, int cand_count, int k,
               float w_sim, float w_dewi, float pref, int use_pref, long long* __restrict__ out_id,
-              float* __restrict__ out_score) {
+              float* __restrict__ out_score, const unsigned int* ready_flags, unsigned int seq) {
   extern __shared__ unsigned long long sh[];
+  if (ready_flags) {
+    // fused exchange: every rank's block must have landed in this buffer (flags are released by the peers'
+    // finalize kernels).  Bounded spin: a dead peer must not hang the GPU forever.
+    if (threadIdx.x < n_shards) {
+      const long long t0 = clock64();
+      while (static_cast<int>(ld_acquire_sys(ready_flags + threadIdx.x) - seq) < 0) {
+        if (clock64() - t0 > (60ll << 30)) __trap();  // ~30 s
+      }
+    }
+    __syncthreads();
+  }
   const int ncand = n_shards * kcand;
   const int p = next_pow2(ncand);
   unsigned long long* key = sh;
@@ -345,20 +396,27 @@ int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn
 
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
-                          float* out_ent, cudaStream_t stream) {
+                          float* out_ent, cudaStream_t stream, const PeerPush* push) {
   const int p = next_pow2(kc_in);
   if (p > 4096) return fail("too many candidates per query");
   const size_t smem = static_cast<size_t>(p) * 12;
-  finalize_local_kernel<<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, out_sim,
-                                                          reinterpret_cast<long long*>(out_id), out_dewi, out_ent);
+  if (push && push->world > 0) {
+    if (push->world > kMaxPeers || !push->ticket) return fail("invalid peer-push descriptor");
+    finalize_local_kernel<1><<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, nullptr,
+                                                               nullptr, nullptr, nullptr, *push);
+  } else {
+    finalize_local_kernel<0><<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, out_sim,
+                                                               reinterpret_cast<long long*>(out_id), out_dewi, out_ent, PeerPush());
+  }
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
                   int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
-                  int64_t* out_id, float* out_score, cudaStream_t stream) {
+                  int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags, unsigned int seq) {
   const int p = next_pow2(n_shards * kcand);
+  if (ready_flags && n_shards > kSelThreads) return fail("too many shards for the fused exchange");
   if (p > 8192) return fail("too many gathered candidates per query");
   const size_t smem = static_cast<size_t>(p) * 16;
   auto kern = rerank_kernel;
@@ -366,7 +424,7 @@ int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const 
     DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<B, kSelThreads, smem, stream>>>(sim, reinterpret_cast<const long long*>(id), dewi, ent, n_shards, kcand,
                                          shard_stride_bytes, cand_count, k, w_sim, w_dewi, pref, use_pref,
-                                         reinterpret_cast<long long*>(out_id), out_score);
+                                         reinterpret_cast<long long*>(out_id), out_score, ready_flags, seq);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

@@ -75,12 +75,65 @@ class PackedCandidates:
         return ids, sim, dewi, ent
 
 
+class SymmetricCandidates:
+    """Gather buffers of the FUSED exchange: two (seq parity) buffers of `world` rank blocks plus `world` ready
+    flags each, allocated as torch symmetric memory so that every rank's copy is mapped into every process
+    (`rendezvous` is the only collective; PyTorch is plumbing here).  The finalize kernel of each rank then writes
+    its block into all copies with peer stores over NVLink and the re-rank kernel acquires the flags
+    (`dewi_index_search_local_push` / `dewi_rerank_gathered`): no NCCL call on the search path."""
+
+    def __init__(self, b: int, kcand: int, device, world: int, rank: int, group):
+        torch = _torch()
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.b, self.kcand, self.world, self.rank = b, kcand, world, rank
+        self.bk = b * kcand
+        self.words = (PackedCandidates.WORDS_PER_CAND * self.bk + 1) // 2 * 2   # int32 words per rank block (8-byte multiple)
+        self.flag_words = (world + 3) // 4 * 4
+        self.half_words = world * self.words + self.flag_words                  # one parity: blocks, then flags
+        self.buf = symm_mem.empty(2 * self.half_words, dtype=torch.int32, device=device)
+        self.buf.zero_()
+        group = group if group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)   # every copy zeroed before anybody's first push
+        base = [int(p) for p in self.handle.buffer_ptrs]
+        self._bases, self._flags = [], []
+        for parity in range(2):
+            off = parity * self.half_words * 4
+            self._bases.append((ctypes.c_uint64 * world)(*[p + off for p in base]))
+            self._flags.append((ctypes.c_uint64 * world)(*[p + off + world * self.words * 4 for p in base]))
+
+    @property
+    def stride_bytes(self) -> int:
+        return self.words * 4
+
+    def tables(self, seq: int):
+        return self._bases[seq & 1], self._flags[seq & 1]
+
+    def local_views(self, seq: int):
+        """(id, sim, dewi, ent, flags) views of THIS rank's buffer for the parity of `seq` (rank block 0)."""
+        torch = _torch()
+        half = self.buf[(seq & 1) * self.half_words: ((seq & 1) + 1) * self.half_words]
+        bk, shape = self.bk, (self.b, self.kcand)
+        ids = half[: 2 * bk].view(torch.int64).view(shape)
+        sim = half[2 * bk: 3 * bk].view(torch.float32).view(shape)
+        dewi = half[3 * bk: 4 * bk].view(torch.float32).view(shape)
+        ent = half[4 * bk: 5 * bk].view(torch.float32).view(shape)
+        flags = half[self.world * self.words: self.world * self.words + self.world]
+        return ids, sim, dewi, ent, flags
+
+
 class ShardedDewiIndex:
     """The row-sharded index.  Every rank constructs it, ingests its own shard, calls `build()`
     (collective) and then `search_batch()` (collective) with the same replicated query batch."""
 
     def __init__(self, dim: int, space: str = "cosine", dtype: str = "bf16", group=None, device: Optional[int] = None,
-                 local_index=None, local_search: Optional[Callable] = None, rerank: Optional[Callable] = None, **kwargs):
+                 local_index=None, local_search: Optional[Callable] = None, rerank: Optional[Callable] = None,
+                 exchange: str = "auto", **kwargs):
+        """exchange: "push" = fused peer-store exchange over NVLink (symmetric memory, no collective on the search
+        path), "nccl" = one `all_gather_into_tensor` per batch, "auto" = push when it can be set up, else nccl."""
         torch = _torch()
         import torch.distributed as dist
 
@@ -103,6 +156,13 @@ class ShardedDewiIndex:
         self.id_base = 0
         self._packed: Optional[PackedCandidates] = None
         self._built = False
+        if exchange not in ("auto", "push", "nccl"):
+            raise ValueError("exchange must be 'auto', 'push' or 'nccl'")
+        self._exchange_want = exchange
+        self.exchange = "nccl"      # what the last search used
+        self._symm: Optional[SymmetricCandidates] = None
+        self._symm_failed = False
+        self._seq = 0
 
     # ---- ingest / build --------------------------------------------------------------------------
     def add_local(self, embeddings, payload_columns=None, normalized: bool = False) -> None:
@@ -123,6 +183,7 @@ class ShardedDewiIndex:
         else:
             counts = [n_local]
         self.n_total = int(sum(counts))
+        self._min_shard = int(min(counts))
         self.id_base = int(sum(counts[: self.rank]))
         if self.n_total == 0:
             raise ValueError("No embeddings to build index from")
@@ -167,6 +228,9 @@ class ShardedDewiIndex:
             raise ValueError(f"k={k} exceeds the number of indexed rows ({self.n_total})")  # backends.py:468
         b = queries.shape[0]
         kcand = min(2 * k, self.n_total)  # backends.py:440
+        if self._push_ready(b, kcand, queries):
+            return self._search_batch_push(queries, b, kcand, k, eta, entropy_pref)
+        self.exchange = "nccl"
         pk = self._packed
         if pk is None or pk.b != b or pk.kcand != kcand or pk.world != self.world:
             pk = self._packed = PackedCandidates(b, kcand, queries.device, self.world)
@@ -181,6 +245,60 @@ class ShardedDewiIndex:
         out_ids = torch.empty((b, k), dtype=torch.int64, device=queries.device)
         out_scores = torch.empty((b, k), dtype=torch.float32, device=queries.device)
         (self._rerank or self._default_rerank)(pk, kcand, k, eta, entropy_pref, out_ids, out_scores)
+        return out_ids, out_scores
+
+    # ---- fused exchange (peer stores over NVLink instead of an all-gather) ---------------------------
+    def _push_ready(self, b: int, kcand: int, queries) -> bool:
+        """Collective decision (identical on every rank: it depends only on replicated state and on whether the
+        symmetric allocation succeeded everywhere)."""
+        torch = _torch()
+        if (self._exchange_want == "nccl" or self._symm_failed or not self.dist or self.world <= 1
+                or self._local_search is not None or self._rerank is not None or not queries.is_cuda
+                or self.world > 16 or getattr(self, "_min_shard", 0) <= 0):
+            return False
+        sy = self._symm
+        if sy is not None and sy.b == b and sy.kcand == kcand:
+            return True
+        ok = 1
+        try:
+            sy = SymmetricCandidates(b, kcand, queries.device, self.world, self.rank, self.group)
+        except Exception as exc:  # symmetric memory unavailable on this box / build
+            ok, sy, err = 0, None, exc
+        flag = torch.tensor([ok], dtype=torch.int32, device=queries.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            self._symm_failed = True
+            self._symm = None
+            if self._exchange_want == "push":
+                raise RuntimeError(f"fused exchange requested but symmetric memory could not be set up: {err if not ok else 'on a peer'}")
+            return False
+        self._symm = sy
+        self._seq = 0
+        return True
+
+    def _search_batch_push(self, queries, b: int, kcand: int, k: int, eta: float, entropy_pref: float):
+        torch = _torch()
+        sy = self._symm
+        self._seq += 1
+        seq = self._seq
+        bases, flag_tabs = sy.tables(seq)
+        lib = _native.load_library()
+        q = queries.detach().to(dtype=torch.float32).contiguous()
+        out_ids = torch.empty((b, k), dtype=torch.int64, device=queries.device)
+        out_scores = torch.empty((b, k), dtype=torch.float32, device=queries.device)
+        ids, sim, dewi, ent, flags = sy.local_views(seq)
+        with torch.cuda.device(self.device):
+            rc = lib.dewi_index_search_local_push(self.local._h, ctypes.c_void_p(q.data_ptr()), b, kcand, self.local._flags,
+                                                  self.world, self.rank, bases, flag_tabs, sy.stride_bytes, seq,
+                                                  _native.stream_ptr())
+            _native.check(rc)
+            rc = lib.dewi_rerank_gathered(ctypes.c_void_p(sim.data_ptr()), ctypes.c_void_p(ids.data_ptr()),
+                                          ctypes.c_void_p(dewi.data_ptr()), ctypes.c_void_p(ent.data_ptr()), b, self.world, kcand,
+                                          sy.stride_bytes, int(kcand), int(k), float(eta), float(entropy_pref),
+                                          ctypes.c_void_p(out_ids.data_ptr()), ctypes.c_void_p(out_scores.data_ptr()),
+                                          ctypes.c_void_p(flags.data_ptr()), seq, self.device, _native.stream_ptr())
+        _native.check(rc)
+        self.exchange = "push"
         return out_ids, out_scores
 
     def search(self, query: np.ndarray, k: int = 10, eta: float = 0.5, entropy_pref: float = 0.0):

@@ -101,6 +101,23 @@ DEWI_API int dewi_index_search_local(dewi_index_t* h, const float* queries, int 
 DEWI_API int dewi_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards,
                 int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
                 int64_t* out_id, float* out_score, int device, void* stream);
+/* Fused exchange for the row-sharded index (one process per GPU; every rank's gather buffer is mapped into
+ * every process, e.g. through torch symmetric memory).  dewi_index_search_local_push is stage 1 + 2 with the
+ * all-gather folded in: the finalize kernel writes this rank's block
+ *     [ id int64 [B, kcand] | sim f32 [B, kcand] | dewi f32 [B, kcand] | ent f32 [B, kcand] ]
+ * into slot `my_rank` (at my_rank * block_stride_bytes) of EVERY rank's gather buffer with peer stores over
+ * NVLink, and its last block releases `flags_r[my_rank] = seq` in every rank's flag array (uint32[world]).
+ * `peer_bases` / `peer_flags` are HOST arrays of `world` device addresses as mapped in this process.
+ * dewi_rerank_gathered is dewi_rerank preceded by an acquire on `ready_flags[0..n_shards) >= seq` (this rank's
+ * own flag array): no collective call and no extra launch sits between the sweep and the re-rank.  Callers
+ * alternate between two buffers (seq parity) so that a rank one search ahead never overwrites a block a peer
+ * is still reading; `seq` must increase by one per search on all ranks.                                   */
+DEWI_API int dewi_index_search_local_push(dewi_index_t* h, const float* queries, int B, int kcand, int flags, int world,
+                            int my_rank, const uint64_t* peer_bases, const uint64_t* peer_flags, int64_t block_stride_bytes,
+                            uint32_t seq, void* stream);
+DEWI_API int dewi_rerank_gathered(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B,
+                int n_shards, int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
+                int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, int device, void* stream);
 /* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,
