@@ -42,3 +42,11 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir() -> Path:
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(scope="session")
+def lib_path() -> Path:
+    """libdewi_b200.so, built in-tree if stale (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as entry
+
+    return entry.build_library()

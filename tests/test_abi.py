@@ -11,13 +11,6 @@ ROOT = Path(__file__).resolve().parent.parent
 HEADER = ROOT / "include" / "dewi_b200.h"
 
 
-@pytest.fixture(scope="module")
-def lib_path():
-    import __graft_entry__ as entry
-
-    return entry.build_library()
-
-
 def declared_symbols():
     text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
     return re.findall(r"DEWI_API\s+[\w\s\*]+?\b(dewi_\w+)\s*\(", text)
