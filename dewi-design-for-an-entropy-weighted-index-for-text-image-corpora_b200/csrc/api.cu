@@ -67,6 +67,7 @@ struct dewi_index {
       out_score;
   int last_launches = 0;
   DevBuf push_ticket;               // block counter of the peer-push finalize kernel
+  DevBuf sync_cnt;                  // rendezvous counters of the CTA-pair sweep
   bool push_ticket_zeroed = false;
   // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
   int profile = 0;
@@ -227,7 +228,7 @@ int dewi_index_destroy(dewi_index_t* h) {
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
   }
   for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
-                    &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score})
+                    &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score, &h->push_ticket, &h->sync_cnt})
     b->release();
   delete h;
   return 0;
@@ -435,9 +436,12 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       const size_t items = static_cast<size_t>(chunks) * n_qb;
       DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
       DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
-      if (use_pair)
+      if (use_pair) {
+        const int64_t sync_words = tc2_sync_words(p2, rows, n_qb);
+        if (sync_words > 0) DEWI_TRY(h->sync_cnt.ensure(static_cast<size_t>(sync_words) * 4));
         DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                            h->part_i.as<int>(), sd, stream));
+                            h->part_i.as<int>(), sd, stream, sync_words > 0 ? h->sync_cnt.as<unsigned int>() : nullptr));
+      }
       else
         DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
                            h->part_i.as<int>(), sd, stream));

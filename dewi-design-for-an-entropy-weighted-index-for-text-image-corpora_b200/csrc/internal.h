@@ -87,9 +87,10 @@ struct Tc2Plan {
 int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks = 0,
                   int64_t tiles_per_item = 0, int a_resident = 0);
 int tc2_box_rows();
+int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb);
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream);
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt = nullptr);
 
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
                     int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,

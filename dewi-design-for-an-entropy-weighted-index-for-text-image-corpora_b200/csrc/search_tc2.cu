@@ -63,6 +63,15 @@ struct Tc2Args {
   int sym;
   int blk0;                        // a_offset / 256
   int rotate;                      // align the clusters' tile walks (item_span)
+  // Top-k sweep with several query-block pairs: the clusters that stream the SAME corpus chunk for different
+  // query pairs only share its tiles through L2 while they stay within a few tiles of each other -- once they
+  // drift, every cluster pulls its own copy from DRAM, the fill rate evicts tiles within ~20 us and the sweep
+  // stays in that state (ncu: the corpus read 8.9x from DRAM at B = 4096).  The producers of a chunk's clusters
+  // therefore meet every kSyncEvery tiles at a counter (bounded spin: a late cluster is never waited for longer
+  // than kSyncSpin cycles, and it catches up because it never waits itself).
+  unsigned int* sync_cnt;          // [n_chunks * 2][sync_blocks] arrival counters, zeroed before the launch (or null)
+  int sync_blocks;
+  int sync_every;
   unsigned long long* row_best;    // [m_rows] packed (orderable(sim) << 32 | ~j), atomicMax
   int* row_count;                  // [m_rows] sims >= tau
   long long* pair_i;
@@ -130,6 +139,9 @@ __device__ __forceinline__ void join_scan_tile(JoinRow& r, const Tc2Args& a, int
     }
   }
 }
+
+constexpr int kSyncEvery = 16;          // tiles between two rendezvous (2 .. 32 measured within 3 % of each other)
+constexpr long long kSyncSpin = 60000;   // cycles (~30-45 us)
 
 // The tiles of one work item: `len` offsets starting at o0 from tile `tbase` (wrapping at n_tiles), walked in
 // the rotated order o0 + (s + rot) % len.  Symmetric join: the clusters running concurrently hold consecutive
@@ -409,7 +421,28 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
         __syncwarp();
         a_ph ^= 1;
       }
+      // rendezvous group of this item: the items of the same chunk that run in the same round
+      int sync_expect = 0;
+      unsigned int* sync_row = nullptr;
+      if (a.sync_cnt && rank == 0) {
+        const int chunk = item / a.n_qpairs, round = item / n_clusters;
+        const int first = chunk * a.n_qpairs, last = first + a.n_qpairs;                 // the chunk's items
+        const int lo = max(first, round * n_clusters), hi = min(min(last, (round + 1) * n_clusters), a.n_items);
+        sync_expect = hi - lo;
+        sync_row = a.sync_cnt + (static_cast<size_t>(chunk) * 2 + (round - first / n_clusters)) * a.sync_blocks;
+      }
       for (int step = 0; step < sp.len; ++step) {
+        if (sync_expect > 1 && (step % a.sync_every) == 0 && step / a.sync_every < a.sync_blocks) {
+          if (ptx::elect_one()) {
+            unsigned int* c = sync_row + step / a.sync_every;
+            atomicAdd(c, 1u);
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile unsigned int*>(c) < static_cast<unsigned int>(sync_expect) &&
+                   clock64() - t0 < kSyncSpin) {
+            }
+          }
+          __syncwarp();
+        }
         const int row0 = tile_at(a, sp.tbase, span_offset(sp, step)) * kNTile + static_cast<int>(rank) * kHalfRows;
         for (int kb = 0; kb < a.n_kb; ++kb) {
           ptx::mbar_wait(&bar_empty[st], ph ^ 1);
@@ -625,9 +658,27 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
 
 int tc2_box_rows() { return kHalfRows; }
 
+// Words of the rendezvous counters tc2_launch needs for this plan (0: the sweep does not rendezvous -- a single
+// query pair, or items too short to drift apart).
+static int sync_every() {
+  if (const char* env = getenv("DEWI_TC2_SYNC_EVERY")) return std::max(1, atoi(env));  // experiments
+  return kSyncEvery;
+}
+
+int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb) {
+  if (n_qb < 4) return 0;
+  if (const char* env = getenv("DEWI_TC2_SYNC")) {
+    if (atoi(env) == 0) return 0;  // experiments
+  }
+  const int64_t n_tiles = ceil_div(n_rows, kNTile);
+  const int64_t per_item = ceil_div(n_tiles, plan.n_chunks);
+  if (per_item < 4 * sync_every()) return 0;
+  return 2 * static_cast<int64_t>(plan.n_chunks) * ceil_div(per_item + 1, sync_every());
+}
+
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream) {
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt) {
   Tc2Args a;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
@@ -652,6 +703,17 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.sym = 0;
   a.blk0 = 0;
   a.rotate = 0;
+  a.sync_cnt = nullptr;
+  a.sync_blocks = 0;
+  a.sync_every = sync_every();
+  if (sync_cnt && a.n_qpairs > 1 && a.n_qpairs <= plan.grid / 2) {
+    const int64_t words = tc2_sync_words(plan, n_rows, n_qb);
+    if (words > 0) {
+      DEWI_CUDA(cudaMemsetAsync(sync_cnt, 0, static_cast<size_t>(words) * 4, stream));
+      a.sync_cnt = sync_cnt;
+      a.sync_blocks = static_cast<int>(words / (2 * plan.n_chunks));
+    }
+  }
   a.row_best = nullptr;
   a.row_count = nullptr;
   a.pair_i = a.pair_j = nullptr;
@@ -699,6 +761,8 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.blk0 = sym ? static_cast<int>(a_offset / kNTile) : 0;
   a.rotate = 1;
   if (const char* env = getenv("DEWI_JOIN_ROTATE")) a.rotate = atoi(env) != 0;  // experiments
+  a.sync_cnt = nullptr;
+  a.sync_blocks = 0;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
   a.n_kb = dim / kKBlock;
