@@ -258,6 +258,31 @@ def test_cta_pair_sweep_matches_single_cta_sweep_and_oracle(dtype, b):
         assert recall_at_k(ids1, ids2) >= 0.999
 
 
+@pytest.mark.parametrize("dtype,b", [("fp32", 512), ("bf16", 640)])
+def test_pair_sweep_with_rendezvous_matches_oracle(dtype, b):
+    """Several query-block pairs over a corpus long enough (>= 64 tiles per work item) for the clusters that
+    stream one chunk to rendezvous at their arrival counters (search_tc2.cu): results must not depend on
+    it -- the same answer as the oracle and as the 1-CTA sweep, call after call."""
+    n, d, k = 750_000, 64, 10
+    emb, pay = make_corpus(n, d, seed=91)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    queries = np.random.RandomState(92).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    for _ in range(3):
+        ids_again, sc_again = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+        assert np.array_equal(ids, ids_again) and np.array_equal(sc, sc_again)
+    ids1, sc1 = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_NO_PAIR)
+    sel = np.arange(0, b, 7)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries[sel], k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for i, q in enumerate(sel):
+            check_topk(rid[i], rsc[i], ids[q], sc[q], what=f"rendezvous q{q}")
+        assert (ids1 == ids).mean() > 0.999
+    else:
+        assert recall_at_k(rid, ids[sel]) >= 0.999 and recall_at_k(ids1, ids) >= 0.999
+
+
 @pytest.mark.parametrize("b", [5, 200])
 def test_seeded_sweep_equals_unseeded_and_oracle(b):
     """Large corpora run a sample pre-pass that seeds the admission thresholds (DEWI_FLAG_NO_SEED turns
