@@ -88,6 +88,7 @@ class SymmetricCandidates:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.b, self.kcand, self.world, self.rank = b, kcand, world, rank
+        self.seq = 0                # searches issued through this buffer (flags hold the last one per rank)
         self.bk = b * kcand
         self.words = (PackedCandidates.WORDS_PER_CAND * self.bk + 1) // 2 * 2   # int32 words per rank block (8-byte multiple)
         self.flag_words = (world + 3) // 4 * 4
@@ -161,8 +162,8 @@ class ShardedDewiIndex:
         self._exchange_want = exchange
         self.exchange = "nccl"      # what the last search used
         self._symm: Optional[SymmetricCandidates] = None
+        self._symm_cache = {}       # (B, kcand) -> SymmetricCandidates; each buffer carries its own sequence number
         self._symm_failed = False
-        self._seq = 0
 
     # ---- ingest / build --------------------------------------------------------------------------
     def add_local(self, embeddings, payload_columns=None, normalized: bool = False) -> None:
@@ -256,8 +257,9 @@ class ShardedDewiIndex:
                 or self._local_search is not None or self._rerank is not None or not queries.is_cuda
                 or self.world > 16 or getattr(self, "_min_shard", 0) <= 0):
             return False
-        sy = self._symm
-        if sy is not None and sy.b == b and sy.kcand == kcand:
+        sy = self._symm_cache.get((b, kcand))
+        if sy is not None:   # the cache evolves identically on every rank (replicated query shapes)
+            self._symm = sy
             return True
         ok = 1
         try:
@@ -272,15 +274,17 @@ class ShardedDewiIndex:
             if self._exchange_want == "push":
                 raise RuntimeError(f"fused exchange requested but symmetric memory could not be set up: {err if not ok else 'on a peer'}")
             return False
+        if len(self._symm_cache) >= 16:   # drop the oldest shape (same order on every rank)
+            self._symm_cache.pop(next(iter(self._symm_cache)))
+        self._symm_cache[(b, kcand)] = sy
         self._symm = sy
-        self._seq = 0
         return True
 
     def _search_batch_push(self, queries, b: int, kcand: int, k: int, eta: float, entropy_pref: float):
         torch = _torch()
         sy = self._symm
-        self._seq += 1
-        seq = self._seq
+        sy.seq += 1
+        seq = sy.seq
         bases, flag_tabs = sy.tables(seq)
         lib = _native.load_library()
         q = queries.detach().to(dtype=torch.float32).contiguous()

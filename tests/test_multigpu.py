@@ -50,6 +50,10 @@ def _worker(rank, world, port, n, d, b, k, dtype, exchange, ret):
             assert torch.equal(ids2, ids) and torch.equal(sc2, sc)
         ids3, sc3 = ix.search_batch(q_dev[: b // 2], k=k, eta=0.3, entropy_pref=0.5)   # another buffer shape
         assert torch.equal(ids3, ids[: b // 2]) and torch.equal(sc3, sc[: b // 2])
+        ids4, sc4 = ix.search_batch(q_dev, k=k, eta=0.3, entropy_pref=0.5)              # back to the first (cached) shape
+        assert torch.equal(ids4, ids) and torch.equal(sc4, sc)
+        one = ix.search(queries[3], k=k, eta=0.3, entropy_pref=0.5)                      # single-query wrapper (B = 1)
+        assert [r for r, _ in one] == ids[3].cpu().tolist()
         torch.cuda.synchronize()
         assert ix.exchange == exchange
         if rank == 0:
