@@ -12,7 +12,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent
 PKG = CSRC.parent
 SOURCES = ["api.cu", "prep.cu", "search_tc.cu", "search_tc2.cu", "search_simt.cu", "select.cu", "scorer.cu", "join.cu", "extras.cu"]
-HEADERS = ["internal.h", "ptx.cuh", "sweep_epilogue.cuh", "../../include/dewi_b200.h"]
+HEADERS = ["internal.h", "ptx.cuh", "sweep_epilogue.cuh", "join_epilogue.cuh", "../../include/dewi_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
