@@ -62,7 +62,8 @@ struct TcPlan {
   int q_rows;    // query rows per MMA (M): 128, or 64 for batches of at most 64 queries
   int n_tile;    // corpus rows per MMA (N): 128 or 256
   int n_stages;  // corpus ring depth
-  int q_stages;  // query ring depth
+  int q_stages;  // query ring depth (or the number of resident query k-blocks)
+  int q_resident;  // the single <= 64-query block stays in shared memory for the whole launch
   int n_chunks;  // corpus chunks (work items per query block)
   int grid;
   size_t smem_bytes;

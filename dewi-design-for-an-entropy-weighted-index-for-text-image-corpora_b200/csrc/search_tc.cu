@@ -54,7 +54,11 @@ struct TcArgs {
   float* max_out;     // pre-pass mode: [item][128] maximum score per query, no candidate lists
 };
 
-template <int MODE, int N_TILE, int Q_ROWS>
+// QRES = 1 ("queries resident"; single query block, M = 64): all dim/64 query k-blocks are loaded ONCE and stay in
+// shared memory (96 KB at dim 768) instead of being re-read from L2 with every corpus tile -- the corpus ring
+// gives up one of its four stages for it (measured: three stages stream as fast as four, two do not).  L2 -> SM
+// traffic per sweep drops from 1.5x to 1.0x the shard.
+template <int MODE, int N_TILE, int Q_ROWS, int QRES>
 __global__ void __launch_bounds__(kThreads, 1)
 search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_constant__ CUtensorMap map_e1,
                  const __grid_constant__ CUtensorMap map_q0, const __grid_constant__ CUtensorMap map_q1,
@@ -78,9 +82,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   uint8_t* ring_e = smem;
   uint8_t* ring_q = ring_e + static_cast<size_t>(a.e_stages) * kEStageBytes;
   const int kl = a.kc + kPending;
+  // candidate lists: [slot][column]; an M = 64 sweep has accumulator rows only in lanes 0-15 of each TMEM lane
+  // quarter, so its lists keep 64 columns per slot (column = quarter * 16 + lane)
+  constexpr int kListCols = (Q_ROWS == 64) ? 64 : kQueryBlock;
   float* list_s = reinterpret_cast<float*>(ring_q + static_cast<size_t>(a.q_stages) * kQStageBytes);
-  int* list_i = reinterpret_cast<int*>(list_s + kl * kQueryBlock);
-  uint64_t* bar_e_full = reinterpret_cast<uint64_t*>(list_i + kl * kQueryBlock);
+  int* list_i = reinterpret_cast<int*>(list_s + kl * kListCols);
+  uint64_t* bar_e_full = reinterpret_cast<uint64_t*>(list_i + kl * kListCols);
   uint64_t* bar_e_empty = bar_e_full + kMaxStages;
   uint64_t* bar_q_full = bar_e_empty + kMaxStages;
   uint64_t* bar_q_empty = bar_q_full + kQStagesMax;
@@ -102,7 +109,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
       ptx::mbar_init(&bar_e_full[s], 1);
       ptx::mbar_init(&bar_e_empty[s], 1);
     }
-    for (int s = 0; s < a.q_stages; ++s) {
+    for (int s = 0; s < (QRES ? 1 : a.q_stages); ++s) {  // (resident queries: one barrier, q_stages = n_kb buffers)
       ptx::mbar_init(&bar_q_full[s], 1);
       ptx::mbar_init(&bar_q_empty[s], 1);
     }
@@ -152,7 +159,19 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
     {
       int sq = 0;
       uint32_t pq = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      if (QRES) {
+        // the one query block of this launch: every k-block once, one barrier for all of them (q_stages == n_kb)
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&bar_q_full[0], static_cast<uint32_t>(a.n_kb) * kQStageBytes);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            uint8_t* sqp = ring_q + static_cast<size_t>(kb) * kQStageBytes;
+            ptx::tma_load_2d(sqp, &map_q0, &bar_q_full[0], kb * kKBlock, 0, ptx::kEvictFirst);
+            if (T::PQ > 1) ptx::tma_load_2d(sqp + kQPlaneBytes, &map_q1, &bar_q_full[0], kb * kKBlock, 0, ptx::kEvictFirst);
+          }
+        }
+        __syncwarp();
+      }
+      for (int item = blockIdx.x; !QRES && item < a.n_items; item += gridDim.x) {
         const int qb = item % a.n_qb;
         int t0, t1;
         tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
@@ -181,6 +200,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t ring_e_addr = ptx::smem_u32(ring_e), ring_q_addr = ptx::smem_u32(ring_q);
+      if (QRES) ptx::mbar_wait(&bar_q_full[0], 0);  // the resident query block has landed (once per launch)
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         int t0, t1;
         tile_range(item / a.n_qb, a.n_chunks, a.n_tiles, t0, t1);
@@ -189,7 +209,8 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
           ptx::tc_fence_after();
           const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * N_TILE);
           for (int kb = 0; kb < a.n_kb; ++kb) {
-            ptx::mbar_wait(&bar_q_full[sq], pq);
+            if (QRES) sq = kb;
+            else ptx::mbar_wait(&bar_q_full[sq], pq);
             ptx::mbar_wait(&bar_e_full[se], pe);  // TMA bytes have landed
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
@@ -207,12 +228,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
                 if (MODE == 2) ptx::mma_bf16_ss(tmem_d, dq0 + adv, de1 + adv, kIdesc, 1u);
               }
               ptx::mma_commit(&bar_e_empty[se]);  // smem slots reusable once these MMAs retire
-              ptx::mma_commit(&bar_q_empty[sq]);
+              if (!QRES) ptx::mma_commit(&bar_q_empty[sq]);
               if (kb == a.n_kb - 1) ptx::mma_commit(&bar_acc_full[acc]);
             }
             __syncwarp();
             if (++se == a.e_stages) { se = 0; pe ^= 1; }
-            if (++sq == a.q_stages) { sq = 0; pq ^= 1; }
+            if (!QRES && ++sq == a.q_stages) { sq = 0; pq ^= 1; }
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -226,8 +247,12 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
     const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const int kc = a.kc;
     LaneList l;
-    l.s = list_s + qlane;
-    l.i = list_i + qlane;
+    const int col = (Q_ROWS == 64) ? quarter * 16 + (lane & 15) : qlane;  // (lanes 16-31 of an M = 64 sweep never append)
+    l.s = list_s + col;
+    l.i = list_i + col;
+    l.ws = list_s + ((Q_ROWS == 64) ? quarter * 16 : quarter * 32);
+    l.wi = list_i + ((Q_ROWS == 64) ? quarter * 16 : quarter * 32);
+    l.stride = kListCols;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
@@ -285,15 +310,16 @@ EncodeTiledFn get_encode_fn() {
 
 size_t e_stage_bytes(int mode, int n_tile) { return static_cast<size_t>((mode == 2) ? 2 : 1) * n_tile * 128; }
 size_t q_stage_bytes(int mode, int q_rows) { return static_cast<size_t>((mode == 0) ? 1 : 2) * q_rows * 128; }
-size_t fixed_bytes(int kc) {
-  return static_cast<size_t>(kc + kPending) * kQueryBlock * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
+size_t fixed_bytes(int kc, int q_rows) {
+  const int list_cols = (q_rows == 64) ? 64 : kQueryBlock;  // M = 64 sweeps keep 64 list columns
+  return static_cast<size_t>(kc + kPending) * list_cols * 8 + (2 * kMaxStages + 2 * kQStagesMax + 4) * 8 + 16 +
          1024 /*alignment slack*/;
 }
 
-template <int MODE, int N_TILE, int Q_ROWS>
+template <int MODE, int N_TILE, int Q_ROWS, int QRES = 0>
 int launch_one(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, const TcArgs& args, cudaStream_t stream) {
-  auto kern = search_tc_kernel<MODE, N_TILE, Q_ROWS>;
+  auto kern = search_tc_kernel<MODE, N_TILE, Q_ROWS, QRES>;
   DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan.smem_bytes)));
   kern<<<plan.grid, kThreads, plan.smem_bytes, stream>>>(e0, e1, q0, q1, args);
   DEWI_CUDA(cudaGetLastError());
@@ -311,10 +337,23 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   const size_t smem_max = 227 * 1024;
   int n_tile = (mode == 2) ? 128 : 256;
-  const size_t fixed = fixed_bytes(kc);
-  const int q_stages = 2;
+  const size_t fixed = fixed_bytes(kc, q_rows);
+  int q_stages = 2;
   int stages = 0;
-  for (;;) {
+  // Single query block of at most 64 queries: keep all its k-blocks resident if the corpus ring still gets 3 stages.
+  bool q_res = n_qb == 1 && q_rows == 64 && mode != 2;
+  if (const char* env = getenv("DEWI_TC_QRES")) q_res = q_res && atoi(env) != 0;  // experiments
+  if (q_res) {
+    const size_t used = fixed + static_cast<size_t>(dim / kKBlock) * q_stage_bytes(mode, q_rows);
+    const int st = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode, n_tile)) : 0;
+    if (st >= 3) {
+      q_stages = dim / kKBlock;
+      stages = st;
+    } else {
+      q_res = false;
+    }
+  }
+  for (; !q_res;) {
     const size_t used = fixed + q_stages * q_stage_bytes(mode, q_rows);
     stages = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode, n_tile)) : 0;
     if (stages >= 3 || n_tile == 128) break;
@@ -322,6 +361,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   }
   if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
   stages = std::min(stages, kMaxStages);
+  if (const char* env = getenv("DEWI_TC_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));  // experiments
   const int64_t n_tiles = ceil_div(n_rows, n_tile);
   // Work items = chunks x query blocks, dealt round-robin to `grid` persistent CTAs.  Choose the
   // number of chunks so the item count is a multiple of the grid (equal work per CTA).
@@ -339,6 +379,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   plan->n_tile = n_tile;
   plan->n_stages = stages;
   plan->q_stages = q_stages;
+  plan->q_resident = q_res ? 1 : 0;
   plan->n_chunks = static_cast<int>(chunks);
   plan->grid = static_cast<int>(std::min<int64_t>(grid, chunks * n_qb));
   plan->smem_bytes = fixed + static_cast<size_t>(stages) * e_stage_bytes(mode, n_tile) + q_stages * q_stage_bytes(mode, q_rows);
@@ -380,6 +421,11 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
   a.n_queries = seed.n_queries;
   a.max_out = seed.max_out;
   if (plan.q_rows == 64) {
+    if (plan.q_resident) {
+      if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256, 64, 1>(plan, e0, e1, q0, q1, a, stream);
+      if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256, 64, 1>(plan, e0, e1, q0, q1, a, stream);
+      return fail("unsupported tcgen05 sweep configuration (resident queries)");
+    }
     if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256, 64>(plan, e0, e1, q0, q1, a, stream);
     if (plan.mode == 1 && plan.n_tile == 256) return launch_one<1, 256, 64>(plan, e0, e1, q0, q1, a, stream);
     if (plan.mode == 2 && plan.n_tile == 128) return launch_one<2, 128, 64>(plan, e0, e1, q0, q1, a, stream);

@@ -282,6 +282,9 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     LaneList l;
     l.s = list_s + qlane;
     l.i = list_i + qlane;
+    l.ws = list_s + quarter * 32;
+    l.wi = list_i + quarter * 32;
+    l.stride = kQueryBlock;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = cluster_id; item < a.n_items; item += n_clusters) {

@@ -29,8 +29,11 @@ __device__ __forceinline__ void tile_range(int chunk, int n_chunks, int n_tiles,
 // and raise their thresholds.  Appending is cheap when candidates are rare (the steady state);
 // pruning is lane-parallel when candidates are frequent (the first tiles of an item).
 struct LaneList {
-  float* s;   // &list_s[qlane]
-  int* i;     // &list_i[qlane]
+  float* s;    // this lane's column: &list_s[column]
+  int* i;      // &list_i[column]
+  float* ws;   // column of the warp's lane 0 (lanes of one warp own consecutive columns)
+  int* wi;
+  int stride;  // columns per slot row: 128, or 64 when only 64 queries are resident (M = 64 sweeps)
   int cnt;
   float thr;
 };
@@ -42,18 +45,18 @@ __device__ __forceinline__ void lane_prune(LaneList& l, int kc) {
     int p = 0;
 #pragma unroll 4
     for (int k = 1; k < l.cnt; ++k) {
-      const float x = l.s[k * kQueryBlock];
+      const float x = l.s[k * l.stride];
       if (x < m) { m = x; p = k; }
     }
     const int last = l.cnt - 1;
-    l.s[p * kQueryBlock] = l.s[last * kQueryBlock];
-    l.i[p * kQueryBlock] = l.i[last * kQueryBlock];
+    l.s[p * l.stride] = l.s[last * l.stride];
+    l.i[p * l.stride] = l.i[last * l.stride];
     l.cnt = last;
   }
   if (l.cnt == kc) {
     float m = l.s[0];
 #pragma unroll 4
-    for (int k = 1; k < kc; ++k) m = fminf(m, l.s[k * kQueryBlock]);
+    for (int k = 1; k < kc; ++k) m = fminf(m, l.s[k * l.stride]);
     l.thr = m;
   }
 }
@@ -80,21 +83,21 @@ __device__ __forceinline__ float seed_threshold(const float* seed, int stride, i
 // are written back in rank order, and the kc-th becomes the threshold.  ~cnt broadcast loads instead
 // of the (cnt - kc) x cnt dependent scans of lane_prune run by a single active lane.
 // Requires kc + kPending <= 64.  `col_s` / `col_i` point at the target lane's column.
-__device__ __forceinline__ float coop_prune(float* col_s, int* col_i, int cnt, int kc, int lane) {
+__device__ __forceinline__ float coop_prune(float* col_s, int* col_i, int cnt, int kc, int lane, int stride) {
   const int e0 = lane, e1 = lane + 32;
   const bool has0 = e0 < cnt, has1 = e1 < cnt;
-  const float v0 = has0 ? col_s[e0 * kQueryBlock] : 0.f, v1 = has1 ? col_s[e1 * kQueryBlock] : 0.f;
-  const int i0 = has0 ? col_i[e0 * kQueryBlock] : 0, i1 = has1 ? col_i[e1 * kQueryBlock] : 0;
+  const float v0 = has0 ? col_s[e0 * stride] : 0.f, v1 = has1 ? col_s[e1 * stride] : 0.f;
+  const int i0 = has0 ? col_i[e0 * stride] : 0, i1 = has1 ? col_i[e1 * stride] : 0;
   int r0 = 0, r1 = 0;
 #pragma unroll 4
   for (int f = 0; f < cnt; ++f) {
-    const float vf = col_s[f * kQueryBlock];  // same address in every lane: broadcast
+    const float vf = col_s[f * stride];  // same address in every lane: broadcast
     r0 += (vf > v0 || (vf == v0 && f < e0)) ? 1 : 0;
     r1 += (vf > v1 || (vf == v1 && f < e1)) ? 1 : 0;
   }
   __syncwarp();  // all reads done before the in-place rewrite
-  if (has0 && r0 < kc) { col_s[r0 * kQueryBlock] = v0; col_i[r0 * kQueryBlock] = i0; }
-  if (has1 && r1 < kc) { col_s[r1 * kQueryBlock] = v1; col_i[r1 * kQueryBlock] = i1; }
+  if (has0 && r0 < kc) { col_s[r0 * stride] = v0; col_i[r0 * stride] = i0; }
+  if (has1 && r1 < kc) { col_s[r1 * stride] = v1; col_i[r1 * stride] = i1; }
   // the entry ranked kc-1 is the new admission threshold
   const bool mine0 = has0 && r0 == kc - 1, mine1 = has1 && r1 == kc - 1;
   const unsigned int who = __ballot_sync(0xffffffffu, mine0 || mine1);
@@ -129,8 +132,8 @@ __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, in
         for (int jj = 0; jj < kGroup; ++jj) {
           const int j = g * kGroup + jj;
           if (v[j] > l.thr) {
-            l.s[l.cnt * kQueryBlock] = v[j];
-            l.i[l.cnt * kQueryBlock] = r0 + j;
+            l.s[l.cnt * l.stride] = v[j];
+            l.i[l.cnt * l.stride] = r0 + j;
             ++l.cnt;
           }
         }
@@ -145,8 +148,7 @@ __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, in
               const int tgt = __ffs(over) - 1;
               over &= over - 1;
               const int tcnt = __shfl_sync(0xffffffffu, l.cnt, tgt);
-              // lanes of one warp own consecutive columns: the target's column is (mine - lane + tgt)
-              const float t = coop_prune(l.s - lane + tgt, l.i - lane + tgt, tcnt, kc, lane);
+              const float t = coop_prune(l.ws + tgt, l.wi + tgt, tcnt, kc, lane, l.stride);
               if (lane == tgt) { l.cnt = kc; l.thr = t; }
             }
           }
@@ -180,8 +182,8 @@ __device__ __forceinline__ void flush_item(LaneList& l, int kc, float* ps, int* 
   lane_prune(l, kc);
   for (int k = 0; k < kc; ++k) {
     const bool live = k < l.cnt;
-    ps[k * kQueryBlock] = live ? l.s[k * kQueryBlock] : -INFINITY;
-    pi[k * kQueryBlock] = live ? l.i[k * kQueryBlock] : -1;
+    ps[k * kQueryBlock] = live ? l.s[k * l.stride] : -INFINITY;   // (the partials keep 128 columns per slot)
+    pi[k * kQueryBlock] = live ? l.i[k * l.stride] : -1;
   }
 }
 
