@@ -36,7 +36,6 @@ using namespace sweep;
 
 constexpr int kThreads = 224;
 constexpr int kQWarp = 6;  // query-ring producer (kept apart so the corpus ring can run ahead)
-constexpr int kEpiWarp0 = 2;
 struct TcArgs {
   int n_rows;
   int n_tiles;
