@@ -3,12 +3,14 @@
 // K3 fit_stats: exact median and MAD of each signal column, replacing RobustStats.fit
 //   (reference src/dewi/scorer.py:18-26: np.median of a float32 column, then np.median of
 //   |v - med| in float32, zero MAD -> 1e-8).  Exact order statistics by MSB-first radix selection
-//   over order-preserving uint32 keys: three histogram passes (11 + 11 + 10 bits) per statistic,
-//   block-private shared-memory histograms flushed with one atomic per non-empty bin.  All columns
-//   and both middle ranks (even n) are selected in the same passes.
+//   over order-preserving uint32 keys: three histogram passes (11 + 11 + 10 bits) per selection,
+//   block-private shared-memory histograms flushed with one atomic per non-empty bin, the last block
+//   of a pass picks the bins.  Large columns select inside a key window found from a sample, so each
+//   statistic reads the column once (window_kernel).  All columns and both middle ranks (even n) are
+//   selected in the same passes.
 // K4 score: RobustStats.z + DewiScorer._components/score/score_conditional (scorer.py:28-31,49-89)
-//   in float64 with one rounding per operation (no FMA contraction), so results match the reference's
-//   Python-float arithmetic; HBM-bound: 7 fp32 loads and one store per row.
+//   in float64: U as a weighted sum of (v - med) with the z-score scales folded into the weights, clip, sigmoid with a
+//   polynomial exp -- within ~1e-11 of the reference's Python-float arithmetic (gate 1e-6); 7 fp32 loads and one store per row.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
