@@ -4,31 +4,65 @@
     python bench.py --gpus 1 --steps 20 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference --steps 3 --warmup 1      # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps 3 --warmup 1      # the reference's own CPU path (baseline/_ref)
 
-A step = one pass of the hot path (sweep -> candidate select -> [all-gather] -> DEWI re-rank -> top-k)
+A step = one pass of the hot path (sweep -> candidate select -> [exchange] -> DEWI re-rank -> top-k)
 over one batch of B synthetic queries.  The corpus (N rows in total, fixed as the GPU count grows:
 strong scaling) is row-sharded across the ranks.  Rank 0 prints ONE JSON line.
 
-value      device-timed throughput, queries and corpus already resident in HBM
-e2e        same metric through the public API with HOST (pinned) query buffers and HOST results
-roofline   the sweep kernel: algorithmic corpus bytes per launch / its CUDA-event duration vs the
-           measured HBM peak (B <= ridge) or algorithmic flops vs the measured bf16 peak (B > ridge)
-cpu_baseline  the oracle port of ExactIndex.search (numpy/OpenBLAS) on a bounded row sample, rank 0
+value         device-timed throughput, queries and corpus already resident in HBM
+e2e           same metric through the public API with HOST (pinned) query buffers and HOST results
+roofline      the sweep kernel: algorithmic corpus bytes per launch / its CUDA-event duration vs the
+              measured HBM peak (B <= ridge) or algorithmic flops vs the measured bf16 peak (B > ridge)
+cpu_baseline  the unmodified reference (`DewiIndex(use_ann=False).search`, baseline/_ref) on the host cores,
+              BASELINE.md section 3 protocol (bench_ref.py), rank 0 at N = 1
+parity_check  outside the timed region: at N > 1 the fused-push exchange, the NCCL exchange and a
+              single-shard re-rank of the gathered candidates must agree bit for bit; on every rank the
+              oracle (`oracle.search.exact_search`) runs over a slab of that rank's stored rows plus the
+              returned candidates' rows and must return the GPU's global result
+extra         the other BASELINE.json configs, driver-visible: C2 (1M x 768 fp32, B = 1..4096), C4 (fit_stats
+              + score over 100M Signals rows), C5 (redundancy self-join), C1 / C2 / C3 single-query latency
 """
 
 from __future__ import annotations
 
-import argparse
-import json
 import os
-import subprocess
 import sys
-import threading
-import time
-from pathlib import Path
 
-import numpy as np
+
+def _is_reference_arm(argv) -> bool:
+    for i, a in enumerate(argv):
+        if a == "--impl" and i + 1 < len(argv) and argv[i + 1] == "reference":
+            return True
+        if a == "--impl=reference":
+            return True
+    return False
+
+
+def _arg_value(argv, name, default):
+    for i, a in enumerate(argv):
+        if a == name and i + 1 < len(argv):
+            return argv[i + 1]
+        if a.startswith(name + "="):
+            return a.split("=", 1)[1]
+    return default
+
+
+if _is_reference_arm(sys.argv):
+    # the BLAS pool must be sized BEFORE numpy loads OpenBLAS: torch.distributed.run exports OMP_NUM_THREADS=1
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import bench_ref as _bench_ref
+
+    _bench_ref.pin_env_threads(_bench_ref.host_threads(int(_arg_value(sys.argv, "--cpu-threads", "0"))))
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+from pathlib import Path  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
@@ -37,7 +71,7 @@ CHUNK_ROWS = 500_000  # corpus rows are generated in globally numbered chunks ->
 METRIC = "queries/sec (100M x 768 bf16, k=10, DEWI re-rank)"
 
 
-def parse_args():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -51,11 +85,15 @@ def parse_args():
     ap.add_argument("--entropy-pref", type=float, default=0.5)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--sweep", default="1,8,256,1024,4096", help="extra batch sizes reported in `batch_sweep` ('' = none)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=500_000)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="BLAS threads of the CPU legs (0 = every core this process may use)")
+    ap.add_argument("--cpu-max-rows", type=int, default=10_000_000, help="largest corpus of the CPU legs (shrunk to fit host RAM)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--extras", default="latency,c2,c4,c5", help="secondary rows reported under `extra` ('' = none)")
+    ap.add_argument("--sustained-s", type=float, default=2.0, help="length of the back-to-back loop reported as `sustained`")
     ap.add_argument("--exchange", default="auto", choices=["auto", "push", "nccl"],
                     help="multi-GPU candidate exchange: fused peer stores (symmetric memory) or one NCCL all-gather per batch")
-    return ap.parse_args()
+    return ap.parse_args(argv)
 
 
 def load_peaks():
@@ -143,78 +181,153 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---- the reference's CPU path (oracle port of ExactIndex.search) --------------------------------------
-def cpu_reference_qps(args, steps: int, warmup: int, queries_per_step: int):
-    """Times oracle.search.exact_search (numpy sgemv + argpartition + blend, backends.py:414-481) on a
-    bounded row sample and scales queries/s linearly to the full corpus (the path is one linear
-    stream over N rows; 100M x 768 fp32 = 307 GB cannot be held on the host)."""
-    from oracle import search as osearch
-
-    try:
-        from threadpoolctl import threadpool_info
-
-        threads = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
-    except Exception:
-        threads = os.cpu_count() or 1
-    import torch
-
-    n, d = args.cpu_sample_rows, args.dim
-    g = torch.Generator()
-    g.manual_seed(7)
-    emb = torch.randn((n, d), generator=g, dtype=torch.float32)
-    emb = torch.nn.functional.normalize(emb, dim=1).numpy()
-    rng = np.random.RandomState(8)
-    dewi = rng.beta(2, 2, n)
-    ent = rng.gamma(2, 0.4, n)
-    qs = gen_queries(torch, 99, queries_per_step * (steps + warmup), d).numpy()
-    qi = 0
-    for _ in range(warmup):
-        for _ in range(queries_per_step):
-            osearch.exact_search(emb, dewi, ent, qs[qi], args.k, args.eta, args.entropy_pref, True)
-            qi += 1
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        for _ in range(queries_per_step):
-            osearch.exact_search(emb, dewi, ent, qs[qi], args.k, args.eta, args.entropy_pref, True)
-            qi += 1
-    dt = time.perf_counter() - t0
-    qps_sample = steps * queries_per_step / dt
-    scale = n / args.rows
-    return {
-        "value": qps_sample * scale, "unit": "queries/s", "cores": int(threads), "kind": "port",
-        "sample": (f"oracle port of ExactIndex.search (numpy/OpenBLAS sgemv, fp32) on a {n}-row x {d} sample, "
-                   f"{steps * queries_per_step} queries at {1e3 / qps_sample:.2f} ms/query; scaled x{scale:.4g} to {args.rows} "
-                   f"rows (linear extrapolation); host has {os.cpu_count()} logical cores"),
-        "ms_per_step_sample": dt / steps * 1e3,
-    }
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    qps = 8
-    res = cpu_reference_qps(args, args.steps, args.warmup, qps)
-    value = res["value"]
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": res.pop("ms_per_step_sample"), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.gpus, args.rows),
-        "cpu_baseline": res,
-        "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line), flush=True)
-
-
 def workload_config(args, world, rows):
+    """Identical in both arms (the driver compares the two `config` objects)."""
     return {
         "workload": f"C3: {rows} x {args.dim} {args.dtype} corpus row-sharded over {world} B200, top-{args.k} DEWI re-rank, "
                     f"query batch {args.batch}",
         "rows": rows, "dim": args.dim, "k": args.k, "batch": args.batch, "eta": args.eta, "entropy_pref": args.entropy_pref,
         "shards": world, "l2": "corpus shard >> 126 MB L2 (streamed once per step); no flush needed",
     }
+
+
+# ---- the reference arm -----------------------------------------------------------------------------------
+def run_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return  # under torchrun rank 0 alone runs the CPU arm
+    import bench_ref
+
+    line = bench_ref.reference_search_line(args, METRIC, workload_config)
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """The reference arm in a fresh process (its own BLAS pool, its own memory), a few steps: the `cpu_baseline`
+    object of our line is the one that run reports."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1", "--rows", str(args.rows),
+           "--dim", str(args.dim), "--k", str(args.k), "--eta", str(args.eta), "--entropy-pref", str(args.entropy_pref),
+           "--batch", str(args.batch), "--dtype", args.dtype, "--cpu-threads", str(args.cpu_threads),
+           "--cpu-max-rows", str(args.cpu_max_rows)]
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or "no output")[-400:]}
+    except Exception as exc:  # the baseline is reported, never required
+        return {"error": repr(exc)[:400]}
+
+
+# ---- parity check (outside the timed region) ---------------------------------------------------------------
+def _topk_agree(ref_ids, ref_sc, got_ids, got_sc, rtol=1e-5, tie=2e-6):
+    """The north-star gate for one query: scores within `rtol`; ids identical except inside a tie window of the
+    reference's own scores (incl. the k-th boundary)."""
+    ref_sc = np.asarray(ref_sc, dtype=np.float64)
+    got_sc = np.asarray(got_sc, dtype=np.float64)
+    scale = np.maximum(1.0, np.abs(ref_sc))
+    err = float(np.max(np.abs(got_sc - ref_sc) / scale))
+    ok = err <= rtol
+    for pos in np.nonzero(np.asarray(ref_ids) != np.asarray(got_ids))[0]:
+        near = np.abs(ref_sc - ref_sc[pos]) <= tie * scale[pos]
+        if not (got_ids[pos] in set(np.asarray(ref_ids)[near].tolist()) or near[-1]):
+            ok = False
+    return ok, err
+
+
+def parity_check(torch, dist, dewi_b200, index, local, args, world, rank, device, lo, hi, rows, q_dev):
+    from dewi_b200 import _native
+    from dewi_b200.sharded import PackedCandidates
+    from oracle import search as osearch
+
+    import ctypes
+
+    k, eta, pref = args.k, args.eta, args.entropy_pref
+    q = q_dev[0]
+    b = q.shape[0]
+    nq = min(8, b)
+    kcand = min(2 * k, rows)
+    out = {}
+    ids_a, sc_a = index.search_batch(q, k=k, eta=eta, entropy_pref=pref)
+    ok_all = True
+    # -- (a) the three exchange paths agree bit for bit (N > 1) --
+    sim_l, gid_l, dewi_l, ent_l = local.search_local(q, kcand)
+    if world > 1:
+        used = index.exchange
+        ids_n, sc_n = index.search_batch(q, k=k, eta=eta, entropy_pref=pref, exchange="nccl")
+        # single-shard re-rank of the gathered candidates: [world, B, kcand] -> [B, world * kcand], dewi_rerank raw
+        def gather(t):
+            g = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
+            dist.all_gather_into_tensor(g, t.contiguous())
+            return g.permute(1, 0, 2).reshape(b, world * kcand).contiguous()
+
+        sim_g, gid_g, dewi_g, ent_g = gather(sim_l), gather(gid_l), gather(dewi_l), gather(ent_l)
+        ids_v = torch.empty((b, k), dtype=torch.int64, device=device)
+        sc_v = torch.empty((b, k), dtype=torch.float32, device=device)
+        lib = _native.load_library()
+        _native.check(lib.dewi_rerank(ctypes.c_void_p(sim_g.data_ptr()), ctypes.c_void_p(gid_g.data_ptr()),
+                                      ctypes.c_void_p(dewi_g.data_ptr()), ctypes.c_void_p(ent_g.data_ptr()), b, 1, world * kcand, 0,
+                                      kcand, k, float(eta), float(pref), ctypes.c_void_p(ids_v.data_ptr()),
+                                      ctypes.c_void_p(sc_v.data_ptr()), device.index, _native.stream_ptr()))
+        eq_n = bool(torch.equal(ids_a, ids_n) and torch.equal(sc_a, sc_n))
+        eq_v = bool(torch.equal(ids_a, ids_v) and torch.equal(sc_a, sc_v))
+        out.update({"exchange_timed": used, "push_vs_nccl_equal": eq_n, "vs_single_shard_rerank_equal": eq_v})
+        ok_all = ok_all and eq_n and eq_v
+    else:
+        sim_g, gid_g, dewi_g, ent_g = sim_l, gid_l, dewi_l, ent_l
+    # -- (b) the oracle over a slab of THIS rank's stored rows + the rows of the global candidates --
+    n_local = hi - lo
+    slab_n = int(min(250_000, n_local))
+    s0 = int(((n_local - slab_n) // 2) // 256 * 256)
+    slab = local.export_rows(s0, slab_n)                       # the stored (bf16-representable) rows, as fp32
+    slab_dewi, slab_ent = local.get_payload_columns(s0, slab_n)
+    order = torch.argsort(sim_g[:nq], dim=1, descending=True, stable=True)[:, :kcand]
+    cand_ids = torch.gather(gid_g[:nq], 1, order).cpu().numpy()          # global top-2k by similarity, per query
+    cand_dewi = torch.gather(dewi_g[:nq], 1, order).cpu().numpy()
+    cand_ent = torch.gather(ent_g[:nq], 1, order).cpu().numpy()
+    cand_rows = np.zeros((nq, kcand, args.dim), dtype=np.float32)        # every rank contributes the rows it owns
+    for j in range(nq):
+        for c in range(kcand):
+            g = int(cand_ids[j, c])
+            if lo <= g < hi:
+                cand_rows[j, c] = local.get_row(g - lo)
+    if world > 1:
+        t = torch.from_numpy(cand_rows).to(device)
+        dist.all_reduce(t)
+        cand_rows = t.cpu().numpy()
+    q_host = q[:nq].cpu().numpy()
+    ids_host, sc_host = ids_a[:nq].cpu().numpy(), sc_a[:nq].cpu().numpy()
+    n_ok, worst, hits = 0, 0.0, 0
+    for j in range(nq):
+        outside = [c for c in range(kcand) if not (lo + s0 <= cand_ids[j, c] < lo + s0 + slab_n) and cand_ids[j, c] >= 0]
+        emb = np.concatenate([slab, cand_rows[j, outside]]) if outside else slab
+        gids = np.concatenate([lo + s0 + np.arange(slab_n, dtype=np.int64), cand_ids[j, outside]])
+        dw = np.concatenate([slab_dewi, cand_dewi[j, outside]])
+        en = np.concatenate([slab_ent, cand_ent[j, outside]]).astype(np.float64)
+        ridx, rsc = osearch.exact_search(emb, dw, en, q_host[j], k, eta, pref, True)
+        rids = gids[ridx]
+        ok, err = _topk_agree(rids, rsc, ids_host[j], sc_host[j])
+        n_ok += int(ok)
+        worst = max(worst, err)
+        hits += len(set(rids.tolist()) & set(ids_host[j].tolist()))
+    oracle_ok = n_ok == nq
+    ok_all = ok_all and oracle_ok
+    flag = torch.tensor([int(ok_all), n_ok, hits], dtype=torch.int64, device=device)
+    werr = torch.tensor([worst], dtype=torch.float64, device=device)
+    if world > 1:
+        mn = flag.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+        dist.all_reduce(werr, op=dist.ReduceOp.MAX)
+        ok_all = bool(mn[0].item() == 1)
+    out["oracle"] = {
+        "what": "oracle.search.exact_search (numpy restatement of backends.py:414-481) on each rank's slab of stored rows + the "
+                "rows of the global top-2k candidates; must return the GPU's global top-k (tie window 2e-6, scores 1e-5)",
+        "queries_checked": nq * world, "queries_ok": int(flag[1].item()), "slab_rows_per_rank": slab_n,
+        "recall_at_k": float(flag[2].item()) / (nq * world * k), "max_score_rel_err": float(werr.item()),
+    }
+    out["ok"] = ok_all
+    return out
 
 
 # ---- our arm -------------------------------------------------------------------------------------------
@@ -241,6 +354,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     peaks = load_peaks()
+    extras = [e for e in args.extras.split(",") if e]
 
     # ---- corpus: fit the requested rows into HBM (state it if it had to shrink) ----------------------
     rows = args.rows
@@ -316,7 +430,8 @@ def main():
         total_ms = timed(step_device, args.steps, args.warmup)
     ms_per_step = total_ms / args.steps
     value = args.batch * args.steps / (total_ms / 1e3)
-    launches_per_step = local.last_launches() + (1 if world > 1 else 0)
+    exchange_used = index.exchange if world > 1 else None
+    launches_per_step = local.last_launches() + (1 if exchange_used == "nccl" else 0)
 
     # ---- roofline: the sweep kernel alone, live over the timed region ----------------------------------
     n_prof = min(args.steps, 64)
@@ -341,11 +456,20 @@ def main():
     # dram__bytes_read+write of the main sweep launch from the committed `ncu --set full` capture
     # (profiles/r1_v7b_prof_b64_12M5rows_raw.csv: 19.2006 GB read + 6.3 MB written for a 19.2 GB shard),
     # scaled to this shard; only the single-query-block kernel (B <= 128) was captured at that ratio
-    traffic = shard_bytes * 1.00036 if (args.batch <= 128 and kind == "tcgen05") else None
+    traffic = shard_bytes * 1.00036 if (args.batch <= 128 and kind.startswith("tcgen05")) else None
     roofline.update({"traffic": traffic, "traffic_source": "ncu capture of the same kernel at 12.5M rows, scaled by shard size"
-                     if traffic else None, "kernel": f"search_tc_kernel ({kind}) incl. its sample pre-pass", "kernel_ms": sweep,
+                     if traffic else None, "kernel": f"similarity sweep ({kind}) incl. its sample pre-pass", "kernel_ms": sweep,
                      "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peaks["source"],
                      "kernel_share_of_step": sweep / ms_per_step})
+
+    # ---- sustained: the same step back to back for >= sustained_s seconds --------------------------------
+    sustained = None
+    if args.sustained_s > 0:
+        steps_s = int(max(args.steps, min(20000, args.sustained_s * 1e3 / ms_per_step)))
+        with ClockSampler(local_rank) as clocks_s:
+            ms_s = timed(step_device, steps_s, 1)
+        sustained = {"value": args.batch * steps_s / (ms_s / 1e3), "unit": "queries/s", "steps": steps_s, "seconds": ms_s / 1e3,
+                     "ms_per_step": ms_s / steps_s, "clocks": clocks_s.summary()}
 
     # ---- e2e: host (pinned) queries in, host results out, through the public API ---------------------
     def step_e2e(i):
@@ -377,28 +501,65 @@ def main():
         qb = gen_queries(torch, 100 + b, b, args.dim).to(device)
         steps_b = 3 if b >= 1024 else 5
         local.set_profiling(True)
-        ms_b = timed(lambda i: step_device(i, qb), steps_b, 2) / steps_b
+        with ClockSampler(local_rank) as clocks_b:
+            ms_b = timed(lambda i: step_device(i, qb), steps_b, 2) / steps_b
         kms = float(np.mean([local.sweep_ms(i)[0] for i in range(steps_b)]))
+        kind_b = local.sweep_ms(0)[1]
         local.set_profiling(False)
         r = roofline_for(b, kms, 2.0 * b * (hi - lo) * args.dim)
-        batch_sweep.append({"batch": b, "value": b / (ms_b / 1e3), "ms_per_step": ms_b, "kernel_ms": kms, "bound": r["bound"],
-                            "achieved": r["achieved"], "frac": r["frac"], "unit": r["unit"]})
+        batch_sweep.append({"batch": b, "value": b / (ms_b / 1e3), "ms_per_step": ms_b, "kernel_ms": kms, "kernel": kind_b,
+                            "bound": r["bound"], "achieved": r["achieved"], "frac": r["frac"], "unit": r["unit"],
+                            "sm_mhz": clocks_b.summary()["sm_mhz"]})
+
+    # ---- parity (outside every timed region) -------------------------------------------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_check(torch, dist, dewi_b200, index, local, args, world, rank, device, lo, hi, rows, q_dev)
+        except Exception as exc:  # a failed check is reported as such, never hidden
+            parity = {"ok": False, "error": repr(exc)[:500]}
+
+    # ---- single-query latency through the reference-facing call (C3 size), then the secondary rows ------
+    extra = {}
+    import bench_paths
+
+    if "latency" in extras and world == 1:
+        extra["latency_ms"] = {"c3": bench_paths.single_query_latency(torch, local, args.dim, args.k, args.eta, args.entropy_pref, 40,
+                                                                      f"{rows} x {args.dim} {args.dtype}")}
+    del index, local
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    if world == 1:
+        if "latency" in extras:
+            extra["latency_ms"].update(bench_paths.quickstart_latency(torch, dewi_b200, args.k))
+        for name in ("c2", "c4", "c5"):
+            if name in extras:
+                extra[name] = bench_paths.run_extra(name, torch, dewi_b200, peaks, local_rank)
+    elif world == 8 and "c5" in extras:
+        extra["c5"] = bench_paths.run_extra("c5", torch, dewi_b200, peaks, local_rank, dist_ready=True)
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cpu = cpu_reference_qps(args, steps=4, warmup=1, queries_per_step=8)
-            cpu.pop("ms_per_step_sample", None)
-        cfg = workload_config(args, world, rows)
-        cfg.update({"build_s": round(t_build, 2), "parallelism": f"row-shard x{world}", "note": shrunk})
+            cpu = cpu_baseline_subprocess(args)
+            if isinstance(extra.get("c2"), dict) and "error" not in extra["c2"]:
+                pt = [p for p in (cpu or {}).get("points", []) if p.get("rows") == 1_000_000]
+                if pt:  # the reference's single-query path at C2's size: B queries cost B x that (no batch API)
+                    extra["c2"]["cpu_baseline"] = {"value": 1e3 / pt[0]["ms_median"], "unit": "queries/s", "cores": cpu.get("cores"),
+                                                   "kind": cpu.get("kind"), "sample": "1M-row point of cpu_baseline.points "
+                                                   f"({pt[0]['ms_median']:.2f} ms/query median of {pt[0]['queries']})"}
+        info = {"build_s": round(t_build, 2), "parallelism": f"row-shard x{world}", "note": shrunk}
         if world > 1:
-            cfg["exchange"] = ("fused peer stores over NVLink (symmetric memory), no collective on the search path"
-                               if index.exchange == "push" else "one NCCL all_gather_into_tensor per batch")
+            info["exchange"] = ("fused peer stores over NVLink (symmetric memory), no collective on the search path"
+                                if exchange_used == "push" else "one NCCL all_gather_into_tensor per batch")
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": args.dtype, "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(), "batch_sweep": batch_sweep,
+            "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world, rows), "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
+            "sustained": sustained, "batch_sweep": batch_sweep, "parity_check": parity, "run_info": info, "extra": extra,
         }
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

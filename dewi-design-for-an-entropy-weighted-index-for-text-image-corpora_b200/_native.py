@@ -53,9 +53,13 @@ SIGNATURES = {
     "dewi_index_set_payload": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "dewi_index_size": (c_int, [c_void_p, POINTER(c_int64)]),
     "dewi_index_get_row": (c_int, [c_void_p, c_int64, c_void_p]),
+    "dewi_index_export_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "dewi_index_export_bf16": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "dewi_index_append_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "dewi_index_get_payload": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int, c_void_p]),
     "dewi_index_search_local": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dewi_index_search_local_push": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_uint64), POINTER(c_uint64), c_int64, c_uint32, c_void_p]),
-    "dewi_rerank_gathered": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_uint32, c_int, c_void_p]),
+    "dewi_rerank_gathered": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_void_p, c_uint32, c_void_p, c_double, c_int, c_void_p]),
     "dewi_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "dewi_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "dewi_index_last_launches": (c_int, [c_void_p, POINTER(c_int)]),

@@ -132,6 +132,26 @@ class ColumnStore:
     def all_default(self) -> bool:
         return all(cols is None for _, cols in self._chunks)
 
+    def write(self, offset: int, cols: np.ndarray) -> None:
+        """Overwrite rows `[offset, offset + len(cols))` (they may span chunks; default chunks are
+        materialised on first write)."""
+        import bisect
+
+        cols = np.ascontiguousarray(cols, dtype=np.float32)
+        if offset < 0 or offset + cols.shape[0] > self.n:
+            raise ValueError("payload rows outside the store")
+        done = 0
+        while done < cols.shape[0]:
+            c = bisect.bisect_right(self._starts, offset + done) - 1
+            n_c, have = self._chunks[c]
+            if have is None:
+                have = np.zeros((n_c, len(PAYLOAD_FIELDS)), dtype=np.float32)
+                self._chunks[c] = (n_c, have)
+            at = offset + done - self._starts[c]
+            m = min(n_c - at, cols.shape[0] - done)
+            have[at:at + m] = cols[done:done + m]
+            done += m
+
 
 class ColumnPayloads:
     """Read-only id -> Payload mapping over a `ColumnStore`."""
@@ -208,6 +228,9 @@ class CudaIndex(BaseIndex):
         self._columns: Optional[ColumnStore] = None  # bulk payload columns (bulk ingest only)
         self._flags = _native.FLAG_PRECISE_QUERY if precise_query else 0
         self._host_rows: Optional[np.ndarray] = None
+        # True once the device payload columns were written without a host mirror (set_payload_columns /
+        # set_payload_from_signals(mirror=False)): build() / refresh_payloads() then leave them alone
+        self._device_payload_direct = False
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -257,6 +280,22 @@ class CudaIndex(BaseIndex):
             n, ptr, is_host, keep = rows.shape[0], rows.data_ptr(), int(not rows.is_cuda), rows
         if rows.ndim != 2 or rows.shape[1] != self.dim:
             raise ValueError(f"Expected embeddings of shape (n, {self.dim}), got {tuple(rows.shape)}")
+        # every argument check happens BEFORE the rows reach the device: a ValueError must leave the index unchanged
+        if doc_ids is not None and len(doc_ids) != n:
+            raise ValueError("doc_ids and embeddings disagree in length")
+        cols = None
+        if payloads is not None:
+            if payload_columns is not None or self._columns is not None:
+                raise ValueError("cannot mix payload objects and payload columns")
+            if len(payloads) != n or doc_ids is None:
+                raise ValueError("payload objects need matching doc_ids")
+        elif payload_columns is not None or self._columns is not None or not self._payloads:
+            if payload_columns is not None:
+                cols = np.ascontiguousarray(payload_columns, dtype=np.float32)
+                if cols.shape != (n, len(PAYLOAD_FIELDS)):
+                    raise ValueError(f"payload_columns must be [n, {len(PAYLOAD_FIELDS)}]")
+            if self._payloads and not isinstance(self._payloads, ColumnPayloads):
+                raise ValueError("cannot mix payload objects and payload columns")
         with torch.cuda.device(self.device):
             rc = self._lib.dewi_index_append(self._h, ctypes.c_void_p(ptr), n, int(bool(normalized)), is_host,
                                              _native.stream_ptr())
@@ -272,24 +311,11 @@ class CudaIndex(BaseIndex):
             else:
                 self._doc_ids = LazyIds(base + n)
         else:
-            if len(doc_ids) != n:
-                raise ValueError("doc_ids and embeddings disagree in length")
             self._doc_ids = list(self._doc_ids) + list(doc_ids)
         if payloads is not None:
-            if payload_columns is not None or self._columns is not None:
-                raise ValueError("cannot mix payload objects and payload columns")
-            if len(payloads) != n or doc_ids is None:
-                raise ValueError("payload objects need matching doc_ids")
             for d, p in zip(doc_ids, payloads):
                 self._payloads[d] = p
         elif payload_columns is not None or self._columns is not None or not self._payloads:
-            cols = None
-            if payload_columns is not None:
-                cols = np.ascontiguousarray(payload_columns, dtype=np.float32)
-                if cols.shape != (n, len(PAYLOAD_FIELDS)):
-                    raise ValueError(f"payload_columns must be [n, {len(PAYLOAD_FIELDS)}]")
-            if self._payloads and not isinstance(self._payloads, ColumnPayloads):
-                raise ValueError("cannot mix payload objects and payload columns")
             if self._columns is None:
                 self._columns = ColumnStore()
             self._columns.append(n, cols)
@@ -326,8 +352,8 @@ class CudaIndex(BaseIndex):
         The reference dereferences the shared Payload objects at *search* time; this backend snapshots
         them at `build()`.  Call this after mutating payloads of an already-built index."""
         n = self._n_device
-        if n == 0:
-            return
+        if n == 0 or self._device_payload_direct:
+            return  # (device columns written directly are authoritative: nothing on the host to re-read)
         if self._columns is not None:
             if self._columns.all_default():
                 return  # device columns are zero-initialised, or were written by set_payload_columns()
@@ -342,10 +368,30 @@ class CudaIndex(BaseIndex):
                 p = pl[d]
                 dewi[i] = p.dewi
                 ent[i] = (p.ht_mean + p.hi_mean) * 0.5
-        self.set_payload_columns(dewi, ent)
+        self._write_payload_columns(dewi, ent)
 
     def set_payload_columns(self, dewi, ent, offset: int = 0) -> None:
-        """Write the two device payload columns directly (numpy arrays or tensors on this GPU)."""
+        """Write the two device payload columns directly (numpy arrays or tensors on this GPU).  The host-side
+        Payload view is NOT updated: from here on the device columns are authoritative -- `build()` /
+        `refresh_payloads()` no longer overwrite them, `search()` tuples carry the host view (defaults for a bulk
+        ingest without payload columns) and `save()` refuses rather than persist stale payloads.  Use
+        `set_payload_from_signals` (mirrored) or `add_batch(payload_columns=...)` to keep both sides in step."""
+        self._write_payload_columns(dewi, ent, offset)
+        self._device_payload_direct = True
+
+    def get_payload_columns(self, offset: int = 0, n: Optional[int] = None):
+        """The device payload columns `(dewi, ent)` of rows `[offset, offset + n)` as float32 numpy arrays."""
+        torch = _torch()
+        self._flush_pending()
+        n = self._n_device - offset if n is None else int(n)
+        dewi = np.empty(n, dtype=np.float32)
+        ent = np.empty(n, dtype=np.float32)
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.dewi_index_get_payload(self._h, int(offset), n, ctypes.c_void_p(dewi.ctypes.data),
+                                                           ctypes.c_void_p(ent.ctypes.data), 1, _native.stream_ptr()))
+        return dewi, ent
+
+    def _write_payload_columns(self, dewi, ent, offset: int = 0) -> None:
         torch = _torch()
 
         def ptr(a):
@@ -364,22 +410,46 @@ class CudaIndex(BaseIndex):
                                                            dh, _native.stream_ptr()))
             torch.cuda.current_stream().synchronize()
 
-    def set_payload_from_signals(self, signals, scorer, fit: bool = True, offset: int = 0):
+    def set_payload_from_signals(self, signals, scorer, fit: bool = True, offset: int = 0, mirror: bool = True):
         """Bulk form of the README loop (README.md:94-110; pipelines.py:199-221): `signals` is a `[7, n]`
         array / tensor in `SIGNAL_FIELDS` order for rows `[offset, offset + n)`.  Fits the scorer's robust
         statistics (unless `fit=False`), scores every row on the device and writes `dewi` and
-        `(ht_mean + hi_mean) * 0.5` straight into the device payload columns -- no per-document Python.
-        Returns the dewi scores (CUDA float32 tensor)."""
+        `(ht_mean + hi_mean) * 0.5` straight into the device payload columns -- no per-document Python on
+        the scoring path.  Returns the dewi scores (CUDA float32 tensor).
+
+        mirror=True (default) also writes the scores and the seven signals into the HOST payload view (the
+        column store of a bulk ingest, or the shared `Payload` objects of per-document `add`), which is what
+        the README loop leaves behind (`payload.dewi = scorer.score(signals)`): a later `build()`,
+        `refresh_payloads()`, `search()` tuple or `save()` sees the same values as the device.
+        mirror=False skips that copy (32 B/row of host memory and a device->host transfer -- the 100M-row
+        case) and marks the device columns authoritative instead (see `set_payload_columns`)."""
         torch = _torch()
         sig = torch.as_tensor(signals).to(torch.device("cuda", self.device), torch.float32)
         if sig.ndim != 2 or sig.shape[0] != 7:
             raise ValueError("expected seven signal columns")
         self._flush_pending()
+        n = sig.shape[1]
+        if offset < 0 or offset + n > self._n_device:
+            raise ValueError("signal rows outside the corpus")
         if fit:
             scorer.fit_stats_columns(sig)
         dewi = scorer.score_batch(sig)
         ent = ((sig[0].double() + sig[2].double()) * 0.5).float()  # backends.py:458
-        self.set_payload_columns(dewi, ent, offset=offset)
+        self._write_payload_columns(dewi, ent, offset=offset)
+        if not mirror:
+            self._device_payload_direct = True
+            return dewi
+        cols = np.empty((n, len(PAYLOAD_FIELDS)), dtype=np.float32)
+        cols[:, 0] = dewi.cpu().numpy()
+        cols[:, 1:] = sig.t().cpu().numpy()
+        if self._columns is not None:
+            self._columns.write(offset, cols)
+        else:
+            pl = self._payloads
+            for r, d in enumerate(self._doc_ids[offset:offset + n]):
+                p = pl[d]
+                for j, f in enumerate(PAYLOAD_FIELDS):
+                    setattr(p, f, float(cols[r, j]))
         return dewi
 
     def reserve(self, rows: int) -> None:
@@ -521,12 +591,26 @@ class CudaIndex(BaseIndex):
         (index.py:101-116).  Fetched lazily; pending rows are included."""
         if self._host_rows is None:
             rows = np.empty((len(self), self.dim), dtype=np.float32)
-            for i in range(self._n_device):
-                _native.check(self._lib.dewi_index_get_row(self._h, i, ctypes.c_void_p(rows[i].ctypes.data)))
+            if self._n_device:
+                self.export_rows(0, self._n_device, out=rows[: self._n_device])
             for j, r in enumerate(self._pending):
                 rows[self._n_device + j] = r
             self._host_rows = rows
         return self._host_rows
+
+    def export_rows(self, row0: int = 0, n: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Stored (normalised) rows `[row0, row0 + n)` as a float32 host array: ONE bulk device->host export in
+        large chunks (`dewi_index_export_rows`), never a transfer per row."""
+        torch = _torch()
+        n = self._n_device - row0 if n is None else int(n)
+        if out is None:
+            out = np.empty((n, self.dim), dtype=np.float32)
+        if out.shape != (n, self.dim) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 [n, dim] array")
+        with torch.cuda.device(self.device):
+            _native.check(self._lib.dewi_index_export_rows(self._h, int(row0), n, ctypes.c_void_p(out.ctypes.data), 1,
+                                                           _native.stream_ptr()))
+        return out
 
     def get_row(self, row: int) -> np.ndarray:
         self._flush_pending()
@@ -534,28 +618,76 @@ class CudaIndex(BaseIndex):
         _native.check(self._lib.dewi_index_get_row(self._h, int(row), ctypes.c_void_p(out.ctypes.data)))
         return out
 
-    def save(self, path: Union[str, Path]) -> None:
+    SIDECAR_SHARD_ROWS = 4_000_000   # rows per bf16 sidecar file (6 GB at dim 768)
+    FP32_EXPORT_CHUNK = 1_000_000    # rows per bulk export while writing embeddings.npy
+
+    def save(self, path: Union[str, Path], fp32: Optional[bool] = None, sidecar: Optional[bool] = None) -> None:
         """Write the directory `ExactIndex.save` writes (backends.py:483-515): `metadata.json`,
-        `payloads.jsonl` (key `doc_id`), `embeddings.npy` (normalised fp32) -- loadable by either."""
+        `payloads.jsonl` (key `doc_id`), `embeddings.npy` (normalised fp32) -- loadable by either backend.
+
+        Rows leave the device in bulk (`dewi_index_export_rows`, ~1M rows per transfer) straight into a
+        memory-mapped `embeddings.npy`; nothing is copied per row and the matrix is never held twice.
+        A bf16-storage index also writes a sharded SIDECAR of the raw bf16 rows
+        (`embeddings_bf16.NNNN.npy`, uint16 `[rows, dim]`, `SIDECAR_SHARD_ROWS` rows each, listed in
+        `metadata.json["bf16_sidecar"]`): `CudaIndex.load` prefers it (half the bytes, bit-exact planes, no
+        re-rounding); the reference ignores it.  `fp32=False` skips `embeddings.npy` (default: skipped only
+        when it would exceed 64 GB -- 100M x 768 fp32 is 307 GB; such a directory is for this backend only),
+        `sidecar=False` skips the sidecar."""
+        torch = _torch()
         path = Path(path)
         path.mkdir(parents=True, exist_ok=True)
-        rows = self._embeddings
+        if self._device_payload_direct:
+            raise ValueError("the device payload columns were written without a host mirror (set_payload_columns / "
+                             "set_payload_from_signals(mirror=False)): saving would persist stale payloads")
+        self._flush_pending()
+        n = self._n_device
+        if fp32 is None:
+            fp32 = n * self.dim * 4 <= (64 << 30)
+        if sidecar is None:
+            sidecar = self.dtype == "bf16"
+        if sidecar and self.dtype != "bf16":
+            raise ValueError("the bf16 sidecar exists for bf16-storage indices only")
         meta = {
             "dim": self.dim, "space": self.space, "doc_ids": list(self._doc_ids), "normalize": self._normalize,
-            "is_trained": self._is_trained, "num_embeddings": int(rows.shape[0]),
-            "type": type(self).__name__, "dtype": self.dtype,
+            "is_trained": self._is_trained, "num_embeddings": int(n),
+            "type": type(self).__name__, "dtype": self.dtype, "has_fp32": bool(fp32 and n > 0),
         }
+        if n > 0 and fp32:
+            if self._host_rows is not None:
+                np.save(str(path / "embeddings.npy"), self._host_rows)
+            else:
+                out = np.lib.format.open_memmap(str(path / "embeddings.npy"), mode="w+", dtype=np.float32, shape=(n, self.dim))
+                buf = np.empty((min(n, self.FP32_EXPORT_CHUNK), self.dim), dtype=np.float32)
+                for lo in range(0, n, self.FP32_EXPORT_CHUNK):
+                    m = min(self.FP32_EXPORT_CHUNK, n - lo)
+                    self.export_rows(lo, m, out=buf[:m])
+                    out[lo:lo + m] = buf[:m]
+                out.flush()
+                del out
+        if n > 0 and sidecar:
+            shards = []
+            for s, lo in enumerate(range(0, n, self.SIDECAR_SHARD_ROWS)):
+                m = min(self.SIDECAR_SHARD_ROWS, n - lo)
+                raw = np.empty((m, self.dim), dtype=np.uint16)
+                with torch.cuda.device(self.device):
+                    _native.check(self._lib.dewi_index_export_bf16(self._h, lo, m, ctypes.c_void_p(raw.ctypes.data), 1,
+                                                                   _native.stream_ptr()))
+                name = f"embeddings_bf16.{s:04d}.npy"
+                np.save(str(path / name), raw)
+                shards.append({"file": name, "row0": lo, "rows": m})
+            meta["bf16_sidecar"] = shards
         (path / "metadata.json").write_text(json.dumps(meta))
         with open(path / "payloads.jsonl", "w") as f:
             for d in self._doc_ids:
                 f.write(json.dumps({"doc_id": d, "payload": self._payloads[d].to_dict()}) + "\n")
-        if rows.shape[0] > 0:
-            np.save(str(path / "embeddings.npy"), rows)
 
     @classmethod
     def load(cls, path: Union[str, Path], **kwargs: Any) -> "CudaIndex":
         """Load a directory written by `CudaIndex.save` or by the reference's `ExactIndex.save`
-        (backends.py:517-556)."""
+        (backends.py:517-556).  A bf16 sidecar, when present and the index is opened in bf16 storage, is
+        uploaded as-is (`dewi_index_append_bf16`); otherwise `embeddings.npy` is read through a memory map and
+        ingested in bulk."""
+        torch = _torch()
         path = Path(path)
         meta = json.loads((path / "metadata.json").read_text())
         index = cls(dim=meta["dim"], space=meta["space"], dtype=kwargs.pop("dtype", meta.get("dtype", "fp32")), **kwargs)
@@ -566,12 +698,34 @@ class CudaIndex(BaseIndex):
                 rec = json.loads(line)
                 payloads[rec.get("doc_id", rec.get("id"))] = Payload.from_dict(rec["payload"])
         emb_path = path / "embeddings.npy"
-        if emb_path.exists() and meta.get("num_embeddings", 0) > 0:
-            rows = np.load(str(emb_path)).astype(np.float32)
-            index.add_batch(ids, rows, payloads=[payloads[d] for d in ids], normalized=True)
+        shards = meta.get("bf16_sidecar") or []
+        n = int(meta.get("num_embeddings", 0))
+        if n > 0 and shards and index.dtype == "bf16":
+            index.reserve(n)
+            for sh in shards:
+                raw = np.ascontiguousarray(np.load(str(path / sh["file"]), mmap_mode="r"), dtype=np.uint16)
+                if raw.shape != (sh["rows"], index.dim):
+                    raise ValueError(f"{sh['file']}: unexpected shape {raw.shape}")
+                with torch.cuda.device(index.device):
+                    _native.check(index._lib.dewi_index_append_bf16(index._h, ctypes.c_void_p(raw.ctypes.data), raw.shape[0], 1,
+                                                                    _native.stream_ptr()))
+                index._n_device += raw.shape[0]
+            index._doc_ids = ids
+            index._payloads = {d: payloads[d] for d in ids}
+            if meta.get("is_trained", False):
+                index.build()
+        elif emb_path.exists() and n > 0:
+            rows = np.load(str(emb_path), mmap_mode="r")
+            index.reserve(n)
+            for lo in range(0, n, cls.FP32_EXPORT_CHUNK):
+                hi = min(lo + cls.FP32_EXPORT_CHUNK, n)
+                block = np.ascontiguousarray(rows[lo:hi], dtype=np.float32)
+                index.add_batch(ids[lo:hi], block, payloads=[payloads[d] for d in ids[lo:hi]], normalized=True)
             if meta.get("is_trained", False):
                 index.build()
         else:
+            if n > 0:
+                raise ValueError(f"{path}: neither embeddings.npy nor a usable bf16 sidecar holds the {n} rows")
             index._doc_ids = ids
             index._payloads = payloads
         return index

@@ -2,7 +2,9 @@
 // Entry points are documented in include/dewi_b200.h next to the reference code they replace.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -15,6 +17,40 @@ void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(const std::string& msg) {
   g_last_error = msg;
   return 1;
+}
+
+namespace {
+std::mutex g_env_mu;
+std::map<std::string, std::pair<bool, int>> g_env_cache;  // name -> (set, value)
+std::pair<bool, int> env_lookup(const char* name) {
+  std::lock_guard<std::mutex> lock(g_env_mu);
+  auto it = g_env_cache.find(name);
+  if (it != g_env_cache.end()) return it->second;
+  const char* v = getenv(name);
+  const std::pair<bool, int> r = v ? std::make_pair(true, atoi(v)) : std::make_pair(false, 0);
+  g_env_cache.emplace(name, r);
+  return r;
+}
+}  // namespace
+
+int env_int(const char* name, int dflt) {
+  const auto r = env_lookup(name);
+  return r.first ? r.second : dflt;
+}
+bool env_set(const char* name) { return env_lookup(name).first; }
+
+int current_sm_count() {
+  static std::mutex mu;
+  static int sms[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
 }
 
 namespace {
@@ -63,9 +99,12 @@ struct dewi_index {
   int64_t map_rows = -1;
   int map_box = 0;
   // workspaces
-  DevBuf stage, qraw, qn, q0, q1, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
+  DevBuf stage, stage2, qraw, qn, q0, q1, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
       out_score;
   int last_launches = 0;
+  // host ingest pipeline: copies run on `copy_stream`, two staging buffers, one "kernel done with buffer" event each
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t stage_free[2] = {}, stage_full[2] = {};
   DevBuf push_ticket;               // block counter of the peer-push finalize kernel
   DevBuf sync_cnt;                  // rendezvous counters of the CTA-pair sweep
   bool push_ticket_zeroed = false;
@@ -227,7 +266,12 @@ int dewi_index_destroy(dewi_index_t* h) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
   }
-  for (DevBuf* b : {&h->stage, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]);
+    if (h->stage_full[i]) cudaEventDestroy(h->stage_full[i]);
+  }
+  for (DevBuf* b : {&h->stage, &h->stage2, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
                     &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score, &h->push_ticket, &h->sync_cnt})
     b->release();
   delete h;
@@ -257,21 +301,40 @@ int dewi_index_append(dewi_index_t* h, const float* rows, int64_t n, int normali
   DEWI_TRY(grow(h, h->n + n, stream));
   const int do_norm = (h->space == DEWI_SPACE_COSINE && !normalized) ? 1 : 0;
   const size_t d = static_cast<size_t>(h->dim);
-  const int64_t chunk = src_is_host ? std::max<int64_t>(1, (int64_t(256) << 20) / static_cast<int64_t>(d * 4)) : n;
-  for (int64_t done = 0; done < n; done += chunk) {
+  // Host rows go through two 64 MB staging buffers: the copy of chunk i+1 (on the handle's copy stream) overlaps
+  // the normalise / plane-split kernel of chunk i (on the caller's stream); events order the two per buffer.
+  const int64_t chunk = src_is_host ? std::max<int64_t>(1, (int64_t(64) << 20) / static_cast<int64_t>(d * 4)) : n;
+  if (src_is_host && !h->copy_stream) {
+    DEWI_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      DEWI_CUDA(cudaEventCreateWithFlags(&h->stage_free[i], cudaEventDisableTiming));
+      DEWI_CUDA(cudaEventCreateWithFlags(&h->stage_full[i], cudaEventDisableTiming));
+    }
+  }
+  int buf = 0;
+  int used[2] = {0, 0};
+  for (int64_t done = 0; done < n; done += chunk, buf ^= 1) {
     const int64_t m = std::min(chunk, n - done);
     const float* src = rows + static_cast<size_t>(done) * d;
     if (src_is_host) {
-      DEWI_TRY(h->stage.ensure(static_cast<size_t>(m) * d * 4));
-      DEWI_CUDA(cudaMemcpyAsync(h->stage.p, src, static_cast<size_t>(m) * d * 4, cudaMemcpyHostToDevice, stream));
-      src = h->stage.as<float>();
+      DevBuf& st = buf ? h->stage2 : h->stage;
+      if (used[buf]) DEWI_CUDA(cudaStreamWaitEvent(h->copy_stream, h->stage_free[buf], 0));  // kernel of chunk i-2 is done
+      else DEWI_TRY(st.ensure(static_cast<size_t>(std::min(chunk, n)) * d * 4));
+      DEWI_CUDA(cudaMemcpyAsync(st.p, src, static_cast<size_t>(m) * d * 4, cudaMemcpyHostToDevice, h->copy_stream));
+      DEWI_CUDA(cudaEventRecord(h->stage_full[buf], h->copy_stream));
+      DEWI_CUDA(cudaStreamWaitEvent(stream, h->stage_full[buf], 0));
+      src = st.as<float>();
     }
     const size_t off = static_cast<size_t>(h->n + done) * d;
     DEWI_TRY(launch_prep_corpus(src, m, h->dim, do_norm, h->rows_f32 ? h->rows_f32 + off : nullptr,
                                 h->plane0 ? h->plane0 + off : nullptr, h->plane1 ? h->plane1 + off : nullptr,
                                 h->bad_flag, stream));
-    if (src_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));  // staging buffer is reused
+    if (src_is_host) {
+      DEWI_CUDA(cudaEventRecord(h->stage_free[buf], stream));
+      used[buf] = 1;
+    }
   }
+  if (src_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));  // the caller's host rows may be released on return
   if (do_norm) {
     int bad = 0;
     DEWI_CUDA(cudaMemcpyAsync(&bad, h->bad_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -321,6 +384,84 @@ int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host) {
       std::memcpy(&out_host[i], &u, 4);
     }
   }
+  return 0;
+}
+
+int dewi_index_export_rows(dewi_index_t* h, int64_t row0, int64_t n, float* out, int dst_is_host, void* stream_) {
+  if (!h || !out) return fail("null argument");
+  if (row0 < 0 || n < 0 || row0 + n > h->n) return fail("row range outside the corpus");
+  if (n == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  const size_t d = static_cast<size_t>(h->dim);
+  const cudaMemcpyKind kind = dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (h->rows_f32) {  // fp32 mode keeps the exact rows: one copy (the driver stages a pageable destination itself)
+    DEWI_CUDA(cudaMemcpyAsync(out, h->rows_f32 + static_cast<size_t>(row0) * d, static_cast<size_t>(n) * d * 4, kind, stream));
+    if (dst_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  // bf16 mode: widen on the device (exact), in >= 64 MB chunks through the staging buffer when the destination is host memory
+  const int64_t chunk = dst_is_host ? std::max<int64_t>(1, (int64_t(128) << 20) / static_cast<int64_t>(d * 4)) : n;
+  for (int64_t done = 0; done < n; done += chunk) {
+    const int64_t m = std::min(chunk, n - done);
+    const __nv_bfloat16* src = h->plane0 + static_cast<size_t>(row0 + done) * d;
+    float* dst = out + static_cast<size_t>(done) * d;
+    if (dst_is_host) {
+      DEWI_TRY(h->stage.ensure(static_cast<size_t>(std::min(chunk, n)) * d * 4));
+      DEWI_TRY(launch_widen_bf16(src, static_cast<int64_t>(m) * h->dim, h->stage.as<float>(), stream));
+      DEWI_CUDA(cudaMemcpyAsync(dst, h->stage.p, static_cast<size_t>(m) * d * 4, cudaMemcpyDeviceToHost, stream));
+      DEWI_CUDA(cudaStreamSynchronize(stream));  // staging buffer is reused
+    } else {
+      DEWI_TRY(launch_widen_bf16(src, static_cast<int64_t>(m) * h->dim, dst, stream));
+    }
+  }
+  return 0;
+}
+
+int dewi_index_export_bf16(dewi_index_t* h, int64_t row0, int64_t n, uint16_t* out, int dst_is_host, void* stream_) {
+  if (!h || !out) return fail("null argument");
+  if (row0 < 0 || n < 0 || row0 + n > h->n) return fail("row range outside the corpus");
+  if (h->dtype != DEWI_DTYPE_BF16 || !h->plane0) return fail("export_bf16 needs a bf16-storage index");
+  if (n == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  const size_t d = static_cast<size_t>(h->dim);
+  DEWI_CUDA(cudaMemcpyAsync(out, h->plane0 + static_cast<size_t>(row0) * d, static_cast<size_t>(n) * d * 2,
+                            dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, stream));
+  if (dst_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));
+  return 0;
+}
+
+int dewi_index_append_bf16(dewi_index_t* h, const uint16_t* rows, int64_t n, int src_is_host, void* stream_) {
+  if (!h) return fail("null handle");
+  if (n < 0) return fail("negative row count");
+  if (n == 0) return 0;
+  if (!rows) return fail("rows is NULL");
+  if (h->dtype != DEWI_DTYPE_BF16) return fail("append_bf16 needs a bf16-storage index");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  if (h->n + n >= (int64_t(1) << 31)) return fail("a shard holds at most 2^31-1 rows");
+  DEWI_TRY(grow(h, h->n + n, stream));
+  const size_t d = static_cast<size_t>(h->dim);
+  DEWI_CUDA(cudaMemcpyAsync(h->plane0 + static_cast<size_t>(h->n) * d, rows, static_cast<size_t>(n) * d * 2,
+                            src_is_host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, stream));
+  if (src_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));
+  h->n += n;
+  h->map_rows = -1;
+  return 0;
+}
+
+int dewi_index_get_payload(dewi_index_t* h, int64_t offset, int64_t n, float* dewi_out, float* ent_out, int dst_is_host,
+                           void* stream_) {
+  if (!h || !dewi_out || !ent_out) return fail("null argument");
+  if (offset < 0 || n < 0 || offset + n > h->n) return fail("payload range outside the corpus");
+  if (n == 0) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DEWI_TRY(set_device(h));
+  const cudaMemcpyKind kind = dst_is_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  DEWI_CUDA(cudaMemcpyAsync(dewi_out, h->dewi_col + offset, static_cast<size_t>(n) * 4, kind, stream));
+  DEWI_CUDA(cudaMemcpyAsync(ent_out, h->ent_col + offset, static_cast<size_t>(n) * 4, kind, stream));
+  if (dst_is_host) DEWI_CUDA(cudaStreamSynchronize(stream));
   return 0;
 }
 
@@ -527,9 +668,10 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
 
 int dewi_rerank_gathered(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int n_shards,
                          int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
-                         int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, int device,
-                         void* stream_) {
+                         int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, uint32_t* status_word,
+                         double timeout_s, int device, void* stream_) {
   if (!sim || !id || !dewi_v || !ent_v || !out_id || !out_score || !ready_flags) return fail("null argument");
+  if (!(timeout_s > 0.0)) timeout_s = static_cast<double>(env_int("DEWI_PUSH_TIMEOUT_S", 120));
   if (B <= 0 || n_shards <= 0 || kcand <= 0 || k <= 0) return fail("B, n_shards, kcand and k must be positive");
   if (shard_stride_bytes % 8 != 0) return fail("shard stride must be a multiple of 8 bytes");
   const int64_t ncand = static_cast<int64_t>(n_shards) * kcand;
@@ -538,7 +680,8 @@ int dewi_rerank_gathered(const float* sim, const int64_t* id, const float* dewi_
   DEWI_CUDA(cudaSetDevice(device));
   return launch_rerank(sim, id, dewi_v, ent_v, B, n_shards, kcand, shard_stride_bytes, cand_count, k,
                        static_cast<float>(1.0 - eta), static_cast<float>(eta), static_cast<float>(entropy_pref),
-                       entropy_pref != 0.0 ? 1 : 0, out_id, out_score, static_cast<cudaStream_t>(stream_), ready_flags, seq);
+                       entropy_pref != 0.0 ? 1 : 0, out_id, out_score, static_cast<cudaStream_t>(stream_), ready_flags, seq,
+                       status_word, timeout_s);
 }
 
 int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const float* ent_v, int B, int n_shards,

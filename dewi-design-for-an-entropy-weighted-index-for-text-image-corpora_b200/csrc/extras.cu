@@ -15,8 +15,9 @@ __global__ void local_weights_kernel(const float* __restrict__ s, long long n, f
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     float z = __fdiv_rn(__fsub_rn(__ldg(s + i), med), den);   // (s - med) / (1.4826 * mad)
+    const bool is_nan = z != z;                               // (fminf / fmaxf drop a NaN, np.clip propagates it)
     z = fminf(fmaxf(z, -5.f), 5.f);                           // np.clip(z, -5, 5)
-    out[i] = log1pf(expf(z));                                 // np.log1p(np.exp(z))
+    out[i] = is_nan ? nanf("") : log1pf(expf(z));             // np.log1p(np.exp(z))
   }
 }
 
@@ -72,7 +73,7 @@ extern "C" int dewi_local_weights(const float* s, int64_t n, float* out, int dev
   const float den = 1.4826f * mad32;  // float32(1.4826) * float32 mad, as numpy's weak-scalar product
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int threads = 256;
-  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n, threads), 148 * 16));
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n, threads), static_cast<int64_t>(current_sm_count()) * 16));
   local_weights_kernel<<<blocks, threads, 0, stream>>>(s, n, static_cast<float>(med), den, out);
   DEWI_CUDA(cudaGetLastError());
   DEWI_CUDA(cudaStreamSynchronize(stream));

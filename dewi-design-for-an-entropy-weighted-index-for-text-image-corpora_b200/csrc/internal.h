@@ -38,6 +38,14 @@ __host__ __device__ inline int query_lane(int j) { return (j & 3) * 32 + (j >> 2
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// SM count of the CURRENT device, looked up once per device (launch geometry: grids are sized in
+// multiples of it instead of a hard-coded 148).  Falls back to 148 only if the query itself fails.
+int current_sm_count();
+// Experiment switches (DEWI_* environment variables): read once per name, then served from a cache.
+// Returns `dflt` when the variable is unset.
+int env_int(const char* name, int dflt);
+bool env_set(const char* name);
+
 // Partial candidate lists: [n_items][kc][128] (score) / (row index); item = chunk * n_qb + qb.
 struct Partials {
   float* s = nullptr;
@@ -129,7 +137,7 @@ int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int
 int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
                   int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
                   int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags = nullptr,
-                  unsigned int seq = 0);
+                  unsigned int seq = 0, unsigned int* status = nullptr, double timeout_s = 120.0);
 
 // ---- operand preparation (prep.cu) -----------------------------------------------------------
 // rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.
@@ -140,5 +148,7 @@ int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, floa
 // lane_order 2 (b < 64 only): row (b & 3) * 16 + (b >> 2), the A-row whose M = 64 accumulator lane is query_lane(b).
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
                         __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0);
+// bf16 -> fp32 (exact widening) of `count` contiguous elements: bulk export of a bf16-storage corpus.
+int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaStream_t stream);
 
 }  // namespace dewi

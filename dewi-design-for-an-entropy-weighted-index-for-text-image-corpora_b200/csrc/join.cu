@@ -147,7 +147,7 @@ __global__ void join_finish_kernel(const unsigned long long* __restrict__ row_be
 
 int normalize_into(const float* src, int64_t n, int d, float* dst, cudaStream_t stream) {
   const int threads = 256;
-  const int64_t blocks = std::min<int64_t>(ceil_div(n * 32, threads), 148 * 16);
+  const int64_t blocks = std::min<int64_t>(ceil_div(n * 32, threads), static_cast<int64_t>(current_sm_count()) * 16);
   normalize_rows_kernel<<<static_cast<int>(std::max<int64_t>(blocks, 1)), threads, 0, stream>>>(src, n, d, 1e-12f, dst);
   DEWI_CUDA(cudaGetLastError());
   return 0;
@@ -264,7 +264,7 @@ int join_tensor(const float* a, int64_t m, const float* b, int64_t n, int d, flo
     DEWI_TRY(tc_encode_rows_map(&mb1, b_lo, n, d, tc2_box_rows()));
   }
   // DEWI_JOIN_TIMING=1: CUDA-event time of the join kernel alone on stderr (profiling / bench_paths.py)
-  const bool timing = getenv("DEWI_JOIN_TIMING") != nullptr;
+  const bool timing = env_set("DEWI_JOIN_TIMING");
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (timing) {
     cudaEventCreate(&ev0);

@@ -77,7 +77,7 @@ int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, i
            float* dst_f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
   if (n_out <= 0) return 0;
   const int threads = 256;
-  const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), 148 * 16);
+  const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), static_cast<int64_t>(current_sm_count()) * 16);
   prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero,
                                                                     lane_order, dst_f32, hi, lo, bad_flag);
   DEWI_CUDA(cudaGetLastError());
@@ -85,6 +85,23 @@ int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, i
 }
 
 }  // namespace
+
+namespace {
+__global__ void widen_bf16_kernel(const uint16_t* __restrict__ src, long long count, float* __restrict__ dst) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    dst[i] = __uint_as_float(static_cast<uint32_t>(src[i]) << 16);
+}
+}  // namespace
+
+int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaStream_t stream) {
+  if (count <= 0) return 0;
+  const int threads = 256;
+  const int64_t blocks = std::min<int64_t>(ceil_div(count, threads), static_cast<int64_t>(current_sm_count()) * 16);
+  widen_bf16_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(reinterpret_cast<const uint16_t*>(src), count, dst);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
                        __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {

@@ -424,9 +424,10 @@ struct ScoreParams {
   double delta;
 };
 
-// exp(x) for |x| <= 700 (U is clipped to +-delta first): round-to-nearest range reduction and a degree-9 Taylor
-// polynomial, relative error 1e-11 -- a third of the float64 instructions of the library exp.  The score kernel
-// is otherwise bound by the float64 pipe, not by HBM: ~90 float64 instructions per row at 1.7e11 rows/s.
+// exp(x) for -700 <= x <= 709.78 (U is clipped to +-delta first; the caller handles the tails): round-to-nearest
+// range reduction and a degree-9 Taylor polynomial, relative error 1e-11 -- a third of the float64 instructions of
+// the library exp.  The score kernel is otherwise bound by the float64 pipe, not by HBM: ~90 float64 instructions
+// per row at 1.7e11 rows/s.  2^k is applied in two halves so that k = 1024 (x just below the overflow point) works.
 __device__ __forceinline__ double exp_small(double x) {
   const double t = fma(x, 1.4426950408889634, 6755399441055744.0);  // round(x * log2 e) in the low mantissa bits
   const int k = __double2loint(t);
@@ -443,7 +444,8 @@ __device__ __forceinline__ double exp_small(double x) {
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
-  return p * __hiloint2double((k + 1023) << 20, 0);  // * 2^k
+  const int k1 = k >> 1, k2 = k - k1;
+  return p * __hiloint2double((k1 + 1023) << 20, 0) * __hiloint2double((k2 + 1023) << 20, 0);  // * 2^k
 }
 
 // U = sum_c k_c (v_c - med_c) is scorer.py:53-57,67-73 (or :80-87) with the constant factors folded; it differs
@@ -460,8 +462,15 @@ score_kernel(const InT* __restrict__ cols, long long n, long long ld, const Scor
       const double v = static_cast<double>(__ldg(cols + static_cast<size_t>(c) * ld + i));
       U = fma(p.k[c], v - p.med[c], U);  // scorer.py:31 `(val - med) / (1.4826 * mad)`, weighted
     }
-    U = fmin(fmax(U, -p.delta), p.delta);       // scorer.py:74
-    const double e = exp_small(-U);             // scorer.py:62: 1 / (1 + exp(-U))
+    // scorer.py:74 np.clip == minimum(maximum(U, -delta), delta).  CUDA's fmin / fmax drop a NaN operand where
+    // numpy propagates it: a row with a NaN signal (or a NaN delta) must score NaN, not sigmoid(-delta).
+    const bool is_nan = (U != U) || (p.delta != p.delta);
+    U = fmin(fmax(U, -p.delta), p.delta);
+    // scorer.py:62: 1 / (1 + exp(-U)); any delta is accepted, as in the reference: exp overflows to +inf beyond
+    // 709.78 (score 0) and 1 + exp(x) == 1 below -700 (score 1)
+    const double x = -U;
+    double e = (x > 709.782712893384) ? INFINITY : ((x < -700.0) ? 0.0 : exp_small(x));
+    if (is_nan) e = nan("");
     if (sizeof(OutT) == 4) out[i] = static_cast<OutT>(__fdiv_rn(1.f, static_cast<float>(1.0 + e)));
     else out[i] = static_cast<OutT>(__ddiv_rn(1.0, 1.0 + e));
   }
@@ -496,7 +505,7 @@ void select3(const void* src, long long n_host, const unsigned int* n_dev, long 
              unsigned int* ghist, unsigned int* done, cudaStream_t stream) {
   const int threads = 512;
   const int per_thread = 8;  // (64 keys per thread on the small key buffers measured slower: 43 vs 30 us per pass)
-  int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * per_thread), std::max(1, 148 * 4 / f)));
+  int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * per_thread), std::max(1, current_sm_count() * 4 / f)));
   dim3 grid(std::max(bx, 1), f);
   for (int pass = 0; pass < 3; ++pass)
     hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist, done);
@@ -603,9 +612,8 @@ extern "C" int dewi_score(const void* cols, int in_f64, int64_t n, int64_t ld, c
     p.k[c] = wk[c] / (1.4826 * mad7[c]);
   }
   p.delta = w6[5];
-  if (!(p.delta >= 0.0) || p.delta > 700.0) return fail("delta must lie in [0, 700] (exp(delta) must be finite, as in the reference)");
   const int threads = 256;
-  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n, threads), 148 * 16));
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n, threads), static_cast<int64_t>(current_sm_count()) * 16));
   const float* c32 = static_cast<const float*>(cols);
   const double* c64 = static_cast<const double*>(cols);
   if (in_f64 && out_f64)

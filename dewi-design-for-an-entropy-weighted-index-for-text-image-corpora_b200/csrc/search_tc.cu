@@ -341,7 +341,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   int stages = 0;
   // Single query block of at most 64 queries: keep all its k-blocks resident if the corpus ring still gets 3 stages.
   bool q_res = n_qb == 1 && q_rows == 64 && mode != 2;
-  if (const char* env = getenv("DEWI_TC_QRES")) q_res = q_res && atoi(env) != 0;  // experiments
+  q_res = q_res && env_int("DEWI_TC_QRES", 1) != 0;  // experiments
   if (q_res) {
     const size_t used = fixed + static_cast<size_t>(dim / kKBlock) * q_stage_bytes(mode, q_rows);
     const int st = used < smem_max ? static_cast<int>((smem_max - used) / e_stage_bytes(mode, n_tile)) : 0;
@@ -360,7 +360,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
   }
   if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
   stages = std::min(stages, kMaxStages);
-  if (const char* env = getenv("DEWI_TC_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));  // experiments
+  if (env_set("DEWI_TC_STAGES")) stages = std::min(stages, std::max(2, env_int("DEWI_TC_STAGES", stages)));  // experiments
   const int64_t n_tiles = ceil_div(n_rows, n_tile);
   // Work items = chunks x query blocks, dealt round-robin to `grid` persistent CTAs.  Choose the
   // number of chunks so the item count is a multiple of the grid (equal work per CTA).

@@ -390,7 +390,7 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   const size_t smem_max = 227 * 1024;
   const size_t fixed = fixed_bytes(kc) + (a_resident ? a_resident_bytes(mode, dim) : 0);
   int stages = fixed < smem_max ? static_cast<int>((smem_max - fixed) / stage_bytes(mode, a_resident != 0)) : 0;
-  if (const char* env = getenv("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, atoi(env)));
+  if (env_set("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, env_int("DEWI_TC2_STAGES", stages)));
   if (stages < 2) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
   stages = std::min(stages, kMaxStages);
   // tiles one query-block pair meets: the whole corpus, or the circulant half of a symmetric self-join
@@ -421,15 +421,13 @@ int tc2_box_rows() { return kHalfRows; }
 // Words of the rendezvous counters tc2_launch needs for this plan (0: the sweep does not rendezvous -- a single
 // query pair, or items too short to drift apart).
 static int sync_every() {
-  if (const char* env = getenv("DEWI_TC2_SYNC_EVERY")) return std::max(1, atoi(env));  // experiments
+  if (env_set("DEWI_TC2_SYNC_EVERY")) return std::max(1, env_int("DEWI_TC2_SYNC_EVERY", kSyncEvery));  // experiments
   return kSyncEvery;
 }
 
 int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb) {
   if (n_qb < 4) return 0;
-  if (const char* env = getenv("DEWI_TC2_SYNC")) {
-    if (atoi(env) == 0) return 0;  // experiments
-  }
+  if (env_int("DEWI_TC2_SYNC", 1) == 0) return 0;  // experiments
   const int64_t n_tiles = ceil_div(n_rows, kNTile);
   const int64_t per_item = ceil_div(n_tiles, plan.n_chunks);
   if (per_item < 4 * sync_every()) return 0;
@@ -510,17 +508,17 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
       sym_chunks = static_cast<int>(c);
       if (static_cast<double>(items) >= 0.98 * static_cast<double>(rounds * clusters)) break;
     }
-    if (const char* env = getenv("DEWI_JOIN_CHUNKS")) sym_chunks = std::max(1, atoi(env));  // experiments
+    if (env_set("DEWI_JOIN_CHUNKS")) sym_chunks = std::max(1, env_int("DEWI_JOIN_CHUNKS", sym_chunks));  // experiments
   }
   // row block resident in shared memory when it fits next to a ring of at least 4 stages
   bool a_res = fixed_bytes(0) + a_resident_bytes(mode, dim) + 4 * stage_bytes(mode, true) <= 227 * 1024;
-  if (const char* env = getenv("DEWI_JOIN_ARES")) a_res = a_res && atoi(env) != 0;  // experiments
+  a_res = a_res && env_int("DEWI_JOIN_ARES", 1) != 0;  // experiments
   DEWI_TRY(tc2_make_plan(mode, dim, n_rows, n_qb, /*kc=*/0, sm_count, &plan, sym_chunks, sym ? all_tiles / 2 + 1 : 0, a_res ? 1 : 0));
   Tc2Args a;
   a.sym = sym ? 1 : 0;
   a.blk0 = sym ? static_cast<int>(a_offset / kNTile) : 0;
   a.rotate = 1;
-  if (const char* env = getenv("DEWI_JOIN_ROTATE")) a.rotate = atoi(env) != 0;  // experiments
+  a.rotate = env_int("DEWI_JOIN_ROTATE", 1) != 0;  // experiments
   a.sync_cnt = nullptr;
   a.sync_blocks = 0;
   a.n_rows = static_cast<int>(n_rows);

@@ -296,22 +296,46 @@ __device__ __forceinline__ T shard_at(const T* base, int c, int b, int kcand, lo
   return __ldcg(reinterpret_cast<const T*>(p) + static_cast<size_t>(b) * kcand + j);
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, const float* __restrict__ dewi,
               const float* __restrict__ ent, int n_shards, int kcand, long long shard_stride, int cand_count, int k,
               float w_sim, float w_dewi, float pref, int use_pref, long long* __restrict__ out_id,
-              float* __restrict__ out_score, const unsigned int* ready_flags, unsigned int seq) {
+              float* __restrict__ out_score, const unsigned int* ready_flags, unsigned int seq,
+              unsigned int* status, unsigned long long timeout_ns) {
   extern __shared__ unsigned long long sh[];
   if (ready_flags) {
     // fused exchange: every rank's block must have landed in this buffer (flags are released by the peers'
-    // finalize kernels).  Bounded spin: a dead peer must not hang the GPU forever.
+    // finalize kernels).  The wait is bounded in WALL time (%globaltimer, independent of the SM clock): host-side
+    // skew between ranks (GC, logging, a debugger) is unbounded in principle, and a peer may be dead.  A block
+    // that gives up does NOT trap -- that would poison the context and lose the resident corpus -- it reports
+    // `*status = seq` (host-visible memory) and returns ids of -1 for its query; the host raises on its next call.
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
     if (threadIdx.x < n_shards) {
-      const long long t0 = clock64();
+      const unsigned long long t0 = globaltimer_ns();
       while (static_cast<int>(ld_acquire_sys(ready_flags + threadIdx.x) - seq) < 0) {
-        if (clock64() - t0 > (60ll << 30)) __trap();  // ~30 s
+        if (globaltimer_ns() - t0 > timeout_ns) { timed_out = 1; break; }
       }
     }
     __syncthreads();
+    if (timed_out) {
+      for (int t = threadIdx.x; t < k; t += blockDim.x) {
+        out_id[static_cast<size_t>(blockIdx.x) * k + t] = -1;
+        out_score[static_cast<size_t>(blockIdx.x) * k + t] = -INFINITY;
+      }
+      if (threadIdx.x == 0 && status) {
+        *reinterpret_cast<volatile unsigned int*>(status) = seq;
+        __threadfence_system();
+      }
+      return;
+    }
   }
   const int ncand = n_shards * kcand;
   const int p = next_pow2(ncand);
@@ -414,7 +438,8 @@ int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int
 
 int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
                   int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
-                  int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags, unsigned int seq) {
+                  int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags, unsigned int seq,
+                  unsigned int* status, double timeout_s) {
   const int p = next_pow2(n_shards * kcand);
   if (ready_flags && n_shards > kSelThreads) return fail("too many shards for the fused exchange");
   if (p > 8192) return fail("too many gathered candidates per query");
@@ -424,7 +449,8 @@ int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const 
     DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kern<<<B, kSelThreads, smem, stream>>>(sim, reinterpret_cast<const long long*>(id), dewi, ent, n_shards, kcand,
                                          shard_stride_bytes, cand_count, k, w_sim, w_dewi, pref, use_pref,
-                                         reinterpret_cast<long long*>(out_id), out_score, ready_flags, seq);
+                                         reinterpret_cast<long long*>(out_id), out_score, ready_flags, seq, status,
+                                         static_cast<unsigned long long>(std::max(timeout_s, 1e-3) * 1e9));
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

@@ -13,14 +13,24 @@ The corpus is partitioned into contiguous row ranges: ran
 The global top-2k by similarity is a subset of the union of the local top-2k lists, so the result is
 exactly the single-index result (`ExactIndex.search`, backends.py:414-481) -- not an approximation.
 
-`local_search` / `rerank` can be injected: the CPU (gloo) tests of the exchange logic plug the
-oracle in there; the product default is the CUDA path and there is no CPU fallback.
+The two CUDA stages are the overridable methods `_local_stage` / `_rerank_stage` (and `_make_local` for
+the shard object): the CPU (gloo) tests of the exchange logic subclass the index and put the oracle
+there.  The class itself has no such switch: the product path is the CUDA path, without a CPU fallback.
+
+Fused exchange and rank skew.  With `exchange="push"` (the default when symmetric memory is available)
+there is no collective on the search path: a rank's re-rank kernel waits, on the device, for its peers'
+candidate blocks.  That wait is bounded in wall time (`push_timeout_s`, default 120 s, or
+DEWI_PUSH_TIMEOUT_S): host-side skew between ranks (GC pauses, logging, a debugger, a first-time
+rendezvous) is expected to stay far below it.  A rank that does time out does not lose its CUDA context --
+the kernel reports through a host-mapped status word and returns ids of -1 for that batch; the next call
+on that rank raises `RuntimeError`.  Applications that cannot bound their skew should use `exchange="nccl"`,
+which simply blocks.
 """
 
 from __future__ import annotations
 
 import ctypes
-from typing import Callable, Optional, Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 
@@ -131,11 +141,10 @@ class ShardedDewiIndex:
     (collective) and then `search_batch()` (collective) with the same replicated query batch."""
 
     def __init__(self, dim: int, space: str = "cosine", dtype: str = "bf16", group=None, device: Optional[int] = None,
-                 local_index=None, local_search: Optional[Callable] = None, rerank: Optional[Callable] = None,
-                 exchange: str = "auto", **kwargs):
+                 exchange: str = "auto", push_timeout_s: float = 0.0, **kwargs):
         """exchange: "push" = fused peer-store exchange over NVLink (symmetric memory, no collective on the search
-        path), "nccl" = one `all_gather_into_tensor` per batch, "auto" = push when it can be set up, else nccl."""
-        torch = _torch()
+        path), "nccl" = one `all_gather_into_tensor` per batch, "auto" = push when it can be set up, else nccl.
+        push_timeout_s: wall-time bound of the device-side wait for the peers' blocks (0: DEWI_PUSH_TIMEOUT_S or 120)."""
         import torch.distributed as dist
 
         self.dim = dim
@@ -144,15 +153,10 @@ class ShardedDewiIndex:
         self.dist = dist if dist.is_available() and dist.is_initialized() else None
         self.rank = self.dist.get_rank(group) if self.dist else 0
         self.world = self.dist.get_world_size(group) if self.dist else 1
-        self._local_search = local_search
-        self._rerank = rerank
-        if local_index is not None:
-            self.local = local_index
-        else:
-            if device is None:
-                device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-            self.local = CudaIndex(dim, space, dtype=dtype, device=device, **kwargs)
+        self.local = self._make_local(dim, space, dtype, device, **kwargs)
         self.device = getattr(self.local, "device", None)
+        self.push_timeout_s = float(push_timeout_s)
+        self._status = None         # pinned host word the re-rank kernel writes when its wait times out
         self.n_total = 0
         self.id_base = 0
         self._packed: Optional[PackedCandidates] = None
@@ -164,6 +168,13 @@ class ShardedDewiIndex:
         self._symm: Optional[SymmetricCandidates] = None
         self._symm_cache = {}       # (B, kcand) -> SymmetricCandidates; each buffer carries its own sequence number
         self._symm_failed = False
+
+    def _make_local(self, dim, space, dtype, device, **kwargs):
+        """This rank's shard: a `CudaIndex` (raises ImportError without a B200 -- no CPU fallback)."""
+        torch = _torch()
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        return CudaIndex(dim, space, dtype=dtype, device=device, **kwargs)
 
     # ---- ingest / build --------------------------------------------------------------------------
     def add_local(self, embeddings, payload_columns=None, normalized: bool = False) -> None:
@@ -203,11 +214,13 @@ class ShardedDewiIndex:
         return self.n_total
 
     # ---- search ----------------------------------------------------------------------------------
-    def _default_local_search(self, queries, kcand, out):
+    def _local_stage(self, queries, kcand, out):
+        """Stage 1 + 2 on this shard: writes the packed block views `(ids, sim, dewi, ent)` in `out`."""
         ids, sim, dewi, ent = out
         self.local.search_local_into(queries, kcand, sim, ids, dewi, ent)
 
-    def _default_rerank(self, packed: PackedCandidates, cand_count, k, eta, pref, out_ids, out_scores):
+    def _rerank_stage(self, packed: PackedCandidates, cand_count, k, eta, pref, out_ids, out_scores):
+        """Stage 3 over the gathered blocks (`dewi_rerank`, shard-strided, in place)."""
         torch = _torch()
         ids, sim, dewi, ent = packed.views(packed.gathered)
         lib = _native.load_library()
@@ -219,17 +232,22 @@ class ShardedDewiIndex:
                                  self.device, _native.stream_ptr())
         _native.check(rc)
 
-    def search_batch(self, queries, k: int = 10, eta: float = 0.5, entropy_pref: float = 0.0):
+    def search_batch(self, queries, k: int = 10, eta: float = 0.5, entropy_pref: float = 0.0,
+                     exchange: Optional[str] = None):
         """Collective.  `queries`: `[B, dim]` float32 tensor on this rank's device, identical on all
-        ranks.  Returns `(global_row_ids [B, k] int64, scores [B, k] float32)` on every rank."""
+        ranks.  Returns `(global_row_ids [B, k] int64, scores [B, k] float32)` on every rank.
+        `exchange` overrides the constructor's choice for this call (every rank must pass the same value)."""
         torch = _torch()
         if not self._built:
             self.build()
         if k > self.n_total:
             raise ValueError(f"k={k} exceeds the number of indexed rows ({self.n_total})")  # backends.py:468
+        if exchange not in (None, "auto", "push", "nccl"):
+            raise ValueError("exchange must be 'auto', 'push' or 'nccl'")
         b = queries.shape[0]
         kcand = min(2 * k, self.n_total)  # backends.py:440
-        if self._push_ready(b, kcand, queries):
+        self._check_status()
+        if self._push_ready(b, kcand, queries, exchange or self._exchange_want):
             return self._search_batch_push(queries, b, kcand, k, eta, entropy_pref)
         self.exchange = "nccl"
         pk = self._packed
@@ -237,7 +255,7 @@ class ShardedDewiIndex:
             pk = self._packed = PackedCandidates(b, kcand, queries.device, self.world)
         ids, sim, dewi, ent = pk.views(pk.local)
         if len(self.local) > 0:
-            (self._local_search or self._default_local_search)(queries, kcand, (ids, sim, dewi, ent))
+            self._local_stage(queries, kcand, (ids, sim, dewi, ent))
         else:  # an empty shard contributes only empty slots
             ids.fill_(-1)
             sim.fill_(float("-inf"))
@@ -245,17 +263,27 @@ class ShardedDewiIndex:
             self.dist.all_gather_into_tensor(pk.gathered, pk.local, group=self.group)
         out_ids = torch.empty((b, k), dtype=torch.int64, device=queries.device)
         out_scores = torch.empty((b, k), dtype=torch.float32, device=queries.device)
-        (self._rerank or self._default_rerank)(pk, kcand, k, eta, entropy_pref, out_ids, out_scores)
+        self._rerank_stage(pk, kcand, k, eta, entropy_pref, out_ids, out_scores)
         return out_ids, out_scores
 
+    def _check_status(self) -> None:
+        """Raise if an earlier fused search on this rank gave up waiting for a peer (its results were ids of -1)."""
+        if self._status is not None and int(self._status[0]) != 0:
+            seq = int(self._status[0])
+            self._status[0] = 0
+            raise RuntimeError(f"fused exchange: search #{seq} on rank {self.rank} timed out waiting for a peer's candidate "
+                               f"block (skew above push_timeout_s, or a dead peer); its results were invalidated")
+
     # ---- fused exchange (peer stores over NVLink instead of an all-gather) ---------------------------
-    def _push_ready(self, b: int, kcand: int, queries) -> bool:
+    def _push_ready(self, b: int, kcand: int, queries, want: str) -> bool:
         """Collective decision (identical on every rank: it depends only on replicated state and on whether the
         symmetric allocation succeeded everywhere)."""
         torch = _torch()
-        if (self._exchange_want == "nccl" or self._symm_failed or not self.dist or self.world <= 1
-                or self._local_search is not None or self._rerank is not None or not queries.is_cuda
+        if (want == "nccl" or self._symm_failed or not self.dist or self.world <= 1 or not queries.is_cuda
                 or self.world > 16 or getattr(self, "_min_shard", 0) <= 0):
+            if want == "push" and self.world > 1 and queries.is_cuda:
+                raise RuntimeError("fused exchange requested but unavailable (symmetric memory failed, an empty shard, "
+                                   "or more than 16 ranks)")
             return False
         sy = self._symm_cache.get((b, kcand))
         if sy is not None:   # the cache evolves identically on every rank (replicated query shapes)
@@ -271,7 +299,7 @@ class ShardedDewiIndex:
         if int(flag.item()) == 0:
             self._symm_failed = True
             self._symm = None
-            if self._exchange_want == "push":
+            if want == "push":
                 raise RuntimeError(f"fused exchange requested but symmetric memory could not be set up: {err if not ok else 'on a peer'}")
             return False
         if len(self._symm_cache) >= 16:   # drop the oldest shape (same order on every rank)
@@ -291,6 +319,9 @@ class ShardedDewiIndex:
         out_ids = torch.empty((b, k), dtype=torch.int64, device=queries.device)
         out_scores = torch.empty((b, k), dtype=torch.float32, device=queries.device)
         ids, sim, dewi, ent, flags = sy.local_views(seq)
+        if self._status is None:
+            # pinned (host-mapped) word: the kernel can report a timed-out wait without a device->host copy
+            self._status = torch.zeros(1, dtype=torch.int32).pin_memory()
         with torch.cuda.device(self.device):
             rc = lib.dewi_index_search_local_push(self.local._h, ctypes.c_void_p(q.data_ptr()), b, kcand, self.local._flags,
                                                   self.world, self.rank, bases, flag_tabs, sy.stride_bytes, seq,
@@ -300,7 +331,8 @@ class ShardedDewiIndex:
                                           ctypes.c_void_p(dewi.data_ptr()), ctypes.c_void_p(ent.data_ptr()), b, self.world, kcand,
                                           sy.stride_bytes, int(kcand), int(k), float(eta), float(entropy_pref),
                                           ctypes.c_void_p(out_ids.data_ptr()), ctypes.c_void_p(out_scores.data_ptr()),
-                                          ctypes.c_void_p(flags.data_ptr()), seq, self.device, _native.stream_ptr())
+                                          ctypes.c_void_p(flags.data_ptr()), seq, ctypes.c_void_p(self._status.data_ptr()),
+                                          self.push_timeout_s, self.device, _native.stream_ptr())
         _native.check(rc)
         self.exchange = "push"
         return out_ids, out_scores

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DEWI_B200_ABI_VERSION 1
+#define DEWI_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DEWI_API __attribute__((visibility("default")))
@@ -81,6 +81,18 @@ DEWI_API int dewi_index_set_payload(dewi_index_t* h, const float* dewi, const fl
 DEWI_API int dewi_index_size(const dewi_index_t* h, int64_t* rows);
 /* Copy the stored (normalised) row back as fp32 -- DewiIndex.get_embedding (index.py:101-116). */
 DEWI_API int dewi_index_get_row(dewi_index_t* h, int64_t row, float* out_host);
+/* Bulk form: rows [row0, row0 + n) as fp32 [n, dim] into `out` (host memory when dst_is_host, else device) --
+ * what ExactIndex.save writes as embeddings.npy (backends.py:483-515) and `_embeddings` exposes.  bf16-storage
+ * rows are widened on the device (exactly) and copied in >= 64 MB chunks; never one transfer per row.        */
+DEWI_API int dewi_index_export_rows(dewi_index_t* h, int64_t row0, int64_t n, float* out, int dst_is_host, void* stream);
+/* bf16-storage index only: the stored rows as raw bf16 bit patterns [n, dim] (2 B / element) -- the sharded
+ * sidecar CudaIndex.save writes next to the ExactIndex directory -- and the matching ingest, which appends rows
+ * that are ALREADY normalised and bf16-rounded without touching them.                                        */
+DEWI_API int dewi_index_export_bf16(dewi_index_t* h, int64_t row0, int64_t n, uint16_t* out, int dst_is_host, void* stream);
+DEWI_API int dewi_index_append_bf16(dewi_index_t* h, const uint16_t* rows, int64_t n, int src_is_host, void* stream);
+/* Read back the two payload columns of rows [offset, offset + n) (see dewi_index_set_payload). */
+DEWI_API int dewi_index_get_payload(dewi_index_t* h, int64_t offset, int64_t n, float* dewi_out, float* ent_out,
+                           int dst_is_host, void* stream);
 
 /* ---- search: replaces ExactIndex.search (backends.py:414-481) ------------------------------ */
 /* Stage 1+2 on one shard: similarity sweep (backends.py:431-436) and candidate selection
@@ -111,13 +123,17 @@ DEWI_API int dewi_rerank(const float* sim, const int64_t* id, const float* dewi,
  * dewi_rerank_gathered is dewi_rerank preceded by an acquire on `ready_flags[0..n_shards) >= seq` (this rank's
  * own flag array): no collective call and no extra launch sits between the sweep and the re-rank.  Callers
  * alternate between two buffers (seq parity) so that a rank one search ahead never overwrites a block a peer
- * is still reading; `seq` must increase by one per search on all ranks.                                   */
+ * is still reading; `seq` must increase by one per search on all ranks.
+ * The acquire is bounded in wall time (`timeout_s` seconds, <= 0: DEWI_PUSH_TIMEOUT_S or 120): a block that gives up
+ * writes ids of -1 / scores of -inf for its query and stores `seq` into `*status_word` (host-mapped or device
+ * memory, may be NULL) instead of trapping, so a slow or dead peer costs one failed search, not the CUDA context. */
 DEWI_API int dewi_index_search_local_push(dewi_index_t* h, const float* queries, int B, int kcand, int flags, int world,
                             int my_rank, const uint64_t* peer_bases, const uint64_t* peer_flags, int64_t block_stride_bytes,
                             uint32_t seq, void* stream);
 DEWI_API int dewi_rerank_gathered(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B,
                 int n_shards, int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
-                int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, int device, void* stream);
+                int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, uint32_t* status_word,
+                double timeout_s, int device, void* stream);
 /* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,

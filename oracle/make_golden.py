@@ -215,6 +215,53 @@ def saved_index_case():
     return {"case": "reference_saved_index", "n": n, "d": d}
 
 
+def quickstart_case():
+    """BASELINE.json config 1: the README quick-start (README.md:67-110) at 10K documents, driven through the
+    reference exactly as the README writes it -- add with `dewi=0.0`, `fit_stats(rows)`, per-document
+    `payload.dewi = scorer.score(signals)`, `build()`, `search(k=10, eta=0.3, entropy_pref=0.5)`.  `Signals` does
+    not exist in the reference's code (SURVEY.md section 0 item 4), so rows are the plain dicts `fit_stats` takes;
+    hnswlib is not installed, so the exact backend answers (`use_ann=False`)."""
+    rng = np.random.RandomState(101)
+    n, d, k, nq = 10_000, 768, 10, 8
+    emb = rng.rand(n, d).astype(np.float32)                      # README.md:76 `np.random.rand(768)`
+    hi = (10, 15, 5, 8, 1, 1, 0.2)                               # README.md:83-91
+    sig = np.stack([rng.uniform(0, h, n) for h in hi]).astype(np.float32)
+    queries = rng.rand(nq, d).astype(np.float32)
+    index = DewiIndex(dim=d, space="cosine", use_ann=False)
+    rows = []
+    for i in range(n):
+        signals = {key: float(sig[j, i]) for j, key in enumerate(oscorer.SIGNAL_KEYS)}
+        rows.append(signals)
+        index.add(f"doc{i}", emb[i], Payload(dewi=0.0, **signals))
+    scorer = DewiScorer(Weights())
+    scorer.fit_stats(rows)
+    for i in range(n):
+        payload = index.get_payload(f"doc{i}")
+        payload.dewi = scorer.score({key: getattr(payload, key) for key in oscorer.SIGNAL_KEYS})
+    index.build()
+    dewi = np.array([index.get_payload(f"doc{i}").dewi for i in range(n)])
+    ids = np.zeros((nq, k), dtype=np.int64)
+    scores = np.zeros((nq, k), dtype=np.float32)
+    for qi in range(nq):
+        res = index.search(queries[qi], k=k, eta=0.3, entropy_pref=0.5)
+        ids[qi] = [int(r[0][3:]) for r in res]
+        scores[qi] = [r[1] for r in res]
+    # the restatement agrees bit for bit
+    cols = {key: sig[j] for j, key in enumerate(oscorer.SIGNAL_KEYS)}
+    omed, omad = oscorer.robust_fit(cols)
+    assert np.array_equal(oscorer.score_rows(cols, omed, omad), dewi), "quickstart: scorer restatement differs"
+    stored = np.asarray(index._backend._embeddings)
+    ent = (sig[0].astype(np.float64) + sig[2].astype(np.float64)) * 0.5
+    for qi in range(nq):
+        oi, osc = osearch.exact_search(stored, dewi, ent, queries[qi], k, 0.3, 0.5, True)
+        assert np.array_equal(oi, ids[qi]) and np.array_equal(osc, scores[qi]), "quickstart: search restatement differs"
+    np.savez_compressed(GOLD / "quickstart_c1.npz", seed=np.int64(101), n=np.int64(n), d=np.int64(d), k=np.int64(k),
+                        emb_sha256=np.array(hashlib.sha256(emb.tobytes()).hexdigest()), signals=sig, queries=queries,
+                        dewi=dewi, med=np.array([omed[key] for key in oscorer.SIGNAL_KEYS]),
+                        mad=np.array([omad[key] for key in oscorer.SIGNAL_KEYS]), ref_idx=ids, ref_scores=scores)
+    return {"case": "quickstart_c1", "n": n, "d": d, "k": k, "nq": nq}
+
+
 def main() -> None:
     GOLD.mkdir(parents=True, exist_ok=True)
     grid_full = [(e, p) for e in (0.0, 0.25, 0.5, 1.0) for p in (-1.0, 0.0, 0.5, 1.0)]
@@ -234,6 +281,7 @@ def main() -> None:
     m.append(redundancy_case("t64_i64_d64", 64, 64, 64, 32))
     m.append(extras_case())
     m.append(saved_index_case())
+    m.append(quickstart_case())
     (GOLD / "MANIFEST.json").write_text(json.dumps(manifest, indent=1))
     print(json.dumps(manifest, indent=1))
 

@@ -35,7 +35,7 @@ def test_binding_table_matches_header(lib_path):
 
     assert set(native.SIGNATURES) == set(declared_symbols())
     lib = native.load_library()
-    assert lib.dewi_abi_version() == 1
+    assert lib.dewi_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_a_gpu(lib_path):

@@ -151,3 +151,70 @@ def test_nccl_sharded_self_join_matches_oracle(align):
     np.fill_diagonal(sim, -np.inf)
     arg = np.concatenate([p[4] for p in parts])
     assert np.all(sim[np.arange(n), arg] >= mx - 1e-5)
+
+
+def _timeout_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dewi_b200 import ShardedDewiIndex, shard_range
+        from _util import make_corpus
+
+        n, d, b, k = 20_000, 128, 8, 5
+        emb, pay = make_corpus(n, d, seed=5)
+        lo, hi = shard_range(n, world, rank, align=128)
+        ix = ShardedDewiIndex(d, dtype="fp32", device=rank, exchange="push", push_timeout_s=0.4)
+        ix.add_local(emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        ix.build()
+        q = torch.from_numpy(np.random.RandomState(1).standard_normal((b, d)).astype(np.float32)).cuda()
+        try:
+            good, _ = ix.search_batch(q, k=k)
+        except RuntimeError as exc:
+            if "symmetric memory" in str(exc) or "unavailable" in str(exc):
+                ret["unavailable"] = str(exc)
+                return
+            raise
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 1:
+            torch.cuda._sleep(int(3.0e9))            # ~1.5 s of device time in front of rank 1's search
+        ids, _ = ix.search_batch(q, k=k)             # rank 0 gives up after 0.4 s, without trapping
+        torch.cuda.synchronize()
+        if rank == 0:
+            ret["timed_out_ids_are_minus_one"] = bool((ids == -1).all().item())
+            try:
+                ix.search_batch(q, k=k)
+                ret["raised"] = False
+            except RuntimeError as exc:
+                ret["raised"] = "timed out" in str(exc)
+            # the context survived: the local shard still answers
+            sim, gid, _, _ = ix.local.search_local(q, 2 * k)
+            torch.cuda.synchronize()
+            ret["context_alive"] = bool((gid[:, 0] >= 0).all().item())
+        else:
+            ret["late_rank_ok"] = bool(torch.equal(ids, good))
+        torch.cuda.synchronize()
+        dist.barrier()                               # nobody unmaps its buffers while a peer may still push
+    finally:
+        dist.destroy_process_group()
+
+
+def test_push_timeout_reports_instead_of_trapping():
+    """A peer that is late by more than `push_timeout_s` costs the waiting rank ONE failed search (ids of -1, then a
+    RuntimeError on its next call) -- not a sticky CUDA error that would lose the resident corpus."""
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_timeout_worker, args=(2, port, ret), nprocs=2, join=True)
+        if "unavailable" in ret:
+            pytest.skip(f"fused exchange unavailable here: {ret['unavailable']}")
+        assert ret["timed_out_ids_are_minus_one"] and ret["raised"] and ret["context_alive"] and ret["late_rank_ok"]

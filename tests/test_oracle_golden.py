@@ -18,8 +18,8 @@ SCORER_CASES = ["readme_n1001", "readme_n1000", "profile_n4096"]
 
 def test_manifest_lists_every_fixture():
     man = json.loads((GOLD / "MANIFEST.json").read_text())
-    assert len(man["cases"]) == 14
-    assert len(list(GOLD.glob("*.npz"))) == 14
+    assert len(man["cases"]) == 15
+    assert len(list(GOLD.glob("*.npz"))) == 15
     assert (GOLD / "reference_saved_index" / "ann_index" / "embeddings.npy").exists()
 
 
@@ -89,3 +89,27 @@ def test_redundancy_oracle(name):
     mx, am, cnt, pairs = ored.join_rowstats(g["tfeat"], g["ifeat"], 0.9)
     np.testing.assert_array_equal(am, np.argmax(sim, axis=1))
     assert cnt.sum() == len(pairs) == int((sim >= np.float32(0.9)).sum()) > 0
+
+
+def test_quickstart_flow_oracle_bit_exact():
+    """BASELINE.json config 1 (README quick-start at 10K documents): fit -> score -> search restated by the oracle
+    equals what the unmodified reference produced for the fixture, bit for bit."""
+    import hashlib
+
+    g = np.load(GOLD / "quickstart_c1.npz")
+    n, d, k = int(g["n"]), int(g["d"]), int(g["k"])
+    rng = np.random.RandomState(int(g["seed"]))
+    emb = rng.rand(n, d).astype(np.float32)
+    assert hashlib.sha256(emb.tobytes()).hexdigest() == str(g["emb_sha256"])
+    sig = g["signals"]
+    cols = {key: sig[j] for j, key in enumerate(oscorer.SIGNAL_KEYS)}
+    med, mad = oscorer.robust_fit(cols)
+    assert [med[key] for key in oscorer.SIGNAL_KEYS] == g["med"].tolist()
+    assert [mad[key] for key in oscorer.SIGNAL_KEYS] == g["mad"].tolist()
+    dewi = oscorer.score_rows(cols, med, mad)
+    assert np.array_equal(dewi, g["dewi"])
+    rows = osearch.normalize_rows_like_add(emb)
+    ent = (sig[0].astype(np.float64) + sig[2].astype(np.float64)) * 0.5
+    for qi, q in enumerate(g["queries"]):
+        idx, sc = osearch.exact_search(rows, dewi, ent, q, k, 0.3, 0.5, True)
+        assert np.array_equal(idx, g["ref_idx"][qi]) and np.array_equal(sc, g["ref_scores"][qi])

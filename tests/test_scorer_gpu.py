@@ -79,3 +79,32 @@ def test_differential_fit_and_score(n, style):
     out = s.score_batch(sig, out_dtype="float64").cpu().numpy()
     np.testing.assert_allclose(out, ref, rtol=SCORE_RTOL, atol=0)
     assert out.min() >= 1 / (1 + np.exp(2.0)) - 1e-12 and out.max() <= 1 / (1 + np.exp(-2.0)) + 1e-12
+
+
+def test_nan_signals_and_extreme_deltas_follow_numpy():
+    """np.clip and the sigmoid propagate NaN (scorer.py:62,74); CUDA's fmin / fmax would not.  Any delta is accepted,
+    as in the reference: exp overflows to inf (score 0) / underflows (score 1) instead of being rejected."""
+    rng = np.random.RandomState(8)
+    pay = synth_payload_columns(rng, 4096, "readme")
+    sig = pay[:, 1:].T.astype(np.float32).copy()
+    cols = {k: sig[i] for i, k in enumerate(SIGNAL_FIELDS)}
+    med, mad = oscorer.robust_fit(cols)
+    bad = sig.copy()
+    bad[2, 7] = np.nan
+    bad[5, 100] = np.nan
+    bad[0, 200] = np.inf
+    bad[0, 201] = -np.inf
+    bcols = {k: bad[i] for i, k in enumerate(SIGNAL_FIELDS)}
+    for delta in (3.0, 705.0, 800.0, 5000.0):
+        s = dewi_b200.DewiScorer(dewi_b200.Weights(), delta=delta)
+        s.stats = dewi_b200.RobustStats(medians=dict(med), mads=dict(mad))
+        with np.errstate(over="ignore", invalid="ignore"):
+            ref = oscorer.score_rows(bcols, med, mad, (1, 1, 1, 1, 1, delta))
+        for dt in ("float64", "float32"):
+            out = s.score_batch(bad, out_dtype=dt).cpu().numpy().astype(np.float64)
+            assert np.isnan(out[7]) and np.isnan(out[100]) and np.array_equal(np.isnan(out), np.isnan(ref))
+            ok = ~np.isnan(ref)
+            want = ref[ok] if dt == "float64" else ref[ok].astype(np.float32).astype(np.float64)
+            np.testing.assert_allclose(out[ok], want, rtol=SCORE_RTOL, atol=1e-300 if dt == "float64" else 1e-45)
+    w = dewi_b200.local_weights_from_surprisal(np.array([0.5, np.nan, 2.0, 1.0, 3.0], np.float32))
+    assert np.isnan(w[1]) and not np.isnan(w[[0, 2, 3, 4]]).any()

@@ -1,4 +1,4 @@
-"""The N>1 exchange logic on CPU: world_size-2 gloo processes, with the oracle plugged in for the two
+"""The N>1 exchange logic on CPU: world_size-2 gloo processes, with the oracle standing in (through a subclass) for the two
 CUDA stages (shard-local top-2k, blend + top-k).  Checks shard ranges, global id bases, the packed
 all-gather layout and that the sharded result equals the single-index result exactly."""
 
@@ -85,7 +85,17 @@ def _worker(rank, world, port, n, d, b, k, eta, pref, ret):
                 out_ids[q] = torch.from_numpy(ids[q, order][best])
                 out_scores[q] = torch.from_numpy(adj[best])
 
-        ix = ShardedDewiIndex(d, local_index=shard, local_search=local_search, rerank=rerank)
+        class HostSharded(ShardedDewiIndex):  # the oracle stands in for the two CUDA stages
+            def _make_local(self, *a, **kw):
+                return shard
+
+            def _local_stage(self, q, kcand, out):
+                local_search(q, kcand, out)
+
+            def _rerank_stage(self, pk, cand_count, k_, eta_, pref_, out_ids, out_scores):
+                rerank(pk, cand_count, k_, eta_, pref_, out_ids, out_scores)
+
+        ix = HostSharded(d)
         ix.build()
         assert ix.n_total == n and ix.id_base == lo and shard.base == lo
         got_ids, got_sc = ix.search_batch(torch.from_numpy(queries), k=k, eta=eta, entropy_pref=pref)
