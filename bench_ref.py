@@ -30,15 +30,22 @@ ROOT = Path(__file__).resolve().parent
 REF_DIR = ROOT / "baseline" / "_ref"
 
 
+DEFAULT_MAX_THREADS = 16
+
+
 def host_threads(requested: int = 0) -> int:
-    """Threads the CPU legs may use: the cores this process is allowed on (capped at OpenBLAS's build limit)."""
+    """Threads the CPU legs use: the cores this process is allowed on, capped at 16 unless `--cpu-threads` says
+    otherwise.  The cap keeps `cores` identical across the 1/2/4/8-GPU runs (the pool hands a job more host cores
+    with more GPUs: 16 at N = 1, 24 at N = 2) and costs the reference nothing: its hot statement is a memory-bound
+    sgemv that saturates well before 16 threads (measured on the B200 host, 10M x 768 rows: 207 ms/query with 16
+    threads, 244 ms with 24)."""
     if requested and requested > 0:
         return int(requested)
     try:
         n = len(os.sched_getaffinity(0))
     except AttributeError:
         n = os.cpu_count() or 1
-    return max(1, min(n, 64))
+    return max(1, min(n, DEFAULT_MAX_THREADS))
 
 
 def pin_env_threads(threads: int) -> None:

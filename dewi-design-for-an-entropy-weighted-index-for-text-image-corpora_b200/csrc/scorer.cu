@@ -7,7 +7,11 @@
 //   block-private shared-memory histograms flushed with one atomic per non-empty bin, the last block
 //   of a pass picks the bins.  Large columns select inside a key window found from a sample, so each
 //   statistic reads the column once (window_kernel).  All columns and both middle ranks (even n) are
-//   selected in the same passes.
+//   selected in the same passes.  The windowed path is FOUR launches per statistic: the sample (with the
+//   first histogram pass fused in), one more histogram pass over the sample (-> window bounds), the window
+//   pass (with the histogram of the window-relative top digit and the pick of the two target bins fused in),
+//   and a survivor pass that gathers the few hundred keys of those bins and sorts them in shared memory
+//   (-> the exact middle values, and the state of the next statistic armed).
 // K4 score: RobustStats.z + DewiScorer._components/score/score_conditional (scorer.py:28-31,49-89)
 //   in float64: U as a weighted sum of (v - med) with the z-score scales folded into the weights, clip, sigmoid with a
 //   polynomial exp -- within ~1e-11 of the reference's Python-float arithmetic (gate 1e-6); 7 fp32 loads and one store per row.
@@ -30,6 +34,7 @@ constexpr int kSampleRuns = 1024;                // evenly spaced runs of ...
 constexpr int kSampleRunLen = 1024;              // ... contiguous elements (coalesced)
 constexpr int kSample = kSampleRuns * kSampleRunLen;
 constexpr int kSampleMargin = 4096;              // +- sample ranks: 8 sigma of a 2^20 sample's median rank
+constexpr int kSurvCap = 8192;                   // keys of the target bins sorted in shared memory (typically a few hundred)
 
 struct SelState {
   // radix selection, per column, two rank slots
@@ -43,6 +48,14 @@ struct SelState {
   unsigned long long below[kMaxCols];       // keys < lo
   unsigned int wcnt[kMaxCols];              // keys appended to the window buffer
   int miss[kMaxCols];                       // window overflowed or does not hold the target ranks
+  // in-window selection: digit = (key - lo) >> wshift is the top <= 11 bits of the window's key span
+  int wshift[kMaxCols];
+  unsigned int wbin[kMaxCols][2];           // digits of the two middle ranks
+  unsigned long long wrank[kMaxCols][2];    // their ranks inside those bins
+  unsigned int tiles_done[kMaxCols];        // window_kernel: tiles of the column finished (self-resetting)
+  unsigned int surv_n[kMaxCols];            // survivor_kernel: keys gathered from the target bins
+  unsigned int surv_n0[kMaxCols];           //   ... of which in bin 0, when the two bins differ
+  unsigned int surv_done[kMaxCols];         // survivor_kernel: block tickets (self-resetting)
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -74,13 +87,37 @@ __device__ __forceinline__ unsigned int load_key(const void* col, long long i, f
 __device__ void pick_column(int pass, int c, SelState* st, unsigned int* ghist, unsigned long long* cum,
                             unsigned long long* wsum);
 
+// What the last block of a selection pass does after it has picked its bins.
+enum { OP_NONE = 0, OP_WINDOW_BOUNDS = 1 };
+
+// The sample selection resolved the top 22 bits (passes 0 and 1) of the keys at sample ranks s/2 -+ margin: rounding
+// the first down and the second up to a multiple of 1024 keeps the window conservative (a third pass would buy
+// < 0.01 % fewer window keys for one more launch).  Also sizes the window-relative digit of the in-window selection.
+__device__ __forceinline__ void arm_window(SelState* st, int c) {
+  const unsigned int lo = st->prefix[c][0] & 0xFFFFFC00u, hi = st->prefix[c][1] | 0x3FFu;
+  st->lo[c] = lo;
+  st->hi[c] = hi;
+  st->below[c] = 0ull;
+  st->wcnt[c] = 0u;
+  const int nbits = 32 - __clz(static_cast<int>(hi - lo));   // hi - lo >= 0x3FF
+  st->wshift[c] = max(nbits - 11, 0);
+}
+
+// State of a fresh sample selection: ranks s/2 -+ margin of the kSample sample keys.
+__device__ __forceinline__ void arm_sample(SelState* st, int c) {
+  st->prefix[c][0] = st->prefix[c][1] = 0u;
+  st->rank[c][0] = kSample / 2 - kSampleMargin;
+  st->rank[c][1] = kSample / 2 + kSampleMargin;
+  st->same[c] = 1;
+}
+
 // Histogram of the current digit over the keys whose higher digits match a slot's prefix: block-private
 // shared-memory histograms (per-thread run-length combining in front of the shared atomics), one global
 // atomic per non-empty bin at the end; the last block of a column then picks the bins (pick_column).
 template <int SRC>
 __global__ void __launch_bounds__(512)
 hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* __restrict__ n_dev, long long ld, int pass,
-            SelState* st, unsigned int* __restrict__ ghist, unsigned int* __restrict__ done) {
+            SelState* st, unsigned int* __restrict__ ghist, unsigned int* __restrict__ done, int op) {
   __shared__ __align__(8) unsigned int sh[2 * kBins];   // two slot histograms; reused as 2048 x u64 by pick_column
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned int ticket;
@@ -145,7 +182,10 @@ hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* 
   if (ticket != gridDim.x - 1) return;
   __threadfence();
   pick_column(pass, c, st, ghist, reinterpret_cast<unsigned long long*>(sh), wsum);
-  if (threadIdx.x == 0) done[c] = 0u;
+  if (threadIdx.x == 0) {
+    done[c] = 0u;
+    if (op == OP_WINDOW_BOUNDS) arm_window(st, c);
+  }
 }
 
 // Locate the bin holding each slot's rank, extend the prefix, clear the histogram.  Runs in the LAST block
@@ -241,10 +281,7 @@ __global__ void glue_kernel(int op, int f, long long n, unsigned int window_cap,
     st->rank[c][1] = r1;
     st->same[c] = 1;
   } else if (op == ARM_SAMPLE) {
-    st->prefix[c][0] = st->prefix[c][1] = 0u;
-    st->rank[c][0] = kSample / 2 - kSampleMargin;
-    st->rank[c][1] = kSample / 2 + kSampleMargin;
-    st->same[c] = 1;
+    arm_sample(st, c);
   } else if (op == ARM_WINDOW) {
     st->lo[c] = st->prefix[c][0];
     st->hi[c] = st->prefix[c][1];
@@ -267,19 +304,54 @@ __global__ void glue_kernel(int op, int f, long long n, unsigned int window_cap,
   }
 }
 
-// Keys of kSampleRuns evenly spaced runs of kSampleRunLen contiguous elements -> skeys[c][kSample].
+// Keys of kSampleRuns evenly spaced runs of kSampleRunLen contiguous elements -> skeys[c][kSample], with the FIRST
+// selection pass over the sample fused in: the block histograms the top 11 key bits of what it gathers, and the last
+// block of a column picks the bins of the two sample ranks (the state must be armed: arm_sample).
 template <int SRC>
 __global__ void __launch_bounds__(256)
-sample_kernel(const float* __restrict__ cols, long long n, long long ld, const SelState* __restrict__ st,
-              unsigned int* __restrict__ skeys) {
+sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelState* st, unsigned int* __restrict__ skeys,
+              unsigned int* __restrict__ ghist, unsigned int* __restrict__ done) {
+  __shared__ __align__(8) unsigned int sh[2 * kBins];   // slot-0 histogram; reused as 2048 x u64 by pick_column
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned int ticket;
   const int c = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
   const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
   const float* col = cols + static_cast<size_t>(c) * ld;
+  unsigned int run_bin = 0xFFFFFFFFu, run_cnt = 0u;
   for (int run = blockIdx.x; run < kSampleRuns; run += gridDim.x) {
     const long long start = static_cast<long long>((static_cast<__int128>(run) * (n - kSampleRunLen)) / (kSampleRuns - 1));
-    for (int j = threadIdx.x; j < kSampleRunLen; j += blockDim.x)
-      skeys[static_cast<size_t>(c) * kSample + run * kSampleRunLen + j] = load_key<SRC>(col, start + j, med);
+    unsigned int key[kSampleRunLen / 256];
+#pragma unroll
+    for (int u = 0; u < kSampleRunLen / 256; ++u) key[u] = load_key<SRC>(col, start + u * 256 + threadIdx.x, med);
+#pragma unroll
+    for (int u = 0; u < kSampleRunLen / 256; ++u) {
+      skeys[static_cast<size_t>(c) * kSample + run * kSampleRunLen + u * 256 + threadIdx.x] = key[u];
+      const unsigned int bin = key[u] >> 21;   // pass 0: bits 31..21
+      if (bin != run_bin) {
+        if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
+        run_bin = bin;
+        run_cnt = 0u;
+      }
+      ++run_cnt;
+    }
   }
+  if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
+  __syncthreads();
+  unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    const unsigned int v = sh[i];
+    if (v) atomicAdd(&g[i], v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&done[c], 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  pick_column(0, c, st, ghist, reinterpret_cast<unsigned long long*>(sh), wsum);
+  if (threadIdx.x == 0) done[c] = 0u;
 }
 
 // THE full pass of the windowed path: count keys below the window, collect the keys inside it.
@@ -303,14 +375,97 @@ constexpr int kWinTile = kWinThreads * kWinPerThread;
 constexpr int kFlushCheckEvery = 8;   // tiles between two looks at the buffer fill (8 tiles add ~260 keys)
 constexpr int kWinBlocksPerSm = 8;
 
+// Inclusive prefix sums of g[0 .. kBins) into cum[] for the whole block (blockDim.x divides kBins, at most 8 bins
+// per thread); `wsum` is 32 words of scratch.
+__device__ void scan_bins(const unsigned int* g, unsigned long long* cum, unsigned long long* wsum) {
+  const int T = blockDim.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int per = kBins / T;
+  unsigned long long mine[8];
+  unsigned long long x = 0ull;
+  for (int i = 0; i < per; ++i) {
+    mine[i] = __ldcg(g + t * per + i);
+    x += mine[i];
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[w] = x;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long y = (lane < T / 32) ? wsum[lane] : 0ull;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long z = __shfl_up_sync(0xffffffffu, y, o);
+      if (lane >= o) y += z;
+    }
+    wsum[lane] = y;
+  }
+  __syncthreads();
+  unsigned long long run = ((w > 0) ? wsum[w - 1] : 0ull) + x;
+  for (int i = per - 1; i >= 0; --i) {
+    cum[t * per + i] = run;
+    run -= mine[i];
+  }
+  __syncthreads();
+}
+
+// Window-relative digit of a key the float predicates admitted: (key - lo) clamped into [0, hi - lo] (float order
+// and key order disagree on -0 / +0 only), top <= 11 bits.
+__device__ __forceinline__ unsigned int window_digit(unsigned int key, unsigned int lo, unsigned int span, int wshift) {
+  const unsigned int rel = key >= lo ? min(key - lo, span) : 0u;
+  return rel >> wshift;
+}
+
+// The block that completes a column of window_kernel (all its tiles accounted for) turns the column's counts into
+// the two target bins of the in-window selection: ranks (middle - below) inside the collected keys, located in the
+// histogram of the window-relative digit.  A window that overflowed or does not hold the ranks is flagged (miss).
+// Kept out of line: it runs once per column and must not cost the streaming loop registers.
+// `shm`: the block's kWinBuf + kBins words (free at this point), reused as 2048 x u64 prefix sums.
+__device__ __noinline__ void window_pick(int c, long long n, unsigned int window_cap, SelState* st, unsigned int* g,
+                                         unsigned int* shm, unsigned long long* wsum) {
+  unsigned long long r0, r1;
+  middle_ranks(n, r0, r1);
+  const unsigned long long nbelow = __ldcg(&st->below[c]), cnt = __ldcg(&st->wcnt[c]);
+  const bool ok = cnt <= window_cap && nbelow <= r0 && r1 < nbelow + cnt;
+  if (ok) {
+    unsigned long long* cum = reinterpret_cast<unsigned long long*>(shm);
+    scan_bins(g, cum, wsum);
+    const unsigned long long rr[2] = {r0 - nbelow, r1 - nbelow};
+    for (int ss = 0; ss < 2; ++ss) {
+      for (int bin = threadIdx.x; bin < kBins; bin += blockDim.x) {
+        const unsigned long long before = bin ? cum[bin - 1] : 0ull;
+        if (rr[ss] >= before && rr[ss] < cum[bin]) {
+          st->wbin[c][ss] = static_cast<unsigned int>(bin);
+          st->wrank[c][ss] = rr[ss] - before;
+        }
+      }
+    }
+    __syncthreads();
+  } else if (threadIdx.x == 0) {
+    st->miss[c] = 1;
+  }
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) g[i] = 0u;                 // the histogram memory is reused
+  for (int i = threadIdx.x; i < kWinBuf + kBins; i += blockDim.x) shm[i] = 0u;    // (clobbered by the prefix sums)
+  if (threadIdx.x == 0) st->tiles_done[c] = 0u;
+  __syncthreads();
+}
+
 template <int SRC>
 __global__ void __launch_bounds__(kWinThreads, kWinBlocksPerSm)
 window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, SelState* st,
-              unsigned int* __restrict__ wkeys, unsigned int window_cap) {
-  __shared__ unsigned int buf[kWinBuf];
-  __shared__ unsigned int buf_n, flush_base;
+              unsigned int* __restrict__ wkeys, unsigned int window_cap, unsigned int* __restrict__ ghist) {
+  // [ buf : keys waiting for the next flush | hist : window-relative digit histogram of the current column ]; the
+  // block that finishes a column last reuses the whole array as 2048 x u64 prefix sums (window_pick)
+  __shared__ __align__(8) unsigned int shm[kWinBuf + kBins];
+  unsigned int* const buf = shm;
+  unsigned int* const hist = shm + kWinBuf;
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned int buf_n, flush_base, ticket_s;
   __shared__ unsigned long long below_blk;
   const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0u;
   const long long tiles_per_col = (n + kWinTile - 1) / kWinTile;
   const long long total_tiles = tiles_per_col * f;
   const long long t_begin = (total_tiles * blockIdx.x) / gridDim.x;
@@ -351,10 +506,30 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
       below_blk = 0ull;
     }
     below = 0u;
+    unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+      const unsigned int v = hist[i];
+      if (v) { atomicAdd(&g[i], v); hist[i] = 0u; }
+    }
+    __threadfence();
     __syncthreads();
+    // tiles of column c inside this block's range [t_begin, t_end)
+    const long long c_lo = static_cast<long long>(c) * tiles_per_col;
+    const unsigned int tiles_mine = static_cast<unsigned int>(min(t_end, c_lo + tiles_per_col) - max(t_begin, c_lo));
+    if (threadIdx.x == 0) ticket_s = atomicAdd(&st->tiles_done[c], tiles_mine);
+    __syncthreads();
+    const bool last = static_cast<long long>(ticket_s) + tiles_mine == tiles_per_col;
+    if (last) {  // block-uniform
+      __threadfence();
+      window_pick(c, n, window_cap, st, g, shm, wsum);
+    }
   };
   auto push = [&](float v) {  // v lies in the window
     const unsigned int key = orderable(v);
+    {  // (rare path: the window parameters are re-read from the cached state instead of living in registers)
+      const unsigned int lo_key = st->lo[c];
+      atomicAdd(&hist[window_digit(key, lo_key, st->hi[c] - lo_key, st->wshift[c])], 1u);
+    }
     const unsigned int slot = atomicAdd(&buf_n, 1u);
     if (slot < kWinBuf) buf[slot] = key;
     else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
@@ -416,6 +591,78 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
     if (++since_check == kFlushCheckEvery) flush(kWinBuf / 2);
   }
   if (c >= 0) commit_column();
+}
+
+// In-window selection, second half.  window_kernel left, per column, the digits (bins) of the two middle ranks and
+// their ranks inside those bins; a bin of the window-relative top digit holds ~1/2048 of the window's keys -- a
+// few hundred.  This pass re-reads the window keys (L2-resident), gathers the keys of the target bins, and the
+// last block of a column sorts them in shared memory and reads off the two middle values: the median (then the
+// sample selection of the MAD is armed) or the MAD.  More than kSurvCap survivors (a large tie group inside the
+// bin) flags the column `miss` and the caller falls back to the plain radix passes.
+constexpr int kSurvThreads = 512;
+
+__global__ void __launch_bounds__(kSurvThreads)
+survivor_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap, long long n, SelState* st,
+                unsigned int* __restrict__ surv, int final_op) {
+  __shared__ unsigned int keys[kSurvCap];
+  __shared__ unsigned int ticket;
+  const int c = blockIdx.y;
+  if (st->miss[c]) return;   // (uniform over the column's blocks: set by an earlier kernel)
+  const unsigned int lo = st->lo[c], span = st->hi[c] - lo;
+  const int wshift = st->wshift[c];
+  const unsigned int b0 = st->wbin[c][0], b1 = st->wbin[c][1];
+  const unsigned int cnt = min(st->wcnt[c], window_cap);
+  const unsigned int* src = wkeys + static_cast<size_t>(c) * window_cap;
+  unsigned int* dst = surv + static_cast<size_t>(c) * kSurvCap;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+    const unsigned int key = __ldg(src + i);
+    const unsigned int d = window_digit(key, lo, span, wshift);
+    if (d == b0 || d == b1) {
+      const unsigned int slot = atomicAdd(&st->surv_n[c], 1u);
+      if (slot < kSurvCap) dst[slot] = key;
+      if (d == b0 && b0 != b1) atomicAdd(&st->surv_n0[c], 1u);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(&st->surv_done[c], 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  const unsigned int m = __ldcg(&st->surv_n[c]), m0 = __ldcg(&st->surv_n0[c]);
+  const unsigned long long i0 = st->wrank[c][0];
+  const unsigned long long i1 = (b0 == b1) ? st->wrank[c][1] : static_cast<unsigned long long>(m0) + st->wrank[c][1];
+  if (m > kSurvCap || i0 >= m || i1 >= m) {
+    if (threadIdx.x == 0) st->miss[c] = 1;
+  } else {
+    int p = 1;
+    while (p < static_cast<int>(m)) p <<= 1;
+    for (int t = threadIdx.x; t < p; t += blockDim.x) keys[t] = t < static_cast<int>(m) ? __ldcg(dst + t) : 0xFFFFFFFFu;
+    for (int size = 2; size <= p; size <<= 1) {       // ascending bitonic sort
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < (p >> 1); t += blockDim.x) {
+          const int a = 2 * t - (t & (stride - 1)), b = a + stride;
+          const bool asc = (a & size) == 0;
+          const unsigned int ka = keys[a], kb = keys[b];
+          if ((ka > kb) == asc) { keys[a] = kb; keys[b] = ka; }
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float v0 = from_orderable(keys[i0]), v1 = from_orderable(keys[i1]);
+      // np.median: mean of the middle element(s) in float32 -> (v0 + v1) / 2, or v0 when n is odd
+      const float mid = (n & 1) ? v0 : __fmul_rn(__fadd_rn(v0, v1), 0.5f);
+      if (final_op == FINAL_MED) {
+        st->med[c] = mid;
+        arm_sample(st, c);   // the MAD's sample selection follows
+      } else {
+        st->mad[c] = mid;
+      }
+    }
+  }
+  if (threadIdx.x == 0) st->surv_n[c] = st->surv_n0[c] = st->surv_done[c] = 0u;
 }
 
 struct ScoreParams {
@@ -483,8 +730,9 @@ struct FitWork {
   unsigned int* ghist = nullptr;
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
-  unsigned int* done = nullptr;   // per-column block tickets of hist_kernel (self-resetting)
-  size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0;
+  unsigned int* surv = nullptr;   // [columns][kSurvCap] keys of the target bins
+  unsigned int* done = nullptr;   // per-column block tickets of hist_kernel / sample_kernel (self-resetting)
+  size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0, surv_bytes = 0;
   int sm_count = 148;
 };
 std::mutex g_fit_mu;
@@ -508,7 +756,7 @@ void select3(const void* src, long long n_host, const unsigned int* n_dev, long 
   int bx = static_cast<int>(std::min<int64_t>(ceil_div(n_host, threads * per_thread), std::max(1, current_sm_count() * 4 / f)));
   dim3 grid(std::max(bx, 1), f);
   for (int pass = 0; pass < 3; ++pass)
-    hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist, done);
+    hist_kernel<SRC><<<grid, threads, 0, stream>>>(src, n_host, n_dev, ld, pass, st, ghist, done, OP_NONE);
 }
 
 // Exact radix selection over the whole column: 3 full passes per statistic.
@@ -523,17 +771,25 @@ void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, c
 
 // One full pass per statistic: window bounds from a sample, keys inside the window collected, the
 // middle ranks selected among them.  st->miss[c] reports a window that did not hold the ranks.
+// Four launches (the state must be armed for a sample selection: glue ARM_SAMPLE, or the previous statistic's
+// survivor pass):
+//   sample_kernel    gathers the sample keys, histograms their top 11 bits, picks the bins of ranks s/2 -+ margin
+//   hist_kernel      pass 1 over the sample keys (next 11 bits)  ->  window bounds [lo, hi]   (OP_WINDOW_BOUNDS)
+//   window_kernel    THE pass over the column: counts keys below the window, collects the keys inside it, histograms
+//                    their window-relative top digit; the block finishing a column picks the two target bins
+//   survivor_kernel  gathers the keys of those bins, sorts them in shared memory  ->  med / mad
 template <int SRC>
 void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsigned int cap, FitWork& w, int final_op,
                        cudaStream_t stream) {
-  sample_kernel<SRC><<<dim3(512, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys);
-  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
-  select3<SRC_KEYS>(w.skeys, kSample, nullptr, kSample, f, w.st, w.ghist, w.done, stream);
-  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_WINDOW, f, n, cap, w.st);
-  window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap);
-  glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_INSIDE, f, n, cap, w.st);
-  select3<SRC_KEYS>(w.wkeys, cap, w.st->wcnt, cap, f, w.st, w.ghist, w.done, stream);
-  glue_kernel<<<1, kMaxCols, 0, stream>>>(final_op, f, n, cap, w.st);
+  sample_kernel<SRC><<<dim3(128, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done);
+  {
+    const int threads = 512, per_thread = 8;
+    const int bx = static_cast<int>(std::min<int64_t>(ceil_div(kSample, threads * per_thread), std::max(1, w.sm_count * 4 / f)));
+    hist_kernel<SRC_KEYS><<<dim3(std::max(bx, 1), f), threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, 1, w.st, w.ghist,
+                                                                             w.done, OP_WINDOW_BOUNDS);
+  }
+  window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
+  survivor_kernel<<<dim3(std::max(1, w.sm_count / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op);
 }
 
 }  // namespace
@@ -567,12 +823,14 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   if (windowed) {
     DEWI_TRY(ensure_buf(&w.skeys, &w.skeys_bytes, static_cast<size_t>(f) * kSample * 4));
     DEWI_TRY(ensure_buf(&w.wkeys, &w.wkeys_bytes, static_cast<size_t>(f) * cap * 4));
+    DEWI_TRY(ensure_buf(&w.surv, &w.surv_bytes, static_cast<size_t>(kMaxCols) * kSurvCap * 4));
   }
   DEWI_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SelState), stream));
   DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
   SelState res;
   bool need_full = !windowed;
   if (windowed) {
+    glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
     fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
     fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
     DEWI_CUDA(cudaGetLastError());
