@@ -16,6 +16,7 @@
 //   in float64: U as a weighted sum of (v - med) with the z-score scales folded into the weights, clip, sigmoid with a
 //   polynomial exp -- within ~1e-11 of the reference's Python-float arithmetic (gate 1e-6); 7 fp32 loads and one store per row.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -33,7 +34,9 @@ constexpr long long kWindowMinRows = 4ll << 20;  // below this the plain radix p
 constexpr int kSampleRuns = 1024;                // evenly spaced runs of ...
 constexpr int kSampleRunLen = 1024;              // ... contiguous elements (coalesced)
 constexpr int kSample = kSampleRuns * kSampleRunLen;
+constexpr int kSampleBlockRuns = 4;              // runs a sample_kernel block gathers per trip (16 loads per thread in flight)
 constexpr int kSampleMargin = 4096;              // +- sample ranks: 8 sigma of a 2^20 sample's median rank
+constexpr int kFitFusedDefault = 1;              // window pass with the in-window histogram fused in (DEWI_FIT_FUSED)
 constexpr int kSurvCap = 8192;                   // keys of the target bins sorted in shared memory (typically a few hundred)
 
 struct SelState {
@@ -320,21 +323,33 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelStat
   const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
   const float* col = cols + static_cast<size_t>(c) * ld;
   unsigned int run_bin = 0xFFFFFFFFu, run_cnt = 0u;
-  for (int run = blockIdx.x; run < kSampleRuns; run += gridDim.x) {
-    const long long start = static_cast<long long>((static_cast<__int128>(run) * (n - kSampleRunLen)) / (kSampleRuns - 1));
-    unsigned int key[kSampleRunLen / 256];
+  // kSampleBlockRuns runs per block and trip: all their loads (16 per thread) are in flight before the first is used --
+  // the gather is a handful of dependent DRAM round trips otherwise
+  constexpr int kPer = kSampleRunLen / 256;
+  for (int run0 = blockIdx.x * kSampleBlockRuns; run0 < kSampleRuns; run0 += gridDim.x * kSampleBlockRuns) {
+    unsigned int key[kSampleBlockRuns * kPer];
 #pragma unroll
-    for (int u = 0; u < kSampleRunLen / 256; ++u) key[u] = load_key<SRC>(col, start + u * 256 + threadIdx.x, med);
+    for (int r = 0; r < kSampleBlockRuns; ++r) {
+      const int run = min(run0 + r, kSampleRuns - 1);
+      const long long start = static_cast<long long>((static_cast<__int128>(run) * (n - kSampleRunLen)) / (kSampleRuns - 1));
 #pragma unroll
-    for (int u = 0; u < kSampleRunLen / 256; ++u) {
-      skeys[static_cast<size_t>(c) * kSample + run * kSampleRunLen + u * 256 + threadIdx.x] = key[u];
-      const unsigned int bin = key[u] >> 21;   // pass 0: bits 31..21
-      if (bin != run_bin) {
-        if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
-        run_bin = bin;
-        run_cnt = 0u;
+      for (int u = 0; u < kPer; ++u) key[r * kPer + u] = load_key<SRC>(col, start + u * 256 + threadIdx.x, med);
+    }
+#pragma unroll
+    for (int r = 0; r < kSampleBlockRuns; ++r) {
+      if (run0 + r >= kSampleRuns) break;
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const unsigned int kk = key[r * kPer + u];
+        skeys[static_cast<size_t>(c) * kSample + (run0 + r) * kSampleRunLen + u * 256 + threadIdx.x] = kk;
+        const unsigned int bin = kk >> 21;   // pass 0: bits 31..21
+        if (bin != run_bin) {
+          if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
+          run_bin = bin;
+          run_cnt = 0u;
+        }
+        ++run_cnt;
       }
-      ++run_cnt;
     }
   }
   if (run_bin != 0xFFFFFFFFu) atomicAdd(&sh[run_bin], run_cnt);
@@ -370,10 +385,16 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelStat
 // for any column count.
 constexpr int kWinBuf = 3072;
 constexpr int kWinThreads = 256;
-constexpr int kWinPerThread = 16;
+#ifndef DEWI_WIN_PER_THREAD
+#define DEWI_WIN_PER_THREAD 16
+#endif
+#ifndef DEWI_WIN_BLOCKS_PER_SM
+#define DEWI_WIN_BLOCKS_PER_SM 8
+#endif
+constexpr int kWinPerThread = DEWI_WIN_PER_THREAD;
 constexpr int kWinTile = kWinThreads * kWinPerThread;
 constexpr int kFlushCheckEvery = 8;   // tiles between two looks at the buffer fill (8 tiles add ~260 keys)
-constexpr int kWinBlocksPerSm = 8;
+constexpr int kWinBlocksPerSm = DEWI_WIN_BLOCKS_PER_SM;
 
 // Inclusive prefix sums of g[0 .. kBins) into cum[] for the whole block (blockDim.x divides kBins, at most 8 bins
 // per thread); `wsum` is 32 words of scratch.
@@ -418,20 +439,29 @@ __device__ __forceinline__ unsigned int window_digit(unsigned int key, unsigned 
   return rel >> wshift;
 }
 
-// The block that completes a column of window_kernel (all its tiles accounted for) turns the column's counts into
-// the two target bins of the in-window selection: ranks (middle - below) inside the collected keys, located in the
-// histogram of the window-relative digit.  A window that overflowed or does not hold the ranks is flagged (miss).
-// Kept out of line: it runs once per column and must not cost the streaming loop registers.
-// `shm`: the block's kWinBuf + kBins words (free at this point), reused as 2048 x u64 prefix sums.
-__device__ __noinline__ void window_pick(int c, long long n, unsigned int window_cap, SelState* st, unsigned int* g,
-                                         unsigned int* shm, unsigned long long* wsum) {
+// Shared state of a window_kernel block that its out-of-line helpers need.
+struct WinShared {
+  // [ buf : keys waiting for the next flush | hist : window-relative digit histogram of the current column ]; the
+  // block that finishes a column last reuses the whole array as 2048 x u64 prefix sums (window_pick)
+  unsigned int shm[kWinBuf + kBins];
+  unsigned long long wsum[32];
+  unsigned int ticket;
+  // digit parameters of the current column (written by thread 0 at a column switch)
+  unsigned int lo_key, span;
+  int wshift;
+};
+
+// The block that completes a column (all its tiles accounted for) turns the column's counts into the two target
+// bins of the in-window selection: ranks (middle - below) inside the collected keys, located in the histogram of
+// the window-relative digit.  A window that overflowed or does not hold the ranks is flagged (miss).
+__device__ __forceinline__ void window_pick(WinShared* ws, int c, long long n, unsigned int window_cap, SelState* st, unsigned int* g) {
   unsigned long long r0, r1;
   middle_ranks(n, r0, r1);
   const unsigned long long nbelow = __ldcg(&st->below[c]), cnt = __ldcg(&st->wcnt[c]);
   const bool ok = cnt <= window_cap && nbelow <= r0 && r1 < nbelow + cnt;
   if (ok) {
-    unsigned long long* cum = reinterpret_cast<unsigned long long*>(shm);
-    scan_bins(g, cum, wsum);
+    unsigned long long* cum = reinterpret_cast<unsigned long long*>(ws->shm);
+    scan_bins(g, cum, ws->wsum);
     const unsigned long long rr[2] = {r0 - nbelow, r1 - nbelow};
     for (int ss = 0; ss < 2; ++ss) {
       for (int bin = threadIdx.x; bin < kBins; bin += blockDim.x) {
@@ -446,30 +476,63 @@ __device__ __noinline__ void window_pick(int c, long long n, unsigned int window
   } else if (threadIdx.x == 0) {
     st->miss[c] = 1;
   }
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) g[i] = 0u;                 // the histogram memory is reused
-  for (int i = threadIdx.x; i < kWinBuf + kBins; i += blockDim.x) shm[i] = 0u;    // (clobbered by the prefix sums)
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) g[i] = 0u;                    // the histogram memory is reused
+  for (int i = threadIdx.x; i < kWinBuf + kBins; i += blockDim.x) ws->shm[i] = 0u;   // (clobbered by the prefix sums)
   if (threadIdx.x == 0) st->tiles_done[c] = 0u;
   __syncthreads();
 }
 
-template <int SRC>
+// End of a column for this block (block-uniform; the key buffer has been flushed): hand the digit histogram over,
+// draw the column's tile ticket and, if that completes the column, pick the target bins.  Out of line: it runs once
+// or twice per block and must not cost the streaming loop registers.
+__device__ __forceinline__ void window_finish_column(WinShared* ws, int c, unsigned int tiles_mine, int tiles_per_col, long long n,
+                                                  unsigned int window_cap, SelState* st, unsigned int* ghist) {
+  unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
+  unsigned int* hist = ws->shm + kWinBuf;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    const unsigned int v = hist[i];
+    if (v) { atomicAdd(&g[i], v); hist[i] = 0u; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ws->ticket = atomicAdd(&st->tiles_done[c], tiles_mine);
+  __syncthreads();
+  if (ws->ticket + tiles_mine == static_cast<unsigned int>(tiles_per_col)) {
+    __threadfence();
+    window_pick(ws, c, n, window_cap, st, g);
+  }
+  __syncthreads();
+}
+
+// Load the digit parameters of column c into the block's shared state (block-uniform).
+__device__ __forceinline__ void window_enter_column(WinShared* ws, int c, const SelState* st) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ws->lo_key = st->lo[c];
+    ws->span = st->hi[c] - st->lo[c];
+    ws->wshift = st->wshift[c];
+  }
+  __syncthreads();
+}
+
+// FUSED = 1: the histogram of the window-relative digit and the pick of the target bins ride along (the digits are
+// counted when the key buffer is flushed; the block that completes a column picks).  FUSED = 0: the pass only counts
+// and collects, and window_hist_kernel histograms the collected keys in a launch of its own.
+template <int SRC, int FUSED>
 __global__ void __launch_bounds__(kWinThreads, kWinBlocksPerSm)
 window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, SelState* st,
               unsigned int* __restrict__ wkeys, unsigned int window_cap, unsigned int* __restrict__ ghist) {
-  // [ buf : keys waiting for the next flush | hist : window-relative digit histogram of the current column ]; the
-  // block that finishes a column last reuses the whole array as 2048 x u64 prefix sums (window_pick)
-  __shared__ __align__(8) unsigned int shm[kWinBuf + kBins];
-  unsigned int* const buf = shm;
-  unsigned int* const hist = shm + kWinBuf;
-  __shared__ unsigned long long wsum[32];
-  __shared__ unsigned int buf_n, flush_base, ticket_s;
+  __shared__ __align__(8) WinShared ws;
+  unsigned int* const buf = ws.shm;
+  __shared__ unsigned int buf_n, flush_base;
   __shared__ unsigned long long below_blk;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) ws.shm[kWinBuf + i] = 0u;
   const int lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0u;
-  const long long tiles_per_col = (n + kWinTile - 1) / kWinTile;
-  const long long total_tiles = tiles_per_col * f;
-  const long long t_begin = (total_tiles * blockIdx.x) / gridDim.x;
-  const long long t_end = (total_tiles * (blockIdx.x + 1)) / gridDim.x;
+  // (tile counts fit 32 bits: 2^31 rows x 32 columns / 4096)
+  const int tiles_per_col = static_cast<int>((n + kWinTile - 1) / kWinTile);
+  const long long total_tiles = static_cast<long long>(tiles_per_col) * f;
+  const int t_begin = static_cast<int>((total_tiles * blockIdx.x) / gridDim.x);
+  const int t_end = static_cast<int>((total_tiles * (blockIdx.x + 1)) / gridDim.x);
   if (threadIdx.x == 0) { buf_n = 0u; below_blk = 0ull; }
   __syncthreads();
 
@@ -487,8 +550,11 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
     if (cnt > min_fill) {
       if (threadIdx.x == 0) flush_base = atomicAdd(&st->wcnt[c], cnt);
       __syncthreads();
-      for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
-        if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
+      for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        const unsigned int key = buf[k];
+        if (flush_base + k < window_cap) out[flush_base + k] = key;
+        if (FUSED) atomicAdd(&ws.shm[kWinBuf + window_digit(key, ws.lo_key, ws.span, ws.wshift)], 1u);
+      }
       __syncthreads();
       if (threadIdx.x == 0) buf_n = 0u;
       __syncthreads();
@@ -506,43 +572,33 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
       below_blk = 0ull;
     }
     below = 0u;
-    unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
-    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
-      const unsigned int v = hist[i];
-      if (v) { atomicAdd(&g[i], v); hist[i] = 0u; }
-    }
-    __threadfence();
     __syncthreads();
-    // tiles of column c inside this block's range [t_begin, t_end)
-    const long long c_lo = static_cast<long long>(c) * tiles_per_col;
-    const unsigned int tiles_mine = static_cast<unsigned int>(min(t_end, c_lo + tiles_per_col) - max(t_begin, c_lo));
-    if (threadIdx.x == 0) ticket_s = atomicAdd(&st->tiles_done[c], tiles_mine);
-    __syncthreads();
-    const bool last = static_cast<long long>(ticket_s) + tiles_mine == tiles_per_col;
-    if (last) {  // block-uniform
-      __threadfence();
-      window_pick(c, n, window_cap, st, g, shm, wsum);
+    if (FUSED) {
+      // tiles of column c inside this block's range [t_begin, t_end)
+      // (the block's first tile is recomputed here rather than kept in a register across the streaming loop)
+      const int c_lo = c * tiles_per_col;
+      const int first = static_cast<int>((static_cast<long long>(tiles_per_col) * f * blockIdx.x) / gridDim.x);
+      window_finish_column(&ws, c, static_cast<unsigned int>(min(t_end, c_lo + tiles_per_col) - max(first, c_lo)), tiles_per_col,
+                           n, window_cap, st, ghist);
     }
   };
   auto push = [&](float v) {  // v lies in the window
     const unsigned int key = orderable(v);
-    {  // (rare path: the window parameters are re-read from the cached state instead of living in registers)
-      const unsigned int lo_key = st->lo[c];
-      atomicAdd(&hist[window_digit(key, lo_key, st->hi[c] - lo_key, st->wshift[c])], 1u);
-    }
     const unsigned int slot = atomicAdd(&buf_n, 1u);
-    if (slot < kWinBuf) buf[slot] = key;
+    if (slot < kWinBuf) buf[slot] = key;   // (its digit is histogrammed when the buffer is flushed)
     else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
       const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
       if (g < window_cap) out[g] = key;
+      if (FUSED) atomicAdd(&ws.shm[kWinBuf + window_digit(key, ws.lo_key, ws.span, ws.wshift)], 1u);
     }
   };
 
-  for (long long t = t_begin; t < t_end; ++t) {
-    const int tc = static_cast<int>(t / tiles_per_col);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int tc = t / tiles_per_col;
     if (tc != c) {
       if (c >= 0) commit_column();
       c = tc;
+      if (FUSED) window_enter_column(&ws, c, st);
       med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
       lo_f = from_orderable(st->lo[c]);
       hi_f = from_orderable(st->hi[c]);
@@ -550,7 +606,7 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
       out = wkeys + static_cast<size_t>(c) * window_cap;
       aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
     }
-    const long long base = (t - static_cast<long long>(c) * tiles_per_col) * kWinTile;
+    const long long base = static_cast<long long>(t - c * tiles_per_col) * kWinTile;
     if (aligned && base + kWinTile <= n) {
       // element e of this thread: base + (e / 4) * (threads * 4) + tid * 4 + (e % 4)  (coalesced 128-bit loads)
       const float* p = col + base + threadIdx.x * 4;
@@ -593,6 +649,50 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
   if (c >= 0) commit_column();
 }
 
+// FUSED = 0 only: the histogram of the window-relative digit over the collected keys (L2-resident), one launch for
+// all columns; the last block of a column picks the target bins (window_pick).
+constexpr int kWhistThreads = 512;
+
+__global__ void __launch_bounds__(kWhistThreads)
+window_hist_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap, long long n, SelState* st,
+                   unsigned int* __restrict__ ghist) {
+  __shared__ __align__(8) WinShared ws;
+  const int c = blockIdx.y;
+  unsigned int* hist = ws.shm + kWinBuf;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const unsigned int lo = st->lo[c], span = st->hi[c] - lo;
+  const int wshift = st->wshift[c];
+  const unsigned int cnt = min(__ldcg(&st->wcnt[c]), window_cap);
+  const unsigned int* src = wkeys + static_cast<size_t>(c) * window_cap;
+  constexpr int kU = 8;   // independent loads in flight per thread (the pass is latency-bound otherwise)
+  const unsigned int stride = gridDim.x * blockDim.x * kU;
+  for (unsigned int base = blockIdx.x * blockDim.x * kU; base < cnt; base += stride) {
+    unsigned int key[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const unsigned int i = base + u * blockDim.x + threadIdx.x;
+      key[u] = i < cnt ? __ldg(src + i) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (base + u * blockDim.x + threadIdx.x < cnt) atomicAdd(&hist[window_digit(key[u], lo, span, wshift)], 1u);
+  }
+  __syncthreads();
+  unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    const unsigned int v = hist[i];
+    if (v) atomicAdd(&g[i], v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) ws.ticket = atomicAdd(&st->tiles_done[c], 1u);
+  __syncthreads();
+  if (ws.ticket != gridDim.x - 1) return;
+  __threadfence();
+  window_pick(&ws, c, n, window_cap, st, g);   // (also resets tiles_done[c] and the histogram)
+}
+
 // In-window selection, second half.  window_kernel left, per column, the digits (bins) of the two middle ranks and
 // their ranks inside those bins; a bin of the window-relative top digit holds ~1/2048 of the window's keys -- a
 // few hundred.  This pass re-reads the window keys (L2-resident), gathers the keys of the target bins, and the
@@ -614,13 +714,24 @@ survivor_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap,
   const unsigned int cnt = min(st->wcnt[c], window_cap);
   const unsigned int* src = wkeys + static_cast<size_t>(c) * window_cap;
   unsigned int* dst = surv + static_cast<size_t>(c) * kSurvCap;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
-    const unsigned int key = __ldg(src + i);
-    const unsigned int d = window_digit(key, lo, span, wshift);
-    if (d == b0 || d == b1) {
-      const unsigned int slot = atomicAdd(&st->surv_n[c], 1u);
-      if (slot < kSurvCap) dst[slot] = key;
-      if (d == b0 && b0 != b1) atomicAdd(&st->surv_n0[c], 1u);
+  constexpr int kU = 8;   // independent loads in flight per thread (the pass is latency-bound otherwise)
+  const unsigned int stride = gridDim.x * blockDim.x * kU;
+  for (unsigned int base = blockIdx.x * blockDim.x * kU; base < cnt; base += stride) {
+    unsigned int key[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const unsigned int i = base + u * blockDim.x + threadIdx.x;
+      key[u] = i < cnt ? __ldg(src + i) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (base + u * blockDim.x + threadIdx.x >= cnt) continue;
+      const unsigned int d = window_digit(key[u], lo, span, wshift);
+      if (d == b0 || d == b1) {
+        const unsigned int slot = atomicAdd(&st->surv_n[c], 1u);
+        if (slot < kSurvCap) dst[slot] = key[u];
+        if (d == b0 && b0 != b1) atomicAdd(&st->surv_n0[c], 1u);
+      }
     }
   }
   __threadfence();
@@ -771,6 +882,36 @@ void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, c
 
 // One full pass per statistic: window bounds from a sample, keys inside the window collected, the
 // middle ranks selected among them.  st->miss[c] reports a window that did not hold the ranks.
+// DEWI_FIT_TIMING=1: CUDA-event time of every stage of a windowed fit on stderr (warm caches, in-stream -- what ncu's
+// serialised cold-cache replays cannot show for the small kernels).
+struct StageTimer {
+  bool on = false;
+  cudaEvent_t ev[32] = {};
+  const char* name[32] = {};
+  int n = 0;
+  void mark(cudaStream_t stream, const char* what) {
+    if (!on || n >= 32) return;
+    if (!ev[n]) cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], stream);
+    name[n++] = what;
+  }
+  void report() {
+    if (!on || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    float total = 0.f;
+    cudaEventElapsedTime(&total, ev[0], ev[n - 1]);
+    fprintf(stderr, "[dewi_fit_stats] %.1f us on the device:", total * 1e3f);
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %s %.1f", name[i], ms * 1e3f);
+    }
+    fprintf(stderr, "\n");
+    n = 0;
+  }
+};
+StageTimer g_fit_timer;
+
 // Four launches (the state must be armed for a sample selection: glue ARM_SAMPLE, or the previous statistic's
 // survivor pass):
 //   sample_kernel    gathers the sample keys, histograms their top 11 bits, picks the bins of ranks s/2 -+ margin
@@ -781,15 +922,26 @@ void fit_full(const float* cols, long long n, int f, long long ld, FitWork& w, c
 template <int SRC>
 void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsigned int cap, FitWork& w, int final_op,
                        cudaStream_t stream) {
-  sample_kernel<SRC><<<dim3(128, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done);
+  sample_kernel<SRC><<<dim3(kSampleRuns / kSampleBlockRuns, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done);
+  g_fit_timer.mark(stream, "sample");
   {
     const int threads = 512, per_thread = 8;
     const int bx = static_cast<int>(std::min<int64_t>(ceil_div(kSample, threads * per_thread), std::max(1, w.sm_count * 4 / f)));
     hist_kernel<SRC_KEYS><<<dim3(std::max(bx, 1), f), threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, 1, w.st, w.ghist,
                                                                              w.done, OP_WINDOW_BOUNDS);
   }
-  window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
+  g_fit_timer.mark(stream, "hist");
+  if (env_int("DEWI_FIT_FUSED", kFitFusedDefault)) {
+    window_kernel<SRC, 1><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
+    g_fit_timer.mark(stream, "window+hist");
+  } else {
+    window_kernel<SRC, 0><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
+    g_fit_timer.mark(stream, "window");
+    window_hist_kernel<<<dim3(std::max(1, w.sm_count * 2 / f), f), kWhistThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.ghist);
+    g_fit_timer.mark(stream, "whist");
+  }
   survivor_kernel<<<dim3(std::max(1, w.sm_count / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op);
+  g_fit_timer.mark(stream, "survivor");
 }
 
 }  // namespace
@@ -830,12 +982,16 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   SelState res;
   bool need_full = !windowed;
   if (windowed) {
+    g_fit_timer.on = env_set("DEWI_FIT_TIMING");
+    g_fit_timer.mark(stream, "start");
     glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
+    g_fit_timer.mark(stream, "arm");
     fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
     fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
     DEWI_CUDA(cudaGetLastError());
     DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
+    g_fit_timer.report();
     for (int c = 0; c < f; ++c) need_full = need_full || res.miss[c] != 0;  // e.g. a huge tie group at the median
     if (need_full) DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
   }
