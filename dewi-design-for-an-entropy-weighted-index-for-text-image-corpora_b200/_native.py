@@ -26,6 +26,7 @@ FLAG_SCOPE_FULL = 1 << 5
 FLAG_NO_PAIR = 1 << 6
 FLAG_NO_SEED = 1 << 7
 FLAG_NO_M64 = 1 << 8
+FLAG_NO_CERT = 1 << 9
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2
@@ -63,6 +64,7 @@ SIGNATURES = {
     "dewi_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int64, c_int, c_int, c_double, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "dewi_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "dewi_index_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "dewi_index_cert_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "dewi_index_set_profiling": (c_int, [c_void_p, c_int]),
     "dewi_index_sweep_ms": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]),
     "dewi_fit_stats": (c_int, [c_void_p, c_int64, c_int, c_int64, POINTER(c_double), POINTER(c_double), c_int, c_void_p]),

@@ -568,6 +568,13 @@ class CudaIndex(BaseIndex):
                                                    ctypes.c_void_p(ent.data_ptr()), _native.stream_ptr())
         _native.check(rc)
 
+    def cert_stats(self) -> Tuple[int, int]:
+        """fp32 index: `(searches answered by the certified single-plane sweep, of which re-run with the full hi/lo
+        product because the certificate could not be given)`."""
+        used, failed = ctypes.c_int64(0), ctypes.c_int64(0)
+        _native.check(self._lib.dewi_index_cert_stats(self._h, ctypes.byref(used), ctypes.byref(failed)))
+        return used.value, failed.value
+
     def last_launches(self) -> int:
         n = ctypes.c_int(0)
         _native.check(self._lib.dewi_index_last_launches(self._h, ctypes.byref(n)))

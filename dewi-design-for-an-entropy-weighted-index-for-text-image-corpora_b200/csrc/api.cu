@@ -79,6 +79,9 @@ struct DevBuf {
 
 // Minimum corpus size for which the tensor-core sweep is selected automatically.
 constexpr int64_t kTcMinRows = 2048;
+// Certified single-plane sweep of an fp32 corpus: worth its host synchronisation (the certificate's verdict is read
+// back before the candidates are used) once a plane is tens of megabytes.
+constexpr int64_t kCertMinElems = int64_t(32) << 20;
 
 }  // namespace
 }  // namespace dewi
@@ -94,12 +97,15 @@ struct dewi_index {
   float* dewi_col = nullptr;          // [cap]
   float* ent_col = nullptr;           // [cap]
   int* bad_flag = nullptr;
+  // certified single-plane sweep (fp32 corpus): running maxima of ||row - hi|| and ||hi|| (float bits), a fail counter
+  unsigned int* plane_max = nullptr;   // [2] plane maxima, [2] = certificate fail counter
+  long long cert_used = 0, cert_failed = 0;   // searches answered by the certified sweep / re-run with the full product
   // cached tensor maps of the corpus planes
   CUtensorMap map_e0, map_e1;
   int64_t map_rows = -1;
   int map_box = 0;
   // workspaces
-  DevBuf stage, stage2, qraw, qn, q0, q1, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
+  DevBuf stage, stage2, qraw, qn, q0, q1, qstats, qbar, part_s, part_i, seed_max, seed_sim, cand_idx, cand_sim, loc_sim, loc_id, loc_dewi, loc_ent, out_id,
       out_score;
   int last_launches = 0;
   // host ingest pipeline: copies run on `copy_stream`, two staging buffers, one "kernel done with buffer" event each
@@ -244,11 +250,13 @@ int dewi_index_create(int dim, int space, int dtype, int device, dewi_index_t** 
   h->dtype = dtype;
   h->device = device;
   h->sm_count = sms;
-  if (cudaMalloc(&h->bad_flag, sizeof(int)) != cudaSuccess) {
+  if (cudaMalloc(&h->bad_flag, sizeof(int)) != cudaSuccess || cudaMalloc(&h->plane_max, 4 * sizeof(unsigned int)) != cudaSuccess) {
+    cudaFree(h->bad_flag);
     delete h;
     return fail("cudaMalloc failed");
   }
   cudaMemset(h->bad_flag, 0, sizeof(int));
+  cudaMemset(h->plane_max, 0, 4 * sizeof(unsigned int));
   *out = h;
   return 0;
 }
@@ -262,6 +270,7 @@ int dewi_index_destroy(dewi_index_t* h) {
   cudaFree(h->dewi_col);
   cudaFree(h->ent_col);
   cudaFree(h->bad_flag);
+  cudaFree(h->plane_max);
   for (int i = 0; i < dewi_index::kEvRing; ++i) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
@@ -271,7 +280,7 @@ int dewi_index_destroy(dewi_index_t* h) {
     if (h->stage_free[i]) cudaEventDestroy(h->stage_free[i]);
     if (h->stage_full[i]) cudaEventDestroy(h->stage_full[i]);
   }
-  for (DevBuf* b : {&h->stage, &h->stage2, &h->qraw, &h->qn, &h->q0, &h->q1, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
+  for (DevBuf* b : {&h->stage, &h->stage2, &h->qraw, &h->qn, &h->q0, &h->q1, &h->qstats, &h->qbar, &h->part_s, &h->part_i, &h->seed_max, &h->seed_sim, &h->cand_idx, &h->cand_sim,
                     &h->loc_sim, &h->loc_id, &h->loc_dewi, &h->loc_ent, &h->out_id, &h->out_score, &h->push_ticket, &h->sync_cnt})
     b->release();
   delete h;
@@ -328,7 +337,7 @@ int dewi_index_append(dewi_index_t* h, const float* rows, int64_t n, int normali
     const size_t off = static_cast<size_t>(h->n + done) * d;
     DEWI_TRY(launch_prep_corpus(src, m, h->dim, do_norm, h->rows_f32 ? h->rows_f32 + off : nullptr,
                                 h->plane0 ? h->plane0 + off : nullptr, h->plane1 ? h->plane1 + off : nullptr,
-                                h->bad_flag, stream));
+                                h->bad_flag, stream, h->dtype == DEWI_DTYPE_FP32 ? h->plane_max : nullptr));
     if (src_is_host) {
       DEWI_CUDA(cudaEventRecord(h->stage_free[buf], stream));
       used[buf] = 1;
@@ -523,23 +532,51 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   int kc = (mode == 0) ? std::max(32, kc_valid + 16) : kc_valid + 8;
   TcPlan plan;
   Tc2Plan plan2;
-  // more than one query block: the CTA-pair sweep (two query blocks share every corpus tile)
-  bool use_pair = use_tc && n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
-  if (use_pair) {
-    const int n_qb2 = static_cast<int>(round_up(n_qb, 2));
-    if (tc2_make_plan(mode, dim, h->n, n_qb2, kc, h->sm_count, &plan2) == 0) {
-      n_qb = n_qb2;
-      b_pad = n_qb * kQueryBlock;
-    } else {
-      use_pair = false;
-    }
-  }
   // at most 64 queries: M = 64 MMAs (half the tensor work / power and half the query re-stream)
   const int q_rows = (B <= 64 && !(flags & DEWI_FLAG_NO_M64)) ? 64 : kQueryBlock;
-  if (use_tc && !use_pair) {
-    if (tc_make_plan(mode, dim, h->n, n_qb, kc, h->sm_count, &plan, 0, q_rows) != 0) {
+  const int n_qb_in = n_qb;
+  // more than one query block: the CTA-pair sweep (two query blocks share every corpus tile)
+  bool use_pair = false;
+  auto make_plans = [&](int mode_, int kc_) -> bool {   // false: no tensor-core plan for this (mode, list capacity)
+    n_qb = n_qb_in;
+    b_pad = n_qb * kQueryBlock;
+    use_pair = n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
+    if (use_pair) {
+      const int n_qb2 = static_cast<int>(round_up(n_qb, 2));
+      if (tc2_make_plan(mode_, dim, h->n, n_qb2, kc_, h->sm_count, &plan2) == 0) {
+        n_qb = n_qb2;
+        b_pad = n_qb * kQueryBlock;
+        return true;
+      }
+      use_pair = false;
+    }
+    return tc_make_plan(mode_, dim, h->n, n_qb, kc_, h->sm_count, &plan, 0, q_rows) == 0;
+  };
+  // CERTIFIED single-plane sweep (fp32 corpus).  The hi plane alone -- half the bytes of the hi/lo stream below the
+  // ridge, a third of its MMAs above -- is swept with a longer candidate list; a certificate (select.cu) then proves,
+  // from rigorous bounds on the two bf16 roundings, that the list holds the exact top-2k, and the exact fp32 re-score
+  // orders it.  Small batches use both query planes (their MMAs are free there and halve the bound), CTA pairs one.
+  // When the certificate cannot be given for some query (scores packed more densely than the bound resolves) the batch
+  // is re-run with the full hi/lo product: results are exact either way.
+  int cert_planes = 0;
+  if (use_tc && mode == 2 && !(flags & DEWI_FLAG_NO_CERT) && env_int("DEWI_CERT", 1) != 0 &&
+      static_cast<int64_t>(h->n) * dim >= kCertMinElems) {
+    const bool pair_intent = n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
+    const int planes = pair_intent ? 1 : 2;
+    const int cert_kc = std::max(pair_intent ? 96 : 64, kc_valid * (pair_intent ? 4 : 3) + 4);
+    if (make_plans(planes == 1 ? 0 : 1, cert_kc) && (use_pair || plan.n_stages >= 3)) {
+      cert_planes = planes;
+      mode = planes == 1 ? 0 : 1;
+      kc = cert_kc;
+    }
+  }
+  if (use_tc && !cert_planes) {
+    if (!make_plans(mode, kc)) {
       if (flags & DEWI_FLAG_FORCE_TC) return 1;
       use_tc = false;
+      use_pair = false;
+      n_qb = n_qb_in;
+      b_pad = n_qb * kQueryBlock;
     }
   } else if (!use_tc && (flags & DEWI_FLAG_FORCE_TC)) {
     return fail("tcgen05 sweep not applicable (needs cosine space and dim % 64 == 0)");
@@ -550,8 +587,10 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   DEWI_TRY(h->q0.ensure(static_cast<size_t>(b_pad) * dim * 2));
   DEWI_TRY(h->q1.ensure(static_cast<size_t>(b_pad) * dim * 2));
   const int qnorm = (h->space == DEWI_SPACE_COSINE && !(flags & DEWI_FLAG_QUERY_NORMALIZED)) ? 1 : 0;
+  if (cert_planes) DEWI_TRY(h->qstats.ensure(static_cast<size_t>(b_pad) * 16));
   DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
-                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/(use_tc && !use_pair && q_rows == 64) ? 2 : 1));
+                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/(use_tc && !use_pair && q_rows == 64) ? 2 : 1,
+                               cert_planes ? h->qstats.as<float>() : nullptr));
   h->last_launches++;
 
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
@@ -655,9 +694,25 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   DEWI_TRY(h->cand_sim.ensure(static_cast<size_t>(B) * kc * 4));
   DEWI_TRY(launch_merge_select(parts, B, kc, h->cand_idx.as<int>(), h->cand_sim.as<float>(), stream));
   h->last_launches++;
+  if (cert_planes) {
+    int* fails_dev = reinterpret_cast<int*>(h->plane_max + 2);
+    DEWI_CUDA(cudaMemsetAsync(fails_dev, 0, sizeof(int), stream));
+    DEWI_TRY(h->qbar.ensure(static_cast<size_t>(B) * 4));
+    DEWI_TRY(launch_certificate(h->cand_sim.as<float>(), h->cand_idx.as<int>(), B, kc, kc_valid, h->qstats.as<float>(), cert_planes,
+                                h->plane_max, dim, fails_dev, h->qbar.as<float>(), stream));
+    h->last_launches++;
+    int fails = 0;
+    DEWI_CUDA(cudaMemcpyAsync(&fails, fails_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+    h->cert_used++;
+    if (fails > 0) {   // not provable for `fails` queries: the whole batch again with the full hi/lo product
+      h->cert_failed++;
+      return search_local_impl(h, queries, B, kcand, flags | DEWI_FLAG_NO_CERT, out_sim, out_id, out_dewi, out_ent, stream_, push);
+    }
+  }
   if (use_tc) {
     DEWI_TRY(launch_rescore(exact_rows, exact_is_bf16, dim, h->qn.as<float>(), h->cand_idx.as<int>(), B, kc,
-                            h->cand_sim.as<float>(), stream));
+                            h->cand_sim.as<float>(), stream, cert_planes ? h->qbar.as<float>() : nullptr));
     h->last_launches++;
   }
   DEWI_TRY(launch_finalize_local(h->cand_idx.as<int>(), h->cand_sim.as<float>(), B, kc, kcand, h->id_base, h->dewi_col,
@@ -768,6 +823,13 @@ int dewi_index_sweep_ms(dewi_index_t* h, int back, float* ms, int* kind) {
   DEWI_CUDA(cudaEventSynchronize(h->ev1[slot]));
   DEWI_CUDA(cudaEventElapsedTime(ms, h->ev0[slot], h->ev1[slot]));
   if (kind) *kind = h->last_sweep_kind;
+  return 0;
+}
+
+int dewi_index_cert_stats(const dewi_index_t* h, int64_t* used, int64_t* failed) {
+  if (!h || !used || !failed) return fail("null argument");
+  *used = h->cert_used;
+  *failed = h->cert_failed;
   return 0;
 }
 

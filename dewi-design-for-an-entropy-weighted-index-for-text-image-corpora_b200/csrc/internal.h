@@ -115,8 +115,12 @@ int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, in
 // seed[b] = the kc-th largest of query b's per-item maxima [n_chunks][n_qb][128] (-inf when n_chunks < kc)
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream);
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
-int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
-                   float* cand_sim, cudaStream_t stream);
+int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, int* cand_idx, int B, int kc,
+                   float* cand_sim, cudaStream_t stream, const float* bar = nullptr);
+// Certified single-plane sweep (fp32 corpus swept through its bf16 hi plane): counts in *fails the queries whose list
+// of the kc best swept scores cannot be PROVEN to contain the exact top-`need` (see select.cu).
+int launch_certificate(const float* cand_sim, const int* cand_idx, int B, int kc, int need, const float* q_stats, int q_planes,
+                       const unsigned int* plane_max, int dim, int* fails, float* bar, cudaStream_t stream);
 // Fused exchange of the multi-GPU search (one process per GPU, peers' buffers mapped through symmetric memory):
 // finalize_local writes this rank's candidate block `[id i64 | sim | dewi | ent]` straight into EVERY rank's gather
 // buffer with peer stores over NVLink (slot `my_rank`), and the last block releases `flags[r][my_rank] = seq` on
@@ -141,13 +145,16 @@ int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const 
 
 // ---- operand preparation (prep.cu) -----------------------------------------------------------
 // rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.
+// plane_max (optional, device, 2 words): running maxima over all rows ever prepared of ||x - hi|| and ||hi|| as
+// float bit patterns -- the corpus side of the certified single-plane sweep's error bound.
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream);
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max = nullptr);
 // queries fp32 [B, dim] -> qn fp32 [b_pad, dim] (natural order), q hi/lo bf16 [b_pad, dim] (rows >= B
 // zeroed).  lane_order 1: plane row of query b is (b / 128) * 128 + query_lane(b % 128) (M = 128 sweeps);
 // lane_order 2 (b < 64 only): row (b & 3) * 16 + (b >> 2), the A-row whose M = 64 accumulator lane is query_lane(b).
+// q_stats (optional, device, [b_pad][4]): per query { ||q||, ||q - hi||, ||q - hi - lo||, ||hi|| }, rounded upwards.
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0);
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0, float* q_stats = nullptr);
 // bf16 -> fp32 (exact widening) of `count` contiguous elements: bulk export of a bf16-storage corpus.
 int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaStream_t stream);
 

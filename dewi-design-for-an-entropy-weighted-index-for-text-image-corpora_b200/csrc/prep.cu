@@ -20,12 +20,19 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
 }
 
+// Rounding bookkeeping for the CERTIFIED single-plane sweep (api.cu): how far the bf16 planes are from the fp32 values.
+//   row_stats[row] = { ||x||, ||x - hi||, ||x - hi - lo||, ||hi|| }   (queries: one record per query)
+//   plane_max      = { max_r ||x_r - hi_r||, max_r ||hi_r|| }          (corpus: running maxima, float bits via atomicMax)
+// Norms are evaluated in fp32 and inflated by 2^-10 (they bound an error, so they may only err upwards).
+__device__ __forceinline__ float up(float v) { return v * 1.0009765625f + 1e-12f; }
+
 __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, long long n_out, int dim, int normalize,
                                  int guard_zero, int lane_order, float* __restrict__ dst_f32,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                 int* __restrict__ bad_flag) {
+                                 int* __restrict__ bad_flag, float* __restrict__ row_stats, unsigned int* __restrict__ plane_max) {
   const int lane = threadIdx.x & 31;
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float warp_max_err = 0.f, warp_max_hi = 0.f;
   for (long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; row < n_out; row += warps) {
     const size_t off = static_cast<size_t>(row) * dim;
     // bf16 planes may use the TMEM-lane order of the sweep (internal.h: query_lane)
@@ -39,6 +46,7 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
         if (hi) hi[poff + d] = __float2bfloat16_rn(0.f);
         if (lo) lo[poff + d] = __float2bfloat16_rn(0.f);
       }
+      if (row_stats && lane < 4) row_stats[row * 4 + lane] = 0.f;
       continue;
     }
     const float* s = src + off;
@@ -59,6 +67,7 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
         atomicExch(bad_flag, 1);  // zero-norm corpus row: the reference would store NaNs
       }
     }
+    float sx = 0.f, s1 = 0.f, s2 = 0.f, sh = 0.f;
     for (int d = lane; d < dim; d += 32) {
       float x = s[d];
       if (do_div) x = __fdiv_rn(x, scale_div);
@@ -68,18 +77,44 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
         split_bf16(x, h, l);
         hi[poff + d] = h;
         if (lo) lo[poff + d] = l;
+        if (row_stats || plane_max) {
+          const float hf = __bfloat162float(h), r1 = x - hf, r2 = r1 - __bfloat162float(l);   // (both differences are exact)
+          sx = fmaf(x, x, sx);
+          s1 = fmaf(r1, r1, s1);
+          s2 = fmaf(r2, r2, s2);
+          sh = fmaf(hf, hf, sh);
+        }
       }
     }
+    if (hi && (row_stats || plane_max)) {
+      sx = up(sqrtf(warp_sum(sx)));
+      s1 = up(sqrtf(warp_sum(s1)));
+      s2 = up(sqrtf(warp_sum(s2)));
+      sh = up(sqrtf(warp_sum(sh)));
+      if (row_stats && lane == 0) {
+        row_stats[row * 4 + 0] = sx;
+        row_stats[row * 4 + 1] = s1;
+        row_stats[row * 4 + 2] = s2;
+        row_stats[row * 4 + 3] = sh;
+      }
+      warp_max_err = fmaxf(warp_max_err, s1);
+      warp_max_hi = fmaxf(warp_max_hi, sh);
+    }
+  }
+  if (plane_max && lane == 0) {  // one pair of atomics per warp (positive floats order like their bit patterns)
+    atomicMax(plane_max + 0, __float_as_uint(warp_max_err));
+    atomicMax(plane_max + 1, __float_as_uint(warp_max_hi));
   }
 }
 
 int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, int guard_zero, int lane_order,
-           float* dst_f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
+           float* dst_f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, float* row_stats = nullptr,
+           unsigned int* plane_max = nullptr) {
   if (n_out <= 0) return 0;
   const int threads = 256;
   const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), static_cast<int64_t>(current_sm_count()) * 16);
   prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero,
-                                                                    lane_order, dst_f32, hi, lo, bad_flag);
+                                                                    lane_order, dst_f32, hi, lo, bad_flag, row_stats, plane_max);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -104,14 +139,14 @@ int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaS
 }
 
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream) {
-  return launch(src, n, n, dim, normalize, 1, 0, dst_f32, hi, lo, bad_flag, stream);
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max) {
+  return launch(src, n, n, dim, normalize, 1, 0, dst_f32, hi, lo, bad_flag, stream, nullptr, plane_max);
 }
 
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order) {
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order, float* q_stats) {
   // a zero query stays zero (backends.py:422-424: divide only when the norm is positive)
-  return launch(q, B, b_pad, dim, normalize, 0, lane_order, qn, hi, lo, nullptr, stream);
+  return launch(q, B, b_pad, dim, normalize, 0, lane_order, qn, hi, lo, nullptr, stream, q_stats, nullptr);
 }
 
 }  // namespace dewi

@@ -163,19 +163,50 @@ seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb
   }
 }
 
+// ---- certificate of the single-plane sweep ----------------------------------------------------------------
+// fp32 corpus, swept through its bf16 hi plane only (api.cu: certified mode).  With s = q . e the exact similarity
+// and S the swept one (bf16 products are exact, fp32 accumulation),
+//     |s - S| <= ||q|| * max_r ||e_r - hi_r|| + ||q - q_planes|| * max_r ||hi_r|| + gamma * ||q_planes|| * max_r ||hi_r|| =: eps
+// (Cauchy-Schwarz on the two rounding residuals; gamma = dim * 2^-22 bounds the fp32 accumulation of `dim` exact
+// products, with a factor two of slack for a truncating adder).  Let S_(j) be the j-th largest swept score.  At least
+// `need` rows have s >= S_(need) - eps, so every row of the exact top-`need` has s >= S_(need) - eps and therefore
+// S >= S_(need) - 2 eps: the list of the kc best swept scores contains the exact top-`need` whenever it is not full or
+// S_(kc) < S_(need) - 2 eps.  Queries for which that cannot be shown are counted in *fails (the caller re-runs the
+// batch with the full hi/lo product).  cand_sim is sorted descending per query, cand_idx < 0 marks empty slots.
+__global__ void certificate_kernel(const float* __restrict__ cand_sim, const int* __restrict__ cand_idx, int B, int kc, int need,
+                                   const float* __restrict__ q_stats, int q_planes, const unsigned int* __restrict__ plane_max,
+                                   float gamma, int* __restrict__ fails, float* __restrict__ bar_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* cs = cand_sim + static_cast<size_t>(b) * kc;
+  const int* ci = cand_idx + static_cast<size_t>(b) * kc;
+  const float row_err = __uint_as_float(plane_max[0]), row_hi = __uint_as_float(plane_max[1]);
+  const float qn = q_stats[b * 4 + 0], qe = q_stats[b * 4 + (q_planes == 1 ? 1 : 2)];
+  const float qp = qn + qe;                         // >= ||q_planes||
+  const float eps = __fmul_ru(qn, row_err) + __fmul_ru(qe, row_hi) + __fmul_ru(gamma, __fmul_ru(qp, row_hi));
+  const float bar = __fsub_rd(cs[need - 1], __fmul_ru(2.f, eps));
+  bar_out[b] = bar;                                 // list entries below the bar cannot be in the exact top-`need`
+  if (ci[kc - 1] < 0) return;                       // fewer than kc rows in play: the list holds them all
+  if (!(cs[kc - 1] < bar)) atomicAdd(fails, 1);     // (a NaN score fails the certificate too)
+}
+
 // ---- rescore ------------------------------------------------------------------------------------
+// `bar` (optional, per query): candidates whose swept score lies below it are dropped instead of re-scored (certified
+// sweep: they provably cannot belong to the exact top-2k).
 template <typename RowT>
 __global__ void rescore_kernel(const RowT* __restrict__ rows, int dim, const float* __restrict__ qn,
-                               const int* __restrict__ cand_idx, int total, int kc, float* __restrict__ cand_sim) {
+                               int* __restrict__ cand_idx, int total, int kc, float* __restrict__ cand_sim,
+                               const float* __restrict__ bar) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= total) return;
   const int idx = cand_idx[w];
-  if (idx < 0) {
-    if (lane == 0) cand_sim[w] = -INFINITY;
+  const int b = w / kc;
+  if (idx < 0 || (bar && cand_sim[w] < bar[b])) {
+    __syncwarp();
+    if (lane == 0) { cand_sim[w] = -INFINITY; cand_idx[w] = -1; }
     return;
   }
-  const int b = w / kc;
   const RowT* r = rows + static_cast<size_t>(idx) * dim;
   const float* q = qn + static_cast<size_t>(b) * dim;
   float acc = 0.f;
@@ -402,18 +433,28 @@ int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, flo
   return 0;
 }
 
-int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, const int* cand_idx, int B, int kc,
-                   float* cand_sim, cudaStream_t stream) {
+int launch_certificate(const float* cand_sim, const int* cand_idx, int B, int kc, int need, const float* q_stats, int q_planes,
+                       const unsigned int* plane_max, int dim, int* fails, float* bar, cudaStream_t stream) {
+  if (need < 1 || need > kc) return fail("certificate: need must lie in [1, kc]");
+  const float gamma = static_cast<float>(dim) * 2.384185791015625e-07f;   // dim * 2^-22
+  certificate_kernel<<<static_cast<int>(ceil_div(B, 128)), 128, 0, stream>>>(cand_sim, cand_idx, B, kc, need, q_stats, q_planes,
+                                                                              plane_max, gamma, fails, bar);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, int* cand_idx, int B, int kc,
+                   float* cand_sim, cudaStream_t stream, const float* bar) {
   if (dim % 8 != 0) return fail("rescore needs dim % 8 == 0");
   const int total = B * kc;
   const int threads = 256;
   const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(total) * 32, threads));
   if (rows_are_bf16)
     rescore_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(rows), dim, qn,
-                                                                   cand_idx, total, kc, cand_sim);
+                                                                   cand_idx, total, kc, cand_sim, bar);
   else
     rescore_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(rows), dim, qn, cand_idx, total, kc,
-                                                           cand_sim);
+                                                           cand_sim, bar);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

@@ -54,7 +54,9 @@ enum {
   DEWI_FLAG_SCOPE_FULL = 1 << 5,       /* (non-reference) blend over the whole corpus; unsupported */
   DEWI_FLAG_NO_PAIR = 1 << 6,          /* B > 128: keep the 1-CTA sweep instead of the CTA-pair one  */
   DEWI_FLAG_NO_SEED = 1 << 7,          /* skip the sample pre-pass that seeds admission thresholds    */
-  DEWI_FLAG_NO_M64 = 1 << 8            /* B <= 64: keep M = 128 MMAs instead of M = 64                */
+  DEWI_FLAG_NO_M64 = 1 << 8,           /* B <= 64: keep M = 128 MMAs instead of M = 64                */
+  DEWI_FLAG_NO_CERT = 1 << 9           /* fp32 corpus: always sweep the full hi/lo product (3 MMAs, both planes) instead
+                                          of the certified single-plane sweep (hi plane + proof + exact re-score)       */
 };
 
 /* ---- library ------------------------------------------------------------------------------ */
@@ -140,6 +142,9 @@ DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int
                       int flags, int64_t* out_id, float* out_score, void* stream);
 /* Kernel launches issued by the last search on this handle (bench.py's `gpu_launches`). */
 DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
+/* fp32 corpus: searches answered by the certified single-plane sweep so far, and how many of those had to be re-run
+ * with the full hi/lo product because the certificate could not be given.                                   */
+DEWI_API int dewi_index_cert_stats(const dewi_index_t* h, int64_t* used, int64_t* failed);
 
 /* Measurement aid: while enabled, every search brackets its sweep kernel (stage 1's dominant launch)
  * with a CUDA event pair on the caller's stream, kept in a ring of 64 (no synchronisation is added to

@@ -343,3 +343,46 @@ def test_precise_query_small_batch():
     rid, rsc = osearch.exact_search_batch(emb16, pay[:, 0], entropy_column(pay), queries, k, 0.3, 0.5, True)
     for q in range(b):  # with both query planes the sweep is as exact as the fp32 one
         check_topk(rid[q], rsc[q], ids[q], sc[q], what=f"q{q}")
+
+
+@pytest.mark.parametrize("b", [5, 200])
+def test_certified_single_plane_sweep_is_exact(b):
+    """fp32 corpus swept through its bf16 hi plane only (half the bytes / a third of the MMAs) + certificate + exact
+    re-score: same answers as the full hi/lo product and as the oracle; the certificate held for every query."""
+    n, d, k = 120_000, 768, 10
+    emb, pay = make_corpus(n, d, seed=91)
+    ix = bulk_index(emb, pay)
+    q = np.random.RandomState(92).standard_normal((b, d)).astype(np.float32)
+    used0, failed0 = ix._backend.cert_stats()
+    ids, sc = ix.search_batch(q, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_FORCE_TC)
+    used1, failed1 = ix._backend.cert_stats()
+    assert used1 == used0 + 1 and failed1 == failed0, "the certified sweep did not run, or its certificate failed"
+    ids3, sc3 = ix.search_batch(q, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_FORCE_TC | _native.FLAG_NO_CERT)
+    assert ix._backend.cert_stats() == (used1, failed1)
+    np.testing.assert_array_equal(ids, ids3)
+    np.testing.assert_array_equal(sc, sc3)          # both orders come from the same exact fp32 re-score
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), q[:24], k, 0.3, 0.5, True)
+    for i in range(min(b, 24)):
+        check_topk(rid[i], rsc[i], ids[i], sc[i], what=f"certified B={b} q{i}")
+
+
+def test_certificate_failure_falls_back_to_the_full_product():
+    """Scores packed more densely than the rounding bound resolves: 300 rows within 2e-4 of each other at the top.
+    The certificate cannot be given, the batch is re-run with the hi/lo product, and the answer is still exact."""
+    n, d, k = 60_000, 768, 10
+    rng = np.random.RandomState(93)
+    emb, pay = make_corpus(n, d, seed=94)
+    target = rng.standard_normal(d).astype(np.float32)
+    target /= np.linalg.norm(target)
+    for j, row in enumerate(rng.choice(n, 300, replace=False)):
+        v = target + (2e-3 + 1e-6 * j) * rng.standard_normal(d).astype(np.float32)
+        emb[row] = v / np.linalg.norm(v)
+    ix = bulk_index(emb, pay)
+    q = np.stack([target, rng.standard_normal(d).astype(np.float32)])
+    used0, failed0 = ix._backend.cert_stats()
+    ids, sc = ix.search_batch(q, k=k, eta=0.0, entropy_pref=0.0, flags=_native.FLAG_FORCE_TC)
+    used1, failed1 = ix._backend.cert_stats()
+    assert used1 == used0 + 1 and failed1 == failed0 + 1
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), q, k, 0.0, 0.0, True)
+    for i in range(2):
+        check_topk(rid[i], rsc[i], ids[i], sc[i], what=f"fallback q{i}")
