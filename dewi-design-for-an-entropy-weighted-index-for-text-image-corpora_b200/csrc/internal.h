@@ -61,6 +61,10 @@ struct SweepSeed {
   const float* values = nullptr;
   int stride = 0, off = 0, n_queries = 0;
   float* max_out = nullptr;
+  // pre-pass granularity: 0 = one maximum per work item, [item][128]; 1 = one per 32-row group of every tile,
+  // [tile * (N_TILE / 32) + group][n_qb][128] -- many more (still distinct-row) maxima from a small sample, which is
+  // what a long candidate list (the certified sweep) needs for a useful seed
+  int max_groups = 0;
 };
 
 // ---- tcgen05 sweep (search_tc.cu) ------------------------------------------------------------

@@ -35,8 +35,13 @@ constexpr int kSampleRuns = 1024;                // evenly spaced runs of ...
 constexpr int kSampleRunLen = 1024;              // ... contiguous elements (coalesced)
 constexpr int kSample = kSampleRuns * kSampleRunLen;
 constexpr int kSampleBlockRuns = 4;              // runs a sample_kernel block gathers per trip (16 loads per thread in flight)
+constexpr int kSampleBlocks = 64;                // blocks per column (4 trips each)
 constexpr int kSampleMargin = 4096;              // +- sample ranks: 8 sigma of a 2^20 sample's median rank
-constexpr int kFitFusedDefault = 1;              // window pass with the in-window histogram fused in (DEWI_FIT_FUSED)
+// Window pass with the in-window histogram fused in (DEWI_FIT_FUSED=1) or as a launch of its own (0).  Measured at
+// 100M x 7 (CUDA events in-stream, warm): fused 483-498 us per pass, separate 445-451 + 20 us -- the extra live state
+// costs the streaming loop more than the launch it saves, so the separate histogram is the default.
+constexpr int kFitFusedDefault = 0;
+constexpr int kWindowDigitBits = 9;              // window-relative digit of the in-window selection (512 bins)
 constexpr int kSurvCap = 8192;                   // keys of the target bins sorted in shared memory (typically a few hundred)
 
 struct SelState {
@@ -69,11 +74,16 @@ __device__ __forceinline__ float from_orderable(unsigned int o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
 }
 
+constexpr int kSamplePass1 = 3;   // pass id of the sample selection's second, coarser digit
+
 __device__ __forceinline__ void pass_bits(int pass, int& shift, int& nbins, unsigned int& himask) {
   // pass 0: bits 31..21, pass 1: bits 20..10, pass 2: bits 9..0
+  // pass 3 (sample selection only, after pass 0): bits 20..13 -- 256 bins instead of 2048, an eighth of the global
+  // atomics when the blocks hand their histograms over; the window bounds round outwards by 2^13 keys instead of 2^10
   if (pass == 0) { shift = 21; nbins = 2048; himask = 0u; }
   else if (pass == 1) { shift = 10; nbins = 2048; himask = 0xFFE00000u; }
-  else { shift = 0; nbins = 1024; himask = 0xFFFFFC00u; }
+  else if (pass == 2) { shift = 0; nbins = 1024; himask = 0xFFFFFC00u; }
+  else { shift = 13; nbins = 256; himask = 0xFFE00000u; }
 }
 
 // Key sources.  RAW: fp32 column value; DEV: |v - med| in fp32 (scorer.py:24); KEYS: a buffer of keys.
@@ -93,17 +103,18 @@ __device__ void pick_column(int pass, int c, SelState* st, unsigned int* ghist, 
 // What the last block of a selection pass does after it has picked its bins.
 enum { OP_NONE = 0, OP_WINDOW_BOUNDS = 1 };
 
-// The sample selection resolved the top 22 bits (passes 0 and 1) of the keys at sample ranks s/2 -+ margin: rounding
-// the first down and the second up to a multiple of 1024 keeps the window conservative (a third pass would buy
-// < 0.01 % fewer window keys for one more launch).  Also sizes the window-relative digit of the in-window selection.
+// The sample selection resolved the top 19 bits (pass 0 and the coarse pass 3) of the keys at sample ranks
+// s/2 -+ margin: rounding the first down and the second up to a multiple of 2^13 keeps the window conservative (finer
+// digits would buy a few per cent fewer window keys for more atomics or another launch).  Also sizes the
+// window-relative digit of the in-window selection.
 __device__ __forceinline__ void arm_window(SelState* st, int c) {
-  const unsigned int lo = st->prefix[c][0] & 0xFFFFFC00u, hi = st->prefix[c][1] | 0x3FFu;
+  const unsigned int lo = st->prefix[c][0] & 0xFFFFE000u, hi = st->prefix[c][1] | 0x1FFFu;
   st->lo[c] = lo;
   st->hi[c] = hi;
   st->below[c] = 0ull;
   st->wcnt[c] = 0u;
-  const int nbits = 32 - __clz(static_cast<int>(hi - lo));   // hi - lo >= 0x3FF
-  st->wshift[c] = max(nbits - 11, 0);
+  const int nbits = 32 - __clz(static_cast<int>(hi - lo));   // hi - lo >= 0x1FFF
+  st->wshift[c] = max(nbits - kWindowDigitBits, 0);
 }
 
 // State of a fresh sample selection: ranks s/2 -+ margin of the kSample sample keys.
@@ -313,7 +324,7 @@ __global__ void glue_kernel(int op, int f, long long n, unsigned int window_cap,
 template <int SRC>
 __global__ void __launch_bounds__(256)
 sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelState* st, unsigned int* __restrict__ skeys,
-              unsigned int* __restrict__ ghist, unsigned int* __restrict__ done) {
+              unsigned int* __restrict__ ghist, unsigned int* __restrict__ done, long long run_step, int run_rem) {
   __shared__ __align__(8) unsigned int sh[2 * kBins];   // slot-0 histogram; reused as 2048 x u64 by pick_column
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned int ticket;
@@ -330,8 +341,9 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelStat
     unsigned int key[kSampleBlockRuns * kPer];
 #pragma unroll
     for (int r = 0; r < kSampleBlockRuns; ++r) {
-      const int run = min(run0 + r, kSampleRuns - 1);
-      const long long start = static_cast<long long>((static_cast<__int128>(run) * (n - kSampleRunLen)) / (kSampleRuns - 1));
+      const long long run = min(run0 + r, kSampleRuns - 1);
+      // run * (n - L) / (R - 1) with the quotient and remainder of (n - L) / (R - 1) from the host (no wide division here)
+      const long long start = run * run_step + (run * run_rem) / (kSampleRuns - 1);
 #pragma unroll
       for (int u = 0; u < kPer; ++u) key[r * kPer + u] = load_key<SRC>(col, start + u * 256 + threadIdx.x, med);
     }
@@ -922,13 +934,15 @@ StageTimer g_fit_timer;
 template <int SRC>
 void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsigned int cap, FitWork& w, int final_op,
                        cudaStream_t stream) {
-  sample_kernel<SRC><<<dim3(kSampleRuns / kSampleBlockRuns, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done);
+  sample_kernel<SRC><<<dim3(kSampleBlocks, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done,
+                                                                   (n - kSampleRunLen) / (kSampleRuns - 1),
+                                                                   static_cast<int>((n - kSampleRunLen) % (kSampleRuns - 1)));
   g_fit_timer.mark(stream, "sample");
   {
     const int threads = 512, per_thread = 8;
     const int bx = static_cast<int>(std::min<int64_t>(ceil_div(kSample, threads * per_thread), std::max(1, w.sm_count * 4 / f)));
-    hist_kernel<SRC_KEYS><<<dim3(std::max(bx, 1), f), threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, 1, w.st, w.ghist,
-                                                                             w.done, OP_WINDOW_BOUNDS);
+    hist_kernel<SRC_KEYS><<<dim3(std::max(bx, 1), f), threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, kSamplePass1, w.st,
+                                                                             w.ghist, w.done, OP_WINDOW_BOUNDS);
   }
   g_fit_timer.mark(stream, "hist");
   if (env_int("DEWI_FIT_FUSED", kFitFusedDefault)) {
@@ -937,10 +951,10 @@ void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsi
   } else {
     window_kernel<SRC, 0><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
     g_fit_timer.mark(stream, "window");
-    window_hist_kernel<<<dim3(std::max(1, w.sm_count * 2 / f), f), kWhistThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.ghist);
+    window_hist_kernel<<<dim3(std::max(1, w.sm_count * 4 / f), f), kWhistThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.ghist);
     g_fit_timer.mark(stream, "whist");
   }
-  survivor_kernel<<<dim3(std::max(1, w.sm_count / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op);
+  survivor_kernel<<<dim3(std::max(1, w.sm_count * 4 / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op);
   g_fit_timer.mark(stream, "survivor");
 }
 

@@ -51,6 +51,7 @@ struct TcArgs {
   const float* seed;  // optional admission thresholds from the sample pre-pass (see seed_threshold)
   int seed_stride, seed_off, n_queries;
   float* max_out;     // pre-pass mode: [item][128] maximum score per query, no candidate lists
+  int max_groups;     // pre-pass mode: one maximum per 32-row group of every tile instead (SweepSeed::max_groups)
 };
 
 // QRES = 1 ("queries resident"; single query block, M = 64): all dim/64 query k-blocks are loaded ONCE and stay in
@@ -266,7 +267,10 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * N_TILE);
         const int row_base = t * N_TILE;
-        if (a.max_out) best = max_tile<N_TILE>(best, tcol, row_base, a.n_rows);
+        if (a.max_out && a.max_groups)
+          max_groups_tile<N_TILE>(a.max_out + static_cast<size_t>(item % a.n_qb) * kQueryBlock + qlane,
+                                  static_cast<size_t>(a.n_qb) * kQueryBlock, t, tcol, row_base, a.n_rows);
+        else if (a.max_out) best = max_tile<N_TILE>(best, tcol, row_base, a.n_rows);
         else scan_tile<N_TILE>(l, kc, tcol, row_base, a.n_rows);
         ptx::tc_fence_before();
         __syncwarp();
@@ -274,7 +278,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
-      if (a.max_out) a.max_out[static_cast<size_t>(item) * kQueryBlock + qlane] = best;
+      if (a.max_out) { if (!a.max_groups) a.max_out[static_cast<size_t>(item) * kQueryBlock + qlane] = best; }
       else flush_item(l, kc, a.part_s + static_cast<size_t>(item) * kc * kQueryBlock + qlane,
                       a.part_i + static_cast<size_t>(item) * kc * kQueryBlock + qlane);
     }
@@ -419,6 +423,7 @@ int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, 
   a.seed_off = seed.off;
   a.n_queries = seed.n_queries;
   a.max_out = seed.max_out;
+  a.max_groups = seed.max_groups;
   if (plan.q_rows == 64) {
     if (plan.q_resident) {
       if (plan.mode == 0 && plan.n_tile == 256) return launch_one<0, 256, 64, 1>(plan, e0, e1, q0, q1, a, stream);

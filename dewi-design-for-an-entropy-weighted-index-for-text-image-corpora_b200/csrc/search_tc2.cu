@@ -319,7 +319,10 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
         const uint32_t tcol = tmem_lane + static_cast<uint32_t>(acc * kNTile);
-        if (EPI == EPI_TOPK && a.max_out) best = max_tile<kNTile>(best, tcol, t * kNTile, a.n_rows);
+        if (EPI == EPI_TOPK && a.max_out && a.max_groups)
+          max_groups_tile<kNTile>(a.max_out + static_cast<size_t>(qb) * kQueryBlock + qlane, static_cast<size_t>(n_qb) * kQueryBlock, t,
+                                  tcol, t * kNTile, a.n_rows);
+        else if (EPI == EPI_TOPK && a.max_out) best = max_tile<kNTile>(best, tcol, t * kNTile, a.n_rows);
         else if (EPI == EPI_TOPK) scan_tile<kNTile>(l, kc, tcol, t * kNTile, a.n_rows);
         else if (a.sym)
           join_scan_tile_sym<kColsPerWarp>(jr, a, i_row + a.a_offset, lane, tcol + col0, t * kNTile + col0, o == 0, lbv, col_cache);
@@ -337,7 +340,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
         if (acc == 0) acc_phase ^= 1;
       }
       if (EPI == EPI_TOPK && a.max_out) {
-        a.max_out[(static_cast<size_t>(chunk) * n_qb + qb) * kQueryBlock + qlane] = best;
+        if (!a.max_groups) a.max_out[(static_cast<size_t>(chunk) * n_qb + qb) * kQueryBlock + qlane] = best;
       } else if (EPI == EPI_TOPK) {
         const size_t slot = (static_cast<size_t>(chunk) * n_qb + qb) * kc * kQueryBlock + qlane;
         flush_item(l, kc, a.part_s + slot, a.part_i + slot);
@@ -454,6 +457,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.seed_off = seed.off;
   a.n_queries = seed.n_queries;
   a.max_out = seed.max_out;
+  a.max_groups = seed.max_groups;
   a.m_rows = 0;
   a.tau = 0.f;
   a.self_join = 0;
@@ -535,6 +539,7 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.seed = nullptr;
   a.seed_stride = a.seed_off = a.n_queries = 0;
   a.max_out = nullptr;
+  a.max_groups = 0;
   a.m_rows = static_cast<int>(m_rows);
   a.tau = tau;
   a.self_join = self_join;

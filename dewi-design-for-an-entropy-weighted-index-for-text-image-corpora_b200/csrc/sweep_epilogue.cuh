@@ -177,6 +177,27 @@ __device__ __forceinline__ float max_tile(float best, uint32_t tcol, int row_bas
   return best;
 }
 
+// Pre-pass epilogue, fine granularity: the maximum of every 32-row group of the tile, written to
+// out[(tile * G + group) * n_qb * 128] (G = N_TILE / 32; `out` already points at this query's column).
+template <int N_TILE>
+__device__ __forceinline__ void max_groups_tile(float* out, size_t group_stride, int tile, uint32_t tcol, int row_base, int n_rows) {
+#pragma unroll 1
+  for (int c = 0; c < N_TILE / 32; ++c) {
+    float v[32];
+    ptx::tmem_ld_32x32(tcol + c * 32, v);
+    const int r0 = row_base + c * 32;
+    if (r0 + 32 > n_rows) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (r0 + j >= n_rows) v[j] = -INFINITY;
+    }
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) m = fmaxf(m, v[j]);
+    out[(static_cast<size_t>(tile) * (N_TILE / 32) + c) * group_stride] = m;
+  }
+}
+
 // End of a work item: keep the kc best and write them as [k][query] partials.
 __device__ __forceinline__ void flush_item(LaneList& l, int kc, float* ps, int* pi) {
   lane_prune(l, kc);
