@@ -100,6 +100,8 @@ struct dewi_index {
   // certified single-plane sweep (fp32 corpus): running maxima of ||row - hi|| and ||hi|| (float bits), a fail counter
   unsigned int* plane_max = nullptr;   // [2] plane maxima, [2] = certificate fail counter
   long long cert_used = 0, cert_failed = 0;   // searches answered by the certified sweep / re-run with the full product
+  bool plane_max_stale = false;               // plane_max changed on the device since plane_hi_max was read
+  float plane_hi_max = 0.f;                   // host copy of max_r ||hi_r|| (fp16 planes: range guard)
   // cached tensor maps of the corpus planes
   CUtensorMap map_e0, map_e1;
   int64_t map_rows = -1;
@@ -337,7 +339,9 @@ int dewi_index_append(dewi_index_t* h, const float* rows, int64_t n, int normali
     const size_t off = static_cast<size_t>(h->n + done) * d;
     DEWI_TRY(launch_prep_corpus(src, m, h->dim, do_norm, h->rows_f32 ? h->rows_f32 + off : nullptr,
                                 h->plane0 ? h->plane0 + off : nullptr, h->plane1 ? h->plane1 + off : nullptr,
-                                h->bad_flag, stream, h->dtype == DEWI_DTYPE_FP32 ? h->plane_max : nullptr));
+                                h->bad_flag, stream, h->dtype == DEWI_DTYPE_FP32 ? h->plane_max : nullptr,
+                                h->dtype == DEWI_DTYPE_FP32 ? 1 : 0));
+    if (h->dtype == DEWI_DTYPE_FP32) h->plane_max_stale = true;
     if (src_is_host) {
       DEWI_CUDA(cudaEventRecord(h->stage_free[buf], stream));
       used[buf] = 1;
@@ -474,8 +478,11 @@ int dewi_index_get_payload(dewi_index_t* h, int64_t offset, int64_t n, float* de
   return 0;
 }
 
+// `rerank` (single shard only): when the fused tail runs, the DEWI blend and the final top-k happen in the same launch
+// and *rerank_done is set; otherwise the caller re-ranks the local outputs itself.
 static int search_local_impl(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
-                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push);
+                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push,
+                             const TailRerank* rerank = nullptr, bool* rerank_done = nullptr);
 
 int dewi_index_search_local(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_) {
@@ -512,8 +519,10 @@ int dewi_index_search_local_push(dewi_index_t* h, const float* queries, int B, i
 }
 
 static int search_local_impl(dewi_index_t* h, const float* queries, int B, int kcand, int flags, float* out_sim,
-                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push) {
+                             int64_t* out_id, float* out_dewi, float* out_ent, void* stream_, const PeerPush* push,
+                             const TailRerank* rerank, bool* rerank_done) {
   if (!h) return fail("null handle");
+  if (rerank_done) *rerank_done = false;
   if (B <= 0 || kcand <= 0) return fail("B and kcand must be positive");
   if (h->n <= 0) return fail("index is empty");
   if (flags & DEWI_FLAG_SCOPE_FULL) return fail("full-corpus blend scope is not implemented (not the reference's semantics)");
@@ -527,6 +536,22 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
 
   bool use_tc = h->space == DEWI_SPACE_COSINE && h->plane0 && tc_supported(dim, h->n) && !(flags & DEWI_FLAG_FORCE_SIMT) &&
                 (h->n >= kTcMinRows || (flags & DEWI_FLAG_FORCE_TC));
+  const int fp16_planes = h->dtype == DEWI_DTYPE_FP32 ? 1 : 0;
+  if (use_tc && fp16_planes) {
+    // The planes of an fp32 corpus are fp16: rows handed in as "already normalised" that are far from unit norm
+    // could leave its range (products would overflow) -- such a corpus is swept on the CUDA cores instead.
+    if (h->plane_max_stale) {
+      unsigned int bits = 0;
+      DEWI_CUDA(cudaMemcpyAsync(&bits, h->plane_max + 1, sizeof(bits), cudaMemcpyDeviceToHost, stream));
+      DEWI_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(&h->plane_hi_max, &bits, 4);
+      h->plane_max_stale = false;
+    }
+    if (!(h->plane_hi_max <= 64.f)) {
+      if (flags & DEWI_FLAG_FORCE_TC) return fail("rows too far from unit norm for the fp16 planes of the tensor-core sweep");
+      use_tc = false;
+    }
+  }
   int mode = (h->dtype == DEWI_DTYPE_FP32) ? 2 : ((flags & DEWI_FLAG_PRECISE_QUERY) ? 1 : 0);
   // list capacity: over-fetch so that rounding in the bf16-plane sweep cannot push a true top-2k row out
   int kc = (mode == 0) ? std::max(32, kc_valid + 16) : kc_valid + 8;
@@ -552,21 +577,21 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     }
     return tc_make_plan(mode_, dim, h->n, n_qb, kc_, h->sm_count, &plan, 0, q_rows) == 0;
   };
-  // CERTIFIED single-plane sweep (fp32 corpus).  The hi plane alone -- half the bytes of the hi/lo stream below the
-  // ridge, a third of its MMAs above -- is swept with a longer candidate list; a certificate (select.cu) then proves,
-  // from rigorous bounds on the two bf16 roundings, that the list holds the exact top-2k, and the exact fp32 re-score
-  // orders it.  Small batches use both query planes (their MMAs are free there and halve the bound), CTA pairs one.
-  // When the certificate cannot be given for some query (scores packed more densely than the bound resolves) the batch
-  // is re-run with the full hi/lo product: results are exact either way.
+  // CERTIFIED single-plane sweep (fp32 corpus).  The fp16 hi plane alone -- half the bytes of the hi/lo stream below
+  // the ridge, a third of its MMAs above -- is swept with a longer candidate list; a certificate (select.cu) then
+  // proves, from rigorous bounds on the two fp16 roundings and the fp32 accumulation, that the list holds the exact
+  // top-2k, and the exact fp32 re-score orders it.  When the certificate cannot be given for some query (scores packed
+  // more densely than the bound resolves) the batch is re-run with the full hi/lo product: exact either way.
   int cert_planes = 0;
   if (use_tc && mode == 2 && !(flags & DEWI_FLAG_NO_CERT) && env_int("DEWI_CERT", 1) != 0 &&
       static_cast<int64_t>(h->n) * dim >= kCertMinElems) {
-    const bool pair_intent = n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
-    const int planes = pair_intent ? 1 : 2;
-    // list capacity: ~46 (one query plane) / ~31 (two) rows are expected inside the proof's margin at k = 10 on Gaussian
-    // rows, Poisson-distributed; 80 / 64 slots put an overflow (-> the batch re-run) below 1e-5 per query.  Measured at
-    // 1M x 768, B = 4096 (CTA pairs, one MMA): 96 slots 640, 80 slots 700, 64 slots 766 TFLOP/s -- the lists cost ring stages.
-    int cert_kc = std::max(pair_intent ? 80 : 64, kc_valid * (pair_intent ? 4 : 3) + (pair_intent ? 0 : 4));
+    const int planes = 1;
+    // List capacity.  With fp16 planes the bound is eps ~ 6e-4 at dim 768 (2.1e-4 per rounded operand, 1.8e-4 for the
+    // accumulation): ~23 rows are expected inside the proof's margin at k = 10 on 1M Gaussian rows, with a heavier
+    // than Poisson tail across queries (the 2k-th best score itself fluctuates); 48 slots keep the re-run rare and
+    // are what fits beside five ring stages (CTA pairs) / the resident query block (B <= 64).  (bf16 planes would need
+    // ~49 expected, 82 seen in 1024 queries -- and every 16 more slots cost the CTA-pair sweep ~9 % at B = 4096.)
+    int cert_kc = std::max(48, kc_valid * 2 + 8);
     if (env_set("DEWI_CERT_KC")) cert_kc = std::max(kc_valid + 1, env_int("DEWI_CERT_KC", cert_kc));   // experiments
     if (make_plans(planes == 1 ? 0 : 1, cert_kc) && (use_pair || plan.n_stages >= 3)) {
       cert_planes = planes;
@@ -594,7 +619,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   if (cert_planes) DEWI_TRY(h->qstats.ensure(static_cast<size_t>(b_pad) * 16));
   DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
                                h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/(use_tc && !use_pair && q_rows == 64) ? 2 : 1,
-                               cert_planes ? h->qstats.as<float>() : nullptr));
+                               cert_planes ? h->qstats.as<float>() : nullptr, fp16_planes));
   h->last_launches++;
 
   const void* exact_rows = h->rows_f32 ? static_cast<const void*>(h->rows_f32) : static_cast<const void*>(h->plane0);
@@ -624,11 +649,11 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
         const int64_t sync_words = tc2_sync_words(p2, rows, n_qb);
         if (sync_words > 0) DEWI_TRY(h->sync_cnt.ensure(static_cast<size_t>(sync_words) * 4));
         DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                            h->part_i.as<int>(), sd, stream, sync_words > 0 ? h->sync_cnt.as<unsigned int>() : nullptr));
+                            h->part_i.as<int>(), sd, stream, sync_words > 0 ? h->sync_cnt.as<unsigned int>() : nullptr, fp16_planes));
       }
       else
         DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                           h->part_i.as<int>(), sd, stream));
+                           h->part_i.as<int>(), sd, stream, fp16_planes));
       h->last_launches++;
       return 0;
     };
@@ -700,12 +725,34 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   parts.n_qb = n_qb;
   parts.kc = kc;
 
+  int* fails_dev = reinterpret_cast<int*>(h->plane_max + 2);
+  if (tail_supported(kc, kcand, rerank ? rerank->k : 1) && env_int("DEWI_FUSED_TAIL", 1) != 0) {
+    // ONE launch for everything after the sweep (select.cu: tail_kernel)
+    TailCert cert{h->qstats.as<float>(), cert_planes, h->plane_max, kc_valid, fails_dev};
+    if (cert_planes) DEWI_CUDA(cudaMemsetAsync(fails_dev, 0, sizeof(int), stream));
+    DEWI_TRY(launch_tail(parts, B, cert_planes ? &cert : nullptr, use_tc ? exact_rows : nullptr, exact_is_bf16, dim, h->qn.as<float>(),
+                         kcand, h->id_base, h->dewi_col, h->ent_col, out_sim, out_id, out_dewi, out_ent, push, rerank, stream));
+    h->last_launches++;
+    if (cert_planes) {
+      int fails = 0;
+      DEWI_CUDA(cudaMemcpyAsync(&fails, fails_dev, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      DEWI_CUDA(cudaStreamSynchronize(stream));
+      h->cert_used++;
+      if (fails > 0 && env_int("DEWI_CERT_IGNORE", 0)) fails = 0;   // experiments (timing only: results may be inexact)
+      if (fails > 0) {   // not provable for `fails` queries: the whole batch again with the full hi/lo product
+        h->cert_failed++;  // (a peer push was withheld by the kernel: the re-run publishes)
+        return search_local_impl(h, queries, B, kcand, flags | DEWI_FLAG_NO_CERT, out_sim, out_id, out_dewi, out_ent, stream_, push,
+                                 rerank, rerank_done);
+      }
+    }
+    if (rerank && rerank_done) *rerank_done = true;
+    return 0;
+  }
   DEWI_TRY(h->cand_idx.ensure(static_cast<size_t>(B) * kc * 4));
   DEWI_TRY(h->cand_sim.ensure(static_cast<size_t>(B) * kc * 4));
   DEWI_TRY(launch_merge_select(parts, B, kc, h->cand_idx.as<int>(), h->cand_sim.as<float>(), stream));
   h->last_launches++;
   if (cert_planes) {
-    int* fails_dev = reinterpret_cast<int*>(h->plane_max + 2);
     DEWI_CUDA(cudaMemsetAsync(fails_dev, 0, sizeof(int), stream));
     DEWI_TRY(h->qbar.ensure(static_cast<size_t>(B) * 4));
     DEWI_TRY(launch_certificate(h->cand_sim.as<float>(), h->cand_idx.as<int>(), B, kc, kc_valid, h->qstats.as<float>(), cert_planes,
@@ -718,7 +765,8 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     if (fails > 0 && env_int("DEWI_CERT_IGNORE", 0)) fails = 0;   // experiments (timing only: results may be inexact)
     if (fails > 0) {   // not provable for `fails` queries: the whole batch again with the full hi/lo product
       h->cert_failed++;
-      return search_local_impl(h, queries, B, kcand, flags | DEWI_FLAG_NO_CERT, out_sim, out_id, out_dewi, out_ent, stream_, push);
+      return search_local_impl(h, queries, B, kcand, flags | DEWI_FLAG_NO_CERT, out_sim, out_id, out_dewi, out_ent, stream_, push,
+                               rerank, rerank_done);
     }
   }
   if (use_tc) {
@@ -786,8 +834,6 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   DEWI_TRY(h->loc_id.ensure(nc * 8));
   DEWI_TRY(h->loc_dewi.ensure(nc * 4));
   DEWI_TRY(h->loc_ent.ensure(nc * 4));
-  DEWI_TRY(dewi_index_search_local(h, q_dev, B, kcand, flags, h->loc_sim.as<float>(), h->loc_id.as<int64_t>(),
-                                   h->loc_dewi.as<float>(), h->loc_ent.as<float>(), stream_));
   int64_t* d_id = out_id;
   float* d_sc = out_score;
   if (host_io) {
@@ -800,9 +846,15 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   const float w_sim = static_cast<float>(1.0 - eta);
   const float w_dewi = static_cast<float>(eta);
   const float pref = static_cast<float>(entropy_pref);
-  DEWI_TRY(launch_rerank(h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(), h->loc_ent.as<float>(),
-                         B, 1, kcand, 0, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
-  h->last_launches++;
+  const TailRerank rr{k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc};
+  bool reranked = false;
+  DEWI_TRY(search_local_impl(h, q_dev, B, kcand, flags, h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(),
+                             h->loc_ent.as<float>(), stream_, nullptr, &rr, &reranked));
+  if (!reranked) {
+    DEWI_TRY(launch_rerank(h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(), h->loc_ent.as<float>(),
+                           B, 1, kcand, 0, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
+    h->last_launches++;
+  }
   if (host_io) {
     DEWI_CUDA(cudaMemcpyAsync(out_id, d_id, static_cast<size_t>(B) * k * 8, cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaMemcpyAsync(out_score, d_sc, static_cast<size_t>(B) * k * 4, cudaMemcpyDeviceToHost, stream));

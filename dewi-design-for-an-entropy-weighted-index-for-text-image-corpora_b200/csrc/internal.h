@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -86,7 +87,7 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
 int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream);
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes = 0);
 
 // ---- tcgen05 sweep on CTA pairs, for more than one query block (search_tc2.cu) -----------------
 struct Tc2Plan {
@@ -103,7 +104,7 @@ int tc2_box_rows();
 int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb);
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt = nullptr);
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt = nullptr, int fp16_planes = 0);
 
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
                     int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,
@@ -142,23 +143,46 @@ struct PeerPush {
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
                           float* out_ent, cudaStream_t stream, const PeerPush* push = nullptr);
+// Fused tail (select.cu: tail_kernel): merge -> [certificate] -> exact re-score -> order + payload (+ peer push) -> [blend +
+// top-k on a single shard] in ONE launch, one block per query.
+struct TailCert {          // certificate of the single-plane sweep
+  const float* q_stats;
+  int q_planes;
+  const unsigned int* plane_max;
+  int need;
+  int* fails;
+};
+struct TailRerank {        // single shard: DEWI blend and final top-k in the same launch
+  int k;
+  float w_sim, w_dewi, pref;
+  int use_pref;
+  int64_t* out_id;
+  float* out_score;
+};
+int tail_supported(int kc, int kcand, int k);
+int launch_tail(const Partials& p, int B, const TailCert* cert, const void* rows, int rows_are_bf16, int dim, const float* qn, int kcand,
+                int64_t id_base, const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi, float* out_ent,
+                const PeerPush* push, const TailRerank* rr, cudaStream_t stream);
 int launch_rerank(const float* sim, const int64_t* id, const float* dewi, const float* ent, int B, int n_shards, int kcand,
                   int64_t shard_stride_bytes, int cand_count, int k, float w_sim, float w_dewi, float pref, int use_pref,
                   int64_t* out_id, float* out_score, cudaStream_t stream, const unsigned int* ready_flags = nullptr,
                   unsigned int seq = 0, unsigned int* status = nullptr, double timeout_s = 120.0);
 
 // ---- operand preparation (prep.cu) -----------------------------------------------------------
-// rows fp32 [n, dim] -> optional fp32 copy (normalised), bf16 hi plane, optional bf16 lo plane.
+// rows fp32 [n, dim] -> optional fp32 copy (normalised), 16-bit hi plane, optional 16-bit lo plane.  The planes are
+// bf16 (hi = bf16(x), lo = bf16(x - hi)) or, with fp16_planes, fp16 (the same split in fp16; typed __nv_bfloat16*
+// here only as "16-bit storage").  fp16 is used for fp32 corpora: unit-norm rows stay inside its range and its
+// 11-bit significand rounds 8x finer than bf16.
 // plane_max (optional, device, 2 words): running maxima over all rows ever prepared of ||x - hi|| and ||hi|| as
 // float bit patterns -- the corpus side of the certified single-plane sweep's error bound.
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max = nullptr);
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max = nullptr, int fp16_planes = 0);
 // queries fp32 [B, dim] -> qn fp32 [b_pad, dim] (natural order), q hi/lo bf16 [b_pad, dim] (rows >= B
 // zeroed).  lane_order 1: plane row of query b is (b / 128) * 128 + query_lane(b % 128) (M = 128 sweeps);
 // lane_order 2 (b < 64 only): row (b & 3) * 16 + (b >> 2), the A-row whose M = 64 accumulator lane is query_lane(b).
 // q_stats (optional, device, [b_pad][4]): per query { ||q||, ||q - hi||, ||q - hi - lo||, ||hi|| }, rounded upwards.
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0, float* q_stats = nullptr);
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order = 0, float* q_stats = nullptr, int fp16_planes = 0);
 // bf16 -> fp32 (exact widening) of `count` contiguous elements: bulk export of a bf16-storage corpus.
 int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaStream_t stream);
 

@@ -26,6 +26,7 @@ struct Tc2Args {
   int seed_stride, seed_off, n_queries;
   float* max_out;     // pre-pass mode: [chunk][qb][128] maximum score per query, no candidate lists
   int max_groups;     // pre-pass mode: one maximum per 32-row group of every tile instead (SweepSeed::max_groups)
+  int fp16;           // operand planes hold fp16 (fp32 corpus) instead of bf16
   // EPI_JOIN: thresholded similarity join instead of candidate lists (dewi_join)
   int m_rows;                      // rows of A (the "query" side); rows >= m_rows are padding
   float tau;

@@ -19,6 +19,16 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(__fsub_rn(x, __bfloat162float(hi)));
 }
+// The same split in fp16 (22 significand bits where lo stays normal); the bit patterns travel in the 16-bit plane
+// storage.  hf / lf return the values the planes hold.
+__device__ __forceinline__ void split_fp16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo, float& hf, float& lf) {
+  const __half h = __float2half_rn(x);
+  hf = __half2float(h);
+  const __half l = __float2half_rn(__fsub_rn(x, hf));
+  lf = __half2float(l);
+  hi = __ushort_as_bfloat16(__half_as_ushort(h));
+  lo = __ushort_as_bfloat16(__half_as_ushort(l));
+}
 
 // Rounding bookkeeping for the CERTIFIED single-plane sweep (api.cu): how far the bf16 planes are from the fp32 values.
 //   row_stats[row] = { ||x||, ||x - hi||, ||x - hi - lo||, ||hi|| }   (queries: one record per query)
@@ -29,7 +39,8 @@ __device__ __forceinline__ float up(float v) { return v * 1.0009765625f + 1e-12f
 __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, long long n_out, int dim, int normalize,
                                  int guard_zero, int lane_order, float* __restrict__ dst_f32,
                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                 int* __restrict__ bad_flag, float* __restrict__ row_stats, unsigned int* __restrict__ plane_max) {
+                                 int* __restrict__ bad_flag, float* __restrict__ row_stats, unsigned int* __restrict__ plane_max,
+                                 int fp16_planes) {
   const int lane = threadIdx.x & 31;
   const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   float warp_max_err = 0.f, warp_max_hi = 0.f;
@@ -74,11 +85,18 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
       if (dst_f32) dst_f32[off + d] = x;
       if (hi) {
         __nv_bfloat16 h, l;
-        split_bf16(x, h, l);
+        float hf, lf;
+        if (fp16_planes) {
+          split_fp16(x, h, l, hf, lf);
+        } else {
+          split_bf16(x, h, l);
+          hf = __bfloat162float(h);
+          lf = __bfloat162float(l);
+        }
         hi[poff + d] = h;
         if (lo) lo[poff + d] = l;
         if (row_stats || plane_max) {
-          const float hf = __bfloat162float(h), r1 = x - hf, r2 = r1 - __bfloat162float(l);   // (both differences are exact)
+          const float r1 = x - hf, r2 = r1 - lf;   // (both differences are exact)
           sx = fmaf(x, x, sx);
           s1 = fmaf(r1, r1, s1);
           s2 = fmaf(r2, r2, s2);
@@ -109,12 +127,12 @@ __global__ void prep_rows_kernel(const float* __restrict__ src, long long n, lon
 
 int launch(const float* src, int64_t n, int64_t n_out, int dim, int normalize, int guard_zero, int lane_order,
            float* dst_f32, __nv_bfloat16* hi, __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, float* row_stats = nullptr,
-           unsigned int* plane_max = nullptr) {
+           unsigned int* plane_max = nullptr, int fp16_planes = 0) {
   if (n_out <= 0) return 0;
   const int threads = 256;
   const int64_t blocks = std::min<int64_t>(ceil_div(n_out * 32, threads), static_cast<int64_t>(current_sm_count()) * 16);
   prep_rows_kernel<<<static_cast<int>(blocks), threads, 0, stream>>>(src, n, n_out, dim, normalize, guard_zero,
-                                                                    lane_order, dst_f32, hi, lo, bad_flag, row_stats, plane_max);
+                                                                    lane_order, dst_f32, hi, lo, bad_flag, row_stats, plane_max, fp16_planes);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -139,14 +157,14 @@ int launch_widen_bf16(const __nv_bfloat16* src, int64_t count, float* dst, cudaS
 }
 
 int launch_prep_corpus(const float* src, int64_t n, int dim, int normalize, float* dst_f32, __nv_bfloat16* hi,
-                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max) {
-  return launch(src, n, n, dim, normalize, 1, 0, dst_f32, hi, lo, bad_flag, stream, nullptr, plane_max);
+                       __nv_bfloat16* lo, int* bad_flag, cudaStream_t stream, unsigned int* plane_max, int fp16_planes) {
+  return launch(src, n, n, dim, normalize, 1, 0, dst_f32, hi, lo, bad_flag, stream, nullptr, plane_max, fp16_planes);
 }
 
 int launch_prep_queries(const float* q, int B, int b_pad, int dim, int normalize, float* qn, __nv_bfloat16* hi,
-                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order, float* q_stats) {
+                        __nv_bfloat16* lo, cudaStream_t stream, int lane_order, float* q_stats, int fp16_planes) {
   // a zero query stays zero (backends.py:422-424: divide only when the norm is positive)
-  return launch(q, B, b_pad, dim, normalize, 0, lane_order, qn, hi, lo, nullptr, stream, q_stats, nullptr);
+  return launch(q, B, b_pad, dim, normalize, 0, lane_order, qn, hi, lo, nullptr, stream, q_stats, nullptr, fp16_planes);
 }
 
 }  // namespace dewi

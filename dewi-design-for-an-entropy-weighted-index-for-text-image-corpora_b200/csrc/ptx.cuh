@@ -181,6 +181,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
+// Same with A = B = fp16 (operand format field 0 instead of 1): the planes of an fp32 corpus are fp16 -- unit-norm
+// rows never leave its range, and its 11-bit significand makes the single-plane sweep's rounding bound 8x tighter.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
 
 // 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread.
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {

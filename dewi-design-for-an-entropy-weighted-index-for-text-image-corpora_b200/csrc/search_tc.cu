@@ -52,6 +52,7 @@ struct TcArgs {
   int seed_stride, seed_off, n_queries;
   float* max_out;     // pre-pass mode: [item][128] maximum score per query, no candidate lists
   int max_groups;     // pre-pass mode: one maximum per 32-row group of every tile instead (SweepSeed::max_groups)
+  int fp16;           // operand planes hold fp16 (fp32 corpus) instead of bf16
 };
 
 // QRES = 1 ("queries resident"; single query block, M = 64): all dim/64 query k-blocks are loaded ONCE and stay in
@@ -72,7 +73,7 @@ search_tc_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_consta
   constexpr uint32_t kEStageBytes = T::PE * kEPlaneBytes;
   constexpr uint32_t kQStageBytes = T::PQ * kQPlaneBytes;
   constexpr uint32_t kTmemCols = 2 * N_TILE;
-  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(Q_ROWS, N_TILE);
+  const uint32_t kIdesc = a.fp16 ? ptx::make_idesc_f16(Q_ROWS, N_TILE) : ptx::make_idesc_bf16(Q_ROWS, N_TILE);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B operand tiles.
@@ -405,8 +406,9 @@ int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim
 
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream) {
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes) {
   TcArgs a;
+  a.fp16 = fp16_planes;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, plan.n_tile));
   a.n_kb = dim / kKBlock;

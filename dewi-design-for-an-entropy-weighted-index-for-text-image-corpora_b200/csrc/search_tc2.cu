@@ -101,7 +101,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
   constexpr uint32_t kTmemCols = 2 * kNTile;
   constexpr int kEpiWarps = (EPI == EPI_JOIN) ? kJoinEpiWarps : 4;
   constexpr int kColsPerWarp = kNTile * 4 / kEpiWarps;   // columns of a tile one epilogue warp walks
-  constexpr uint32_t kIdesc = ptx::make_idesc_bf16(2 * kQueryBlock, kNTile);
+  const uint32_t kIdesc = a.fp16 ? ptx::make_idesc_f16(2 * kQueryBlock, kNTile) : ptx::make_idesc_bf16(2 * kQueryBlock, kNTile);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -439,8 +439,9 @@ int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb) {
 
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt) {
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt, int fp16_planes) {
   Tc2Args a;
+  a.fp16 = fp16_planes;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kNTile));
   a.n_kb = dim / kKBlock;
@@ -540,6 +541,7 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.seed_stride = a.seed_off = a.n_queries = 0;
   a.max_out = nullptr;
   a.max_groups = 0;
+  a.fp16 = 0;
   a.m_rows = static_cast<int>(m_rows);
   a.tau = tau;
   a.self_join = self_join;

@@ -137,29 +137,25 @@ merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ pa
 // lower bound of the query's kc-th best score over the corpus.
 __global__ void __launch_bounds__(kMergeThreads)
 seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb, int kc, float* __restrict__ seed) {
+  // rank counting instead of a sort: the key beaten by exactly kc - 1 others is the kc-th largest (keys are distinct)
   __shared__ unsigned long long key[kWindow];
-  __shared__ int val[kWindow];
   const int b = blockIdx.x;
   const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
-  const int p = next_pow2(n_chunks);
-  for (int t = threadIdx.x; t < p; t += blockDim.x) {
-    unsigned long long kk = 0ull;
-    if (t < n_chunks) {
-      const float v = maxima[(static_cast<size_t>(t) * n_qb + qb) * kQueryBlock + ql];
-      if (v > -INFINITY) kk = make_key(v, static_cast<uint32_t>(t));
-    }
-    key[t] = kk;
-    val[t] = t;
+  for (int t = threadIdx.x; t < n_chunks; t += blockDim.x) {
+    const float v = maxima[(static_cast<size_t>(t) * n_qb + qb) * kQueryBlock + ql];
+    key[t] = (v > -INFINITY) ? make_key(v, static_cast<uint32_t>(t)) : 0ull;
   }
-  bitonic_sort_desc(key, val, p);
-  if (threadIdx.x == 0) {
-    const unsigned long long kk = key[kc - 1];
-    float s = -INFINITY;
-    if (kk != 0ull) {
-      const uint32_t o = static_cast<uint32_t>(kk >> 32);
-      s = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+  if (threadIdx.x == 0) seed[b] = -INFINITY;   // fewer than kc finite maxima: no seed
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_chunks; e += blockDim.x) {
+    const unsigned long long x = key[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < n_chunks; ++f) rank += (key[f] > x) ? 1 : 0;
+    if (rank == kc - 1) {
+      const uint32_t o = static_cast<uint32_t>(x >> 32);
+      seed[b] = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
     }
-    seed[b] = s;
   }
 }
 
@@ -417,11 +413,284 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
   }
 }
 
+
+// ---- fused tail ---------------------------------------------------------------------------------------------
+// Everything after the sweep for ONE query per block, in one launch instead of four or five: merge the per-CTA
+// partial lists (merge_select), give the certificate of a single-plane sweep (certificate_kernel), re-score the
+// candidates exactly (rescore), order them and attach the payload columns (finalize_local, incl. the peer push of
+// the multi-GPU exchange) and -- on a single shard -- blend and pick the final top-k (rerank).  The stages are
+// per-query independent, so block-level barriers replace the launches; selections are done by RANK COUNTING
+// (every thread counts how many keys beat its own: a few hundred broadcast shared-memory reads) instead of bitonic
+// sorts (dozens of block-wide barrier rounds each), which is what made the separate kernels latency-bound.
+constexpr int kTailThreads = 512;
+constexpr int kTailWindow = 2048;     // candidate keys gathered between two selections
+constexpr int kTailMaxKc = 512;       // list capacity the fused tail supports (longer lists use the separate kernels)
+
+struct TailArgs {
+  // merge: partial lists [item][kc][128] of (score, row); item = chunk * n_qb + qb
+  const float* part_s;
+  const int* part_i;
+  int n_chunks, n_qb, kc;
+  // certificate of the single-plane sweep (q_planes == 0: none)
+  const float* q_stats;
+  int q_planes;
+  const unsigned int* plane_max;
+  float gamma;
+  int need;
+  int* fails;
+  // exact re-score (rows == nullptr: the swept scores are exact already)
+  const void* rows;
+  int rows_are_bf16, dim;
+  const float* qn;
+  // local result: the shard's best kcand rows by exact similarity, with payload columns
+  int kcand;
+  long long id_base;
+  const float* dewi;
+  const float* ent;
+  float* out_sim;
+  long long* out_id;
+  float* out_dewi;
+  float* out_ent;
+  PeerPush push;          // world > 0: write the block into every rank's gather buffer instead
+  // single shard: DEWI blend + final top-k in the same launch (backends.py:461-471)
+  int fuse_rerank, k;
+  float w_sim, w_dewi, pref;
+  int use_pref;
+  long long* fin_id;
+  float* fin_score;
+};
+
+__device__ __forceinline__ float key_score(unsigned long long key) {
+  const uint32_t o = static_cast<uint32_t>(key >> 32);
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ uint32_t key_id(unsigned long long key) { return ~static_cast<uint32_t>(key); }
+
+// dst[rank] = key for the `keep` largest of the m distinct keys src[0 .. m) (block-wide; dst and src disjoint).
+__device__ __forceinline__ void select_by_rank(const unsigned long long* src, int m, unsigned long long* dst, int keep) {
+  for (int e = threadIdx.x; e < m; e += blockDim.x) {
+    const unsigned long long x = src[e];
+    int rank = 0;
+    for (int f = 0; f < m; ++f) rank += (src[f] > x) ? 1 : 0;   // same address in every lane of a warp: broadcast
+    if (rank < keep) dst[rank] = x;
+  }
+}
+
+template <typename RowT>
+__device__ __forceinline__ float exact_dot(const RowT* __restrict__ r, const float* __restrict__ q, int dim, int lane) {
+  float acc = 0.f;
+  for (int d = lane * 8; d < dim; d += 256) {
+    float x[8];
+    if (sizeof(RowT) == 2) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(r + d));
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[2 * i] = __uint_as_float(u[i] << 16);
+        x[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
+      }
+    } else {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(r + d));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(r + d) + 1);
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w;
+      x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+    }
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(q + d));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(q + d) + 1);
+    acc = fmaf(x[0], q0.x, acc); acc = fmaf(x[1], q0.y, acc); acc = fmaf(x[2], q0.z, acc); acc = fmaf(x[3], q0.w, acc);
+    acc = fmaf(x[4], q1.x, acc); acc = fmaf(x[5], q1.y, acc); acc = fmaf(x[6], q1.z, acc); acc = fmaf(x[7], q1.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__global__ void __launch_bounds__(kTailThreads)
+tail_kernel(const TailArgs a) {
+  __shared__ unsigned long long win[kTailWindow];      // keys gathered from the partial lists
+  __shared__ unsigned long long best[2][kTailMaxKc];   // running best (sorted), double-buffered
+  __shared__ float s_sim[kTailMaxKc], s_dewi[kTailMaxKc], s_ent[kTailMaxKc];
+  __shared__ int fill_s, nb_s;
+  __shared__ float bar_s;
+  __shared__ unsigned int ticket;
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int kc = a.kc;
+  if (threadIdx.x == 0) { fill_s = 0; nb_s = 0; bar_s = -INFINITY; }
+  __syncthreads();
+
+  // 1. merge: stream the query's n_chunks * kc partial entries through the window; whenever it is (nearly) full, and at
+  //    the end, keep the kc best of {running best, window} by rank counting.  Keys are (score, ~row): distinct.
+  int cur = 0;
+  unsigned long long floor_key = 0ull;   // admission bar: the kc-th best so far (0: any valid key)
+  const int total = a.n_chunks * kc;
+  for (int base = 0; base < total; base += blockDim.x) {
+    const int e = base + threadIdx.x;
+    unsigned long long kk = 0ull;
+    if (e < total) {
+      const int chunk = e / kc, k = e - chunk * kc;
+      const size_t off = ((static_cast<size_t>(chunk) * a.n_qb + qb) * kc + k) * kQueryBlock + ql;
+      const int idx = a.part_i[off];
+      if (idx >= 0) kk = make_key(a.part_s[off], static_cast<uint32_t>(idx));
+    }
+    const bool pass = kk > floor_key;
+    const unsigned int m = __ballot_sync(0xffffffffu, pass);
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(&fill_s, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (pass) win[wbase + __popc(m & ((1u << lane) - 1u))] = kk;   // (fits: a selection runs whenever < blockDim slots remain)
+    __syncthreads();
+    const int fill = fill_s;
+    __syncthreads();   // everybody has read the fill count before the next round's appends move it
+    // (a selection runs while the window still has room for the next round's keys AND the running best behind them)
+    if (fill > kTailWindow - 2 * static_cast<int>(blockDim.x) - kTailMaxKc || base + static_cast<int>(blockDim.x) >= total) {
+      const int nb = nb_s;
+      // append the running best to the window, then select into the other buffer
+      for (int t = threadIdx.x; t < nb; t += blockDim.x) win[fill + t] = best[cur][t];
+      __syncthreads();
+      const int m_all = fill + nb;
+      select_by_rank(win, m_all, best[cur ^ 1], kc);
+      __syncthreads();
+      cur ^= 1;
+      if (threadIdx.x == 0) { nb_s = min(kc, m_all); fill_s = 0; }
+      __syncthreads();
+      if (nb_s == kc) floor_key = best[cur][kc - 1];
+    }
+  }
+  const int nb = nb_s;   // candidates: best[cur][0 .. nb), sorted by swept score, descending
+
+  // 2. certificate of the single-plane sweep (see certificate_kernel)
+  if (a.q_planes && threadIdx.x == 0 && nb > 0) {
+    const float row_err = __uint_as_float(a.plane_max[0]), row_hi = __uint_as_float(a.plane_max[1]);
+    const float qn = a.q_stats[b * 4 + 0], qe = a.q_stats[b * 4 + (a.q_planes == 1 ? 1 : 2)];
+    const float eps = __fmul_ru(qn, row_err) + __fmul_ru(qe, row_hi) + __fmul_ru(a.gamma, __fmul_ru(qn + qe, row_hi));
+    const int need = min(a.need, nb);
+    const float bar = __fsub_rd(key_score(best[cur][need - 1]), __fmul_ru(2.f, eps));
+    bar_s = bar;
+    if (nb == kc && !(key_score(best[cur][kc - 1]) < bar)) atomicAdd(a.fails, 1);
+  }
+  __syncthreads();
+
+  // 3. exact re-score (one warp per candidate), dropping what the certificate proves irrelevant; keys by exact score
+  unsigned long long* exact = win;   // [nb]
+  {
+    const float bar = bar_s;
+    for (int t = warp; t < nb; t += blockDim.x / 32) {
+      const unsigned long long kk = best[cur][t];
+      const uint32_t idx = key_id(kk);
+      float s = key_score(kk);
+      unsigned long long out = 0ull;
+      if (!(a.q_planes && s < bar)) {
+        if (a.rows) {
+          const float* q = a.qn + static_cast<size_t>(b) * a.dim;
+          s = a.rows_are_bf16 ? exact_dot(static_cast<const __nv_bfloat16*>(a.rows) + static_cast<size_t>(idx) * a.dim, q, a.dim, lane)
+                              : exact_dot(static_cast<const float*>(a.rows) + static_cast<size_t>(idx) * a.dim, q, a.dim, lane);
+        }
+        out = make_key(s, idx);
+      }
+      if (lane == 0) exact[t] = out;
+    }
+  }
+  __syncthreads();
+
+  // 4. order by exact similarity (ties: lower row first), keep the shard's top kcand, attach id + payload columns
+  unsigned long long* sorted = best[cur ^ 1];
+  for (int t = threadIdx.x; t < kc; t += blockDim.x) sorted[t] = 0ull;
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb; e += blockDim.x) {
+    const unsigned long long x = exact[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < nb; ++f) rank += (exact[f] > x) ? 1 : 0;
+    sorted[rank] = x;
+  }
+  __syncthreads();
+  const size_t bk = static_cast<size_t>(gridDim.x) * a.kcand;   // elements per section of a pushed block
+  for (int t = threadIdx.x; t < a.kcand; t += blockDim.x) {
+    const unsigned long long kk = (t < kc) ? sorted[t] : 0ull;
+    float v_sim = -INFINITY, v_dewi = 0.f, v_ent = 0.f;
+    long long v_id = -1;
+    if (kk != 0ull) {
+      const uint32_t idx = key_id(kk);
+      v_sim = key_score(kk);
+      v_id = a.id_base + idx;
+      v_dewi = a.dewi[idx];
+      v_ent = a.ent[idx];
+    }
+    const size_t o = static_cast<size_t>(b) * a.kcand + t;
+    if (a.push.world > 0) {
+      for (int r = 0; r < a.push.world; ++r) {  // block layout: [id i64 bk | sim bk | dewi bk | ent bk]
+        char* blk = reinterpret_cast<char*>(a.push.base[r]) + static_cast<long long>(a.push.my_rank) * a.push.block_stride;
+        reinterpret_cast<long long*>(blk)[o] = v_id;
+        reinterpret_cast<float*>(blk + 8 * bk)[o] = v_sim;
+        reinterpret_cast<float*>(blk + 12 * bk)[o] = v_dewi;
+        reinterpret_cast<float*>(blk + 16 * bk)[o] = v_ent;
+      }
+    } else if (a.out_sim) {
+      a.out_sim[o] = v_sim;
+      a.out_id[o] = v_id;
+      a.out_dewi[o] = v_dewi;
+      a.out_ent[o] = v_ent;
+    }
+    if (a.fuse_rerank && t < kTailMaxKc) { s_sim[t] = v_sim; s_dewi[t] = v_dewi; s_ent[t] = v_ent; }
+  }
+  if (a.push.world > 0) {
+    // every block's stores are fenced at system scope before its ticket; the block that draws the last ticket publishes
+    // the ready flags -- unless a certificate failed somewhere in the batch: the host re-runs it, and the re-run publishes
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) ticket = atomicAdd(a.push.ticket, 1u);
+    __syncthreads();
+    if (ticket == gridDim.x - 1) {
+      __threadfence_system();
+      const bool ok = !a.q_planes || *reinterpret_cast<volatile int*>(a.fails) == 0;
+      if (ok && threadIdx.x < a.push.world)
+        st_release_sys(reinterpret_cast<unsigned int*>(a.push.flags[threadIdx.x]) + a.push.my_rank, a.push.seq);
+      if (threadIdx.x == 0) *a.push.ticket = 0u;
+    }
+    return;
+  }
+  if (!a.fuse_rerank) return;
+  __syncthreads();
+
+  // 5. single shard: adj = w_sim * sim + w_dewi * dewi (+ pref * ent) in fp32, one rounding per operation as numpy
+  //    (backends.py:461-465); top-k by adj, descending, ties: lower id first (backends.py:468-471)
+  unsigned long long* adjk = win;   // [kcand]
+  const int nc = min(a.kcand, kTailMaxKc);
+  for (int t = threadIdx.x; t < nc; t += blockDim.x) {
+    const unsigned long long kk = (t < kc) ? sorted[t] : 0ull;
+    unsigned long long out = 0ull;
+    if (kk != 0ull) {
+      float adj = __fadd_rn(__fmul_rn(a.w_sim, s_sim[t]), __fmul_rn(a.w_dewi, s_dewi[t]));
+      if (a.use_pref) adj = __fadd_rn(adj, __fmul_rn(a.pref, s_ent[t]));
+      out = make_key(adj, static_cast<uint32_t>(a.id_base + key_id(kk)));
+    }
+    adjk[t] = out;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < a.k; t += blockDim.x) {   // defaults: fewer than k candidates
+    a.fin_id[static_cast<size_t>(b) * a.k + t] = -1;
+    a.fin_score[static_cast<size_t>(b) * a.k + t] = -INFINITY;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nc; e += blockDim.x) {
+    const unsigned long long x = adjk[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < nc; ++f) rank += (adjk[f] > x) ? 1 : 0;
+    if (rank < a.k) {
+      a.fin_id[static_cast<size_t>(b) * a.k + rank] = a.id_base + key_id(sorted[e]);
+      a.fin_score[static_cast<size_t>(b) * a.k + rank] = key_score(x);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream) {
   if (n_chunks < kc || n_chunks > kWindow) return fail("seed_from_maxima: item count outside [kc, 2048]");
-  seed_from_maxima_kernel<<<B, kMergeThreads, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
+  seed_from_maxima_kernel<<<B, 512, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -473,6 +742,51 @@ int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int
     finalize_local_kernel<0><<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, out_sim,
                                                                reinterpret_cast<long long*>(out_id), out_dewi, out_ent, PeerPush());
   }
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int tail_supported(int kc, int kcand, int k) { return kc >= 1 && kc <= kTailMaxKc && kcand >= 1 && kcand <= kTailMaxKc && k <= kcand; }
+
+int launch_tail(const Partials& p, int B, const TailCert* cert, const void* rows, int rows_are_bf16, int dim, const float* qn, int kcand,
+                int64_t id_base, const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi, float* out_ent,
+                const PeerPush* push, const TailRerank* rr, cudaStream_t stream) {
+  if (!tail_supported(p.kc, kcand, rr ? rr->k : 1)) return fail("fused tail: unsupported list capacity");
+  TailArgs a;
+  a.part_s = p.s;
+  a.part_i = p.i;
+  a.n_chunks = p.n_chunks;
+  a.n_qb = p.n_qb;
+  a.kc = p.kc;
+  a.q_stats = cert ? cert->q_stats : nullptr;
+  a.q_planes = cert ? cert->q_planes : 0;
+  a.plane_max = cert ? cert->plane_max : nullptr;
+  a.gamma = static_cast<float>(dim) * 2.384185791015625e-07f;   // dim * 2^-22
+  a.need = cert ? cert->need : 0;
+  a.fails = cert ? cert->fails : nullptr;
+  a.rows = rows;
+  a.rows_are_bf16 = rows_are_bf16;
+  a.dim = dim;
+  a.qn = qn;
+  a.kcand = kcand;
+  a.id_base = id_base;
+  a.dewi = dewi;
+  a.ent = ent;
+  a.out_sim = out_sim;
+  a.out_id = reinterpret_cast<long long*>(out_id);
+  a.out_dewi = out_dewi;
+  a.out_ent = out_ent;
+  a.push = (push && push->world > 0) ? *push : PeerPush();
+  a.fuse_rerank = rr ? 1 : 0;
+  a.k = rr ? rr->k : 0;
+  a.w_sim = rr ? rr->w_sim : 0.f;
+  a.w_dewi = rr ? rr->w_dewi : 0.f;
+  a.pref = rr ? rr->pref : 0.f;
+  a.use_pref = rr ? rr->use_pref : 0;
+  a.fin_id = rr ? reinterpret_cast<long long*>(rr->out_id) : nullptr;
+  a.fin_score = rr ? rr->out_score : nullptr;
+  if (rows && dim % 8 != 0) return fail("fused tail: the exact re-score needs dim % 8 == 0");
+  tail_kernel<<<B, kTailThreads, 0, stream>>>(a);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

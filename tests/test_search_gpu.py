@@ -89,7 +89,7 @@ def test_device_tensor_io_matches_host_io():
     ids_h, sc_h = ix.search_batch(q, k=10, eta=0.25, entropy_pref=0.0)
     ids_d, sc_d = ix.search_batch(torch.from_numpy(q).cuda(), k=10, eta=0.25, entropy_pref=0.0)
     assert np.array_equal(ids_h, ids_d.cpu().numpy()) and np.array_equal(sc_h, sc_d.cpu().numpy())
-    assert ix._backend.last_launches() >= 4
+    assert ix._backend.last_launches() >= 3   # query prep, sweep, fused tail (+ pre-pass and seed on larger corpora)
 
 
 def test_device_side_normalisation_close_to_numpy():
