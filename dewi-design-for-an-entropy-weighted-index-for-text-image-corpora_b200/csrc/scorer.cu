@@ -38,18 +38,9 @@ constexpr int kSampleBlockRuns = 4;              // runs a sample_kernel block g
 constexpr int kSampleBlocks = 64;                // blocks per column (4 trips each)
 // +- sample ranks around the middle: 4 sigma of a 2^20 sample's median rank (sigma = 512).  A window that misses its
 // ranks (6e-5 per column) is detected and costs the fallback to the plain radix passes, never a wrong answer; a
-// narrower window means fewer keys to collect in the full pass (the one-pass path collects ~5x the window's mass).
+// narrower window means fewer keys for the full pass to collect.
 constexpr int kSampleMargin = 2048;
-// Window pass with the in-window histogram fused in (DEWI_FIT_FUSED=1) or as a launch of its own (0).  Measured at
-// 100M x 7 (CUDA events in-stream, warm): fused 483-498 us per pass, separate 445-451 + 20 us -- the extra live state
-// costs the streaming loop more than the launch it saves, so the separate histogram is the default.
-constexpr int kFitFusedDefault = 0;
 constexpr int kWindowDigitBits = 11;             // window-relative digit of the in-window selection (2048 bins)
-// One full pass for BOTH statistics (DEWI_FIT_ONEPASS): the sample also brackets the MAD -- as a window of |y - c0|
-// around the centre c0 of the median's window -- so the pass over the column collects the median's keys and the
-// MAD's keys together; the exact median then turns the second set into exact deviations.  Half the bytes of the
-// "median, then a dependent pass for the MAD" scheme.
-constexpr int kFitOnePassDefault = 1;
 constexpr int kSurvCap = 8192;                   // keys of the target bins sorted in shared memory (typically a few hundred)
 
 struct SelState {
@@ -72,13 +63,7 @@ struct SelState {
   unsigned int surv_n[kMaxCols];            // survivor_kernel: keys gathered from the target bins
   unsigned int surv_n0[kMaxCols];           //   ... of which in bin 0, when the two bins differ
   unsigned int surv_done[kMaxCols];         // survivor_kernel: block tickets (self-resetting)
-  // one-pass path: the MAD's keys are collected in the SAME pass as the median's, around the window centre c0
-  float c0[kMaxCols], w[kMaxCols];          // centre and (inflated) half-width of the median window, value space
-  float A[kMaxCols], B[kMaxCols];           // collect y with A <= |y - c0| <= B  (deviation window around c0)
-  float r0[kMaxCols];                       // radius of the median window around c0 as the pass tests it: |y - c0| <= r0
-  float cd[kMaxCols], rd[kMaxCols];         // centre / radius of the deviation window as the pass tests it
-  unsigned long long belowd[kMaxCols];      // #(|y - c0| < A)
-  unsigned int cntd[kMaxCols];              // keys appended to the deviation window buffer
+  float c0[kMaxCols], r0[kMaxCols];         // the window as the full pass tests it: |fl(x - c0)| <= r0 (a superset of [lo, hi])
 };
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -102,17 +87,11 @@ __device__ __forceinline__ void pass_bits(int pass, int& shift, int& nbins, unsi
 }
 
 // Key sources.  RAW: fp32 column value; DEV: |v - med| in fp32 (scorer.py:24); KEYS: a buffer of keys.
-// SKEY_DEV: a buffer of keys of VALUES, re-keyed as |value - centre| (one-pass path: deviations of the sample around c0).
-enum { SRC_RAW = 0, SRC_DEV = 1, SRC_KEYS = 2, SRC_SKEY_DEV = 3 };
+enum { SRC_RAW = 0, SRC_DEV = 1, SRC_KEYS = 2 };
 
 template <int SRC>
 __device__ __forceinline__ unsigned int load_key(const void* col, long long i, float med) {
   if (SRC == SRC_KEYS) return __ldg(static_cast<const unsigned int*>(col) + i);
-  if (SRC == SRC_SKEY_DEV) {
-    const unsigned int k = __ldg(static_cast<const unsigned int*>(col) + i);
-    const float y = __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);   // from_orderable
-    return orderable(fabsf(__fsub_rn(y, med)));
-  }
   float v = __ldg(static_cast<const float*>(col) + i);
   if (SRC == SRC_DEV) v = fabsf(__fsub_rn(v, med));
   return orderable(v);
@@ -122,7 +101,7 @@ __device__ void pick_column(int pass, int c, SelState* st, unsigned int* ghist, 
                             unsigned long long* wsum);
 
 // What the last block of a selection pass does after it has picked its bins.
-enum { OP_NONE = 0, OP_WINDOW_BOUNDS = 1, OP_WINDOW_BOUNDS_1P = 2, OP_DEV_BOUNDS = 3 };
+enum { OP_NONE = 0, OP_WINDOW_BOUNDS = 1 };
 
 // The sample selection resolved the top 19 bits (pass 0 and the coarse pass 3) of the keys at sample ranks
 // s/2 -+ margin: rounding the first down and the second up to a multiple of 2^13 keeps the window conservative (finer
@@ -136,6 +115,16 @@ __device__ __forceinline__ void arm_window(SelState* st, int c) {
   st->wcnt[c] = 0u;
   const int nbits = 32 - __clz(static_cast<int>(hi - lo));   // hi - lo >= 0x1FFF
   st->wshift[c] = max(nbits - kWindowDigitBits, 0);
+  // The full pass tests the window in centre / radius form, |fl(x - c0)| <= r0 (one subtraction shared by the
+  // "below" count and the membership test): r0 is the half-width inflated by 2^-10 and by a slack far above the
+  // rounding of the subtraction, so the tested window is a superset of [lo, hi].
+  const float lo_f = from_orderable(lo), hi_f = from_orderable(hi);
+  const float c0 = 0.5f * lo_f + 0.5f * hi_f;
+  float r0 = fmaxf(hi_f - c0, c0 - lo_f);
+  r0 = r0 * 1.0009765625f + (fabsf(c0) + r0) * 3.814697265625e-06f + 1e-30f;
+  st->c0[c] = c0;
+  st->r0[c] = r0;
+  if (!(r0 < INFINITY) || !(c0 == c0)) st->miss[c] = 1;   // infinite / NaN bounds: not a usable window
 }
 
 // State of a fresh sample selection: ranks s/2 -+ margin of the kSample sample keys.
@@ -144,47 +133,6 @@ __device__ __forceinline__ void arm_sample(SelState* st, int c) {
   st->rank[c][0] = kSample / 2 - kSampleMargin;
   st->rank[c][1] = kSample / 2 + kSampleMargin;
   st->same[c] = 1;
-}
-
-__device__ __forceinline__ float key_to_float(unsigned int o) {
-  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
-}
-
-// One-pass path, after the median window [lo, hi] is known: its centre c0 and half-width w in value space (w inflated
-// by 2^-10 and by a slack far above any fp32 rounding of the quantities below), and the sample selection of the
-// deviations |s - c0| armed.  With med anywhere in the window, ||y - c0| - |y - med|| <= w for every y.
-__device__ __forceinline__ void arm_dev_sample(SelState* st, int c) {
-  const float lo_f = key_to_float(st->lo[c]), hi_f = key_to_float(st->hi[c]);
-  const float c0 = 0.5f * lo_f + 0.5f * hi_f;
-  float w = fmaxf(hi_f - c0, c0 - lo_f);
-  w = w * 1.0009765625f + (fabsf(c0) + w) * 3.814697265625e-06f + 1e-30f;   // * (1 + 2^-10) + 2^-18 (|c0| + w)
-  st->c0[c] = c0;
-  st->w[c] = w;
-  st->r0[c] = w;   // the pass collects |fl(y - c0)| <= r0: a superset of [lo, hi] (w is the inflated half-width)
-  if (!(w < INFINITY) || !(c0 == c0)) st->miss[c] = 1;   // infinite / NaN bounds: not a usable window
-  arm_sample(st, c);
-}
-
-// One-pass path, after the sample's deviations |s - c0| bracket the middle rank by [dlo, dhi] (19 key bits resolved,
-// rounded outwards): the column's MAD -- deviations around the exact median, each within w of the deviation around
-// c0 -- lies in [dlo - w, dhi + w], and every element with such a deviation has |y - c0| in [dlo - 2w, dhi + 2w] = [A, B].
-__device__ __forceinline__ void arm_dev_window(SelState* st, int c) {
-  const float dlo = key_to_float(st->prefix[c][0] & 0xFFFFE000u), dhi = key_to_float(st->prefix[c][1] | 0x1FFFu);
-  const float w = st->w[c];
-  // The pass tests | |fl(y - c0)| - cd | <= rd with cd, rd the centre and radius of [dlo - 2w, dhi + 2w]; A and B are
-  // what the later exactness argument may assume of every uncollected element (|y - c0| < A or > B): the tested
-  // interval shrunk by a slack far above the rounding of the two subtractions.
-  const float a = dlo - 2.f * w, b = dhi + 2.f * w;
-  const float cd = 0.5f * a + 0.5f * b;
-  const float rd = fmaxf(b - cd, cd - a) * 1.0000038146972656f;
-  const float slack = (fabsf(st->c0[c]) + fabsf(b)) * 3.814697265625e-06f;
-  st->cd[c] = cd;
-  st->rd[c] = rd;
-  st->A[c] = fmaxf(cd - rd + slack, 0.f);
-  st->B[c] = cd + rd - slack;    // (+inf / NaN collect everything: the buffer overflows and the column is flagged)
-  if (!(rd < INFINITY) || !(cd == cd)) st->miss[c] = 1;
-  st->belowd[c] = 0ull;
-  st->cntd[c] = 0u;
 }
 
 // Histogram of the current digit over the keys whose higher digits match a slot's prefix: block-private
@@ -205,7 +153,7 @@ hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* 
   __syncthreads();
   const unsigned int p0 = st->prefix[c][0] & himask, p1 = st->prefix[c][1] & himask;
   const bool same = st->same[c] != 0;
-  const float med = (SRC == SRC_DEV) ? st->med[c] : ((SRC == SRC_SKEY_DEV) ? st->c0[c] : 0.f);
+  const float med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
   const long long n = n_dev ? static_cast<long long>(min(static_cast<long long>(n_dev[c]), n_host)) : n_host;
   const char* col = static_cast<const char*>(src) + static_cast<size_t>(c) * ld * 4;
   const unsigned int binmask = static_cast<unsigned int>(nbins - 1);
@@ -260,9 +208,7 @@ hist_kernel(const void* __restrict__ src, long long n_host, const unsigned int* 
   pick_column(pass, c, st, ghist, reinterpret_cast<unsigned long long*>(sh), wsum);
   if (threadIdx.x == 0) {
     done[c] = 0u;
-    if (op == OP_WINDOW_BOUNDS || op == OP_WINDOW_BOUNDS_1P) arm_window(st, c);
-    if (op == OP_WINDOW_BOUNDS_1P) arm_dev_sample(st, c);
-    if (op == OP_DEV_BOUNDS) arm_dev_window(st, c);
+    if (op == OP_WINDOW_BOUNDS) arm_window(st, c);
   }
 }
 
@@ -346,8 +292,7 @@ __device__ __forceinline__ void middle_ranks(long long n, unsigned long long& r0
 //   ARM_WINDOW : the sample selection just finished: prefix[] are the window bounds -> lo/hi
 //   ARM_INSIDE : the window pass just finished: select ranks (middle - below) inside the window
 //   FINAL_MED / FINAL_MAD : the selection of the middle ranks finished: prefix[] -> med / mad
-//   FINAL_MED_1P : one-pass path: prefix[] -> med, then the exact-deviation window of the MAD selection is armed
-enum { ARM_FULL, ARM_SAMPLE, ARM_WINDOW, ARM_INSIDE, FINAL_MED, FINAL_MAD, FINAL_MED_1P };
+enum { ARM_FULL, ARM_SAMPLE, ARM_WINDOW, ARM_INSIDE, FINAL_MED, FINAL_MAD };
 
 __global__ void glue_kernel(int op, int f, long long n, unsigned int window_cap, SelState* st) {
   const int c = threadIdx.x;
@@ -448,30 +393,28 @@ sample_kernel(const float* __restrict__ cols, long long n, long long ld, SelStat
 
 // THE full pass of the windowed path: count keys below the window, collect the keys inside it.
 //
-// The pass is a pure HBM stream, so the per-element instruction count is what has to stay small:
-// the window bounds are turned back into floats and every element costs four instructions --
-// `p = x >= lo` (FSETP), `below += !p`, `q = p && x <= hi` (FSETP.AND), `mask |= q << e`.  Window hits
-// are ~0.8 % of the keys, i.e. ~4 per warp per 16-element tile, so nearly every warp has SOME lane with
-// a hit: the hit path must be short too.  Lanes with a non-zero mask walk its set bits, re-read the
-// element (an L1 / L2 hit), and append its order-preserving key to a per-block shared buffer with one
-// shared atomic each; the buffer goes to the global window with one global atomic when it is half full.
-// Float order and key order differ only in (-0, +0) and NaNs: counting and collecting use the SAME float
-// predicates and the selection inside the window uses key order (a refinement of float order), so the
-// selected VALUE is exact.  The [column][row] space is flattened into 4096-element tiles and cut into
-// one contiguous tile range per block, so a grid of exactly (SMs x resident blocks) is one balanced wave
-// for any column count.
+// The pass is an HBM stream that the instruction issue rate must not hold back: the first version -- `x >= lo`,
+// `below += !p`, `p && x <= hi`, a hit mask, and every hit re-read, re-keyed and appended on the spot -- ran 292M warp
+// instructions for 700M elements (ncu: issue slots 62 % busy, DRAM at 80 % of its peak, 425 us per pass).  Now
+// (1) the window is tested in centre / radius form on t = fl(x - c0): `t < -r0` feeds the "below" count and
+// `|t| <= r0` the membership, four instructions per element; the tests are monotone in x, so they define a proper
+// window (a superset of the [lo, hi] the sample bracketed), and count and collection partition the column
+// consistently because both use the same rounded t.  (2) Hits (~0.5 % of the elements) set a bit of a per-thread mask;
+// lanes with a non-zero mask walk its set bits, re-read the element (an L1 hit: it was loaded a few instructions ago)
+// and append its order-preserving key to a per-block shared buffer with one shared atomic each; the buffer goes to the
+// global window with one global atomic when it is half full.  Variants that were measured and lost: queueing the
+// thread's element index and re-testing at flush time (the re-reads miss L2 -- ncu: 4.99 GB read from DRAM for a
+// 2.8 GB pass, 731 us); appending the hits from the registers (x[16] stays live across the hit path, 32 registers
+// spill: 571-614 us); fusing the window histogram into the pass (483-498 us).  Float order and key order differ
+// only in (-0, +0) and NaNs, and the selection inside the window uses key order (a refinement of float order), so
+// the selected VALUE is exact.  The [column][row] space is flattened into 4096-element tiles and cut into one
+// contiguous tile range per block, so a grid of exactly (SMs x resident blocks) is one balanced wave for any column count.
 constexpr int kWinBuf = 3072;
 constexpr int kWinThreads = 256;
-#ifndef DEWI_WIN_PER_THREAD
-#define DEWI_WIN_PER_THREAD 16
-#endif
-#ifndef DEWI_WIN_BLOCKS_PER_SM
-#define DEWI_WIN_BLOCKS_PER_SM 8
-#endif
-constexpr int kWinPerThread = DEWI_WIN_PER_THREAD;
+constexpr int kWinPerThread = 16;
 constexpr int kWinTile = kWinThreads * kWinPerThread;
-constexpr int kFlushCheckEvery = 8;   // tiles between two looks at the buffer fill (8 tiles add ~260 keys)
-constexpr int kWinBlocksPerSm = DEWI_WIN_BLOCKS_PER_SM;
+constexpr int kWinBlocksPerSm = 8;
+constexpr int kFlushCheckEvery = 8;  // tiles between two looks at the buffer fill (8 tiles add ~160 keys)
 
 // Inclusive prefix sums of g[0 .. kBins) into cum[] for the whole block (blockDim.x divides kBins, at most 8 bins
 // per thread); `wsum` is 32 words of scratch.
@@ -516,16 +459,11 @@ __device__ __forceinline__ unsigned int window_digit(unsigned int key, unsigned 
   return rel >> wshift;
 }
 
-// Shared state of a window_kernel block that its out-of-line helpers need.
+// Shared memory of the block that picks a column's target bins (window_pick): 2048 x u64 prefix sums + scratch.
 struct WinShared {
-  // [ buf : keys waiting for the next flush | hist : window-relative digit histogram of the current column ]; the
-  // block that finishes a column last reuses the whole array as 2048 x u64 prefix sums (window_pick)
-  unsigned int shm[kWinBuf + kBins];
+  unsigned int shm[kWinBuf + kBins];   // [ (unused here) | histogram of the window-relative digit ], reused as the prefix sums
   unsigned long long wsum[32];
   unsigned int ticket;
-  // digit parameters of the current column (written by thread 0 at a column switch)
-  unsigned int lo_key, span;
-  int wshift;
 };
 
 // The block that completes a column (all its tiles accounted for) turns the column's counts into the two target
@@ -559,51 +497,13 @@ __device__ __forceinline__ void window_pick(WinShared* ws, int c, long long n, u
   __syncthreads();
 }
 
-// End of a column for this block (block-uniform; the key buffer has been flushed): hand the digit histogram over,
-// draw the column's tile ticket and, if that completes the column, pick the target bins.  Out of line: it runs once
-// or twice per block and must not cost the streaming loop registers.
-__device__ __forceinline__ void window_finish_column(WinShared* ws, int c, unsigned int tiles_mine, int tiles_per_col, long long n,
-                                                  unsigned int window_cap, SelState* st, unsigned int* ghist) {
-  unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
-  unsigned int* hist = ws->shm + kWinBuf;
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
-    const unsigned int v = hist[i];
-    if (v) { atomicAdd(&g[i], v); hist[i] = 0u; }
-  }
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) ws->ticket = atomicAdd(&st->tiles_done[c], tiles_mine);
-  __syncthreads();
-  if (ws->ticket + tiles_mine == static_cast<unsigned int>(tiles_per_col)) {
-    __threadfence();
-    window_pick(ws, c, n, window_cap, st, g);
-  }
-  __syncthreads();
-}
-
-// Load the digit parameters of column c into the block's shared state (block-uniform).
-__device__ __forceinline__ void window_enter_column(WinShared* ws, int c, const SelState* st) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    ws->lo_key = st->lo[c];
-    ws->span = st->hi[c] - st->lo[c];
-    ws->wshift = st->wshift[c];
-  }
-  __syncthreads();
-}
-
-// FUSED = 1: the histogram of the window-relative digit and the pick of the target bins ride along (the digits are
-// counted when the key buffer is flushed; the block that completes a column picks).  FUSED = 0: the pass only counts
-// and collects, and window_hist_kernel histograms the collected keys in a launch of its own.
-template <int SRC, int FUSED>
+template <int SRC>
 __global__ void __launch_bounds__(kWinThreads, kWinBlocksPerSm)
 window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, SelState* st,
-              unsigned int* __restrict__ wkeys, unsigned int window_cap, unsigned int* __restrict__ ghist) {
-  __shared__ __align__(8) WinShared ws;
-  unsigned int* const buf = ws.shm;
+              unsigned int* __restrict__ wkeys, unsigned int window_cap) {
+  __shared__ unsigned int buf[kWinBuf];   // keys waiting for the next flush
   __shared__ unsigned int buf_n, flush_base;
   __shared__ unsigned long long below_blk;
-  for (int i = threadIdx.x; i < kBins; i += blockDim.x) ws.shm[kWinBuf + i] = 0u;
   const int lane = threadIdx.x & 31;
   // (tile counts fit 32 bits: 2^31 rows x 32 columns / 4096)
   const int tiles_per_col = static_cast<int>((n + kWinTile - 1) / kWinTile);
@@ -614,12 +514,15 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
   __syncthreads();
 
   int c = -1;
-  float med = 0.f, lo_f = 0.f, hi_f = 0.f;
+  float med = 0.f, c0 = 0.f, r0 = 0.f;
   const float* col = nullptr;
   unsigned int* out = nullptr;
   bool aligned = false;
   unsigned int below = 0u;
   int since_check = 0;
+
+  // the key of an element: RAW the value, DEV |v - med| in fp32 (scorer.py:24)
+  auto keyed = [&](float y) { return (SRC == SRC_DEV) ? fabsf(__fsub_rn(y, med)) : y; };
 
   auto flush = [&](unsigned int min_fill) {  // block-uniform
     __syncthreads();
@@ -627,11 +530,8 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
     if (cnt > min_fill) {
       if (threadIdx.x == 0) flush_base = atomicAdd(&st->wcnt[c], cnt);
       __syncthreads();
-      for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
-        const unsigned int key = buf[k];
-        if (flush_base + k < window_cap) out[flush_base + k] = key;
-        if (FUSED) atomicAdd(&ws.shm[kWinBuf + window_digit(key, ws.lo_key, ws.span, ws.wshift)], 1u);
-      }
+      for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x)
+        if (flush_base + k < window_cap) out[flush_base + k] = buf[k];
       __syncthreads();
       if (threadIdx.x == 0) buf_n = 0u;
       __syncthreads();
@@ -650,40 +550,31 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
     }
     below = 0u;
     __syncthreads();
-    if (FUSED) {
-      // tiles of column c inside this block's range [t_begin, t_end)
-      // (the block's first tile is recomputed here rather than kept in a register across the streaming loop)
-      const int c_lo = c * tiles_per_col;
-      const int first = static_cast<int>((static_cast<long long>(tiles_per_col) * f * blockIdx.x) / gridDim.x);
-      window_finish_column(&ws, c, static_cast<unsigned int>(min(t_end, c_lo + tiles_per_col) - max(first, c_lo)), tiles_per_col,
-                           n, window_cap, st, ghist);
-    }
   };
-  auto push = [&](float v) {  // v lies in the window
-    const unsigned int key = orderable(v);
+  auto push = [&](float x) {  // x lies in the window
+    const unsigned int key = orderable(x);
     const unsigned int slot = atomicAdd(&buf_n, 1u);
-    if (slot < kWinBuf) buf[slot] = key;   // (its digit is histogrammed when the buffer is flushed)
+    if (slot < kWinBuf) buf[slot] = key;
     else {  // shared buffer full (a huge tie group): straight to global; the caller will see wcnt > cap
       const unsigned int g = atomicAdd(&st->wcnt[c], 1u);
       if (g < window_cap) out[g] = key;
-      if (FUSED) atomicAdd(&ws.shm[kWinBuf + window_digit(key, ws.lo_key, ws.span, ws.wshift)], 1u);
     }
   };
 
+  int next_switch = t_begin;   // first tile of the next column
   for (int t = t_begin; t < t_end; ++t) {
-    const int tc = t / tiles_per_col;
-    if (tc != c) {
+    if (t >= next_switch) {
       if (c >= 0) commit_column();
-      c = tc;
-      if (FUSED) window_enter_column(&ws, c, st);
+      c = t / tiles_per_col;
+      next_switch = (c + 1) * tiles_per_col;
       med = (SRC == SRC_DEV) ? st->med[c] : 0.f;
-      lo_f = from_orderable(st->lo[c]);
-      hi_f = from_orderable(st->hi[c]);
+      c0 = st->c0[c];
+      r0 = st->r0[c];
       col = cols + static_cast<size_t>(c) * ld;
       out = wkeys + static_cast<size_t>(c) * window_cap;
       aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
     }
-    const long long base = static_cast<long long>(t - c * tiles_per_col) * kWinTile;
+    const long long base = static_cast<long long>(t - (next_switch - tiles_per_col)) * kWinTile;
     if (aligned && base + kWinTile <= n) {
       // element e of this thread: base + (e / 4) * (threads * 4) + tid * 4 + (e % 4)  (coalesced 128-bit loads)
       const float* p = col + base + threadIdx.x * 4;
@@ -694,30 +585,26 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
         x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
       }
       unsigned int mask = 0u;
+      const float nr0 = -r0;
 #pragma unroll
       for (int e = 0; e < kWinPerThread; ++e) {
-        float y = x[e];
-        if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
-        const bool ge = y >= lo_f;
-        below += ge ? 0u : 1u;
-        mask |= (ge && y <= hi_f) ? (1u << e) : 0u;
+        const float tt = __fsub_rn(keyed(x[e]), c0);
+        below += (tt < nr0) ? 1u : 0u;
+        mask |= (fabsf(tt) <= r0) ? (1u << e) : 0u;
       }
-      while (mask) {  // rare per lane; the element is re-read (cache hit) instead of indexing registers dynamically
+      while (mask) {  // rare per lane; the element is re-read (an L1 hit) instead of indexing registers dynamically
         const int e = __ffs(mask) - 1;
         mask &= mask - 1u;
-        float y = p[(e >> 2) * (kWinThreads * 4) + (e & 3)];
-        if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
-        push(y);
+        push(keyed(p[(e >> 2) * (kWinThreads * 4) + (e & 3)]));
       }
     } else {  // ragged last tile of a column, or a column that is not 16-byte aligned
       for (int e = 0; e < kWinPerThread; ++e) {
         const long long i = base + static_cast<long long>(e >> 2) * kWinThreads * 4 + threadIdx.x * 4 + (e & 3);
         if (i < n) {
-          float y = __ldg(col + i);
-          if (SRC == SRC_DEV) y = fabsf(__fsub_rn(y, med));
-          const bool ge = y >= lo_f;
-          below += ge ? 0u : 1u;
-          if (ge && y <= hi_f) push(y);
+          const float xx = keyed(__ldg(col + i));
+          const float tt = __fsub_rn(xx, c0);
+          below += (tt < -r0) ? 1u : 0u;
+          if (fabsf(tt) <= r0) push(xx);
         }
       }
     }
@@ -726,235 +613,22 @@ window_kernel(const float* __restrict__ cols, long long n, long long ld, int f, 
   if (c >= 0) commit_column();
 }
 
-// THE pass of the one-pass path: per element y, the median window [lo, hi] as in window_kernel (count below, collect
-// inside) AND the deviation window A <= |y - c0| <= B around the centre of the median window (count below A, collect
-// inside): one read of the column instead of two.  The MAD's keys are stored as keys of the VALUES: the exact median
-// is not known yet.
-//
-// The pass is bound by instruction issue, not by HBM, unless the hits (~2.8 % of the elements, a dozen per warp and
-// tile) stay off the streaming loop: ncu on the first version -- every hit re-read, re-keyed and appended on the spot in
-// a divergent loop -- showed 681M warp instructions (500 per 512 elements) at 70 % issue utilisation and 40 % of the
-// DRAM peak.  So (1) both windows are tested in centre / radius form on t = fl(y - c0), which they share: |t| <= r0
-// for the median window, | |t| - cd | <= rd for the deviation window, t < -r0 and |t| - cd < -rd for the two "below"
-// counts; the tests are monotone in y, so they define proper windows, and the counts and the collection partition
-// the column consistently because both use the same rounded quantities.  (2) The loop only notes WHETHER any of a
-// thread's 16 elements hit and queues the thread's element index -- one warp-aggregated shared atomic per warp and
-// tile; the entries are re-tested and expanded into keys when the queue is flushed, every thread working on a
-// different entry (dense, no divergence against the streaming loop).
-constexpr int kWin2BlocksPerSm = 6;
-constexpr int kWin2Queue = 2048;   // queued entries per block (one per thread and tile with a hit; ~80 per tile)
-
-template <int DUMMY>
-__global__ void __launch_bounds__(kWinThreads, kWin2BlocksPerSm)
-window2_kernel(const float* __restrict__ cols, long long n, long long ld, int f, SelState* st, unsigned int* __restrict__ wkeys0,
-               unsigned int cap0, unsigned int* __restrict__ wkeysd, unsigned int capd) {
-  __shared__ unsigned int q_elem[kWin2Queue];   // index (within the column) of the queued thread's first element
-  __shared__ unsigned int q_mask[kWin2Queue];   // flush: bit e = element e in the median window, bit 16 + e = in the deviation window
-  __shared__ unsigned int warp_sum[2][kWinThreads / 32];
-  __shared__ unsigned int q_n, base0_s, based_s;
-  __shared__ unsigned long long below0_blk, belowd_blk;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_per_col = static_cast<int>((n + kWinTile - 1) / kWinTile);
-  const long long total_tiles = static_cast<long long>(tiles_per_col) * f;
-  const int t_begin = static_cast<int>((total_tiles * blockIdx.x) / gridDim.x);
-  const int t_end = static_cast<int>((total_tiles * (blockIdx.x + 1)) / gridDim.x);
-  if (threadIdx.x == 0) { q_n = 0u; below0_blk = 0ull; belowd_blk = 0ull; }
-  __syncthreads();
-
-  int c = -1;
-  float c0 = 0.f, r0 = 0.f, cd = 0.f, rd = 0.f;
-  const float* col = nullptr;
-  bool aligned = false;
-  unsigned int below0 = 0u, belowd = 0u;
-  int since_check = 0;
-
-  // The two window tests of one element (the streaming loop evaluates the same expressions).
-  auto in0 = [&](float y) { return fabsf(__fsub_rn(y, c0)) <= r0; };
-  auto ind = [&](float y) { return fabsf(__fsub_rn(fabsf(__fsub_rn(y, c0)), cd)) <= rd; };
-
-  // Expand the queued entries into keys (block-uniform): re-test each entry's 16 elements, count the hits per window,
-  // reserve both ranges with one global atomic each, then every thread writes the keys of its entries at its scanned offset.
-  auto flush = [&]() {
-    __syncthreads();
-    const unsigned int cnt = min(q_n, static_cast<unsigned int>(kWin2Queue));
-    unsigned int my0 = 0u, myd = 0u;
-    for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
-      const float* p = col + q_elem[k];
-      unsigned int m = 0u;
-#pragma unroll
-      for (int e = 0; e < kWinPerThread; ++e) {
-        const float y = __ldg(p + (e >> 2) * (kWinThreads * 4) + (e & 3));   // (cache hit: read a few tiles ago)
-        m |= in0(y) ? (1u << e) : 0u;
-        m |= ind(y) ? (0x10000u << e) : 0u;
-      }
-      q_mask[k] = m;
-      my0 += __popc(m & 0xFFFFu);
-      myd += __popc(m >> 16);
-    }
-    unsigned int inc0 = my0, incd = myd;   // inclusive warp scans
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const unsigned int y0 = __shfl_up_sync(0xffffffffu, inc0, o), yd = __shfl_up_sync(0xffffffffu, incd, o);
-      if (lane >= o) { inc0 += y0; incd += yd; }
-    }
-    if (lane == 31) { warp_sum[0][warp] = inc0; warp_sum[1][warp] = incd; }
-    __syncthreads();
-    unsigned int off0 = inc0 - my0, offd = incd - myd, tot0 = 0u, totd = 0u;
-#pragma unroll
-    for (int w2 = 0; w2 < kWinThreads / 32; ++w2) {
-      if (w2 < warp) { off0 += warp_sum[0][w2]; offd += warp_sum[1][w2]; }
-      tot0 += warp_sum[0][w2];
-      totd += warp_sum[1][w2];
-    }
-    if (threadIdx.x == 0) {
-      base0_s = tot0 ? atomicAdd(&st->wcnt[c], tot0) : 0u;
-      based_s = totd ? atomicAdd(&st->cntd[c], totd) : 0u;
-    }
-    __syncthreads();
-    unsigned int* out0 = wkeys0 + static_cast<size_t>(c) * cap0;
-    unsigned int* outd = wkeysd + static_cast<size_t>(c) * capd;
-    unsigned int p0 = base0_s + off0, pd = based_s + offd;
-    for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) {
-      unsigned int m = q_mask[k];
-      const float* p = col + q_elem[k];
-      while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1u;
-        const int e = bit & 15;
-        const unsigned int key = orderable(__ldg(p + (e >> 2) * (kWinThreads * 4) + (e & 3)));   // (L2 hit: read a few tiles ago)
-        if (bit < 16) { if (p0 < cap0) out0[p0] = key; ++p0; }
-        else { if (pd < capd) outd[pd] = key; ++pd; }
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) q_n = 0u;
-    __syncthreads();
-    since_check = 0;
-  };
-  auto commit_column = [&]() {  // block-uniform
-    flush();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      below0 += __shfl_xor_sync(0xffffffffu, below0, o);
-      belowd += __shfl_xor_sync(0xffffffffu, belowd, o);
-    }
-    if (lane == 0) {
-      if (below0) atomicAdd(&below0_blk, static_cast<unsigned long long>(below0));
-      if (belowd) atomicAdd(&belowd_blk, static_cast<unsigned long long>(belowd));
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (below0_blk) atomicAdd(&st->below[c], below0_blk);
-      if (belowd_blk) atomicAdd(&st->belowd[c], belowd_blk);
-      below0_blk = 0ull;
-      belowd_blk = 0ull;
-    }
-    below0 = 0u;
-    belowd = 0u;
-    __syncthreads();
-  };
-  // Ragged tile / unaligned column: per-element path, hits go straight to the global buffers (rare).
-  auto slow_hit = [&](float y, bool dev) {
-    const unsigned int g = atomicAdd(dev ? &st->cntd[c] : &st->wcnt[c], 1u);
-    if (dev) { if (g < capd) wkeysd[static_cast<size_t>(c) * capd + g] = orderable(y); }
-    else if (g < cap0) wkeys0[static_cast<size_t>(c) * cap0 + g] = orderable(y);
-  };
-
-  int next_switch = t_begin;   // first tile of the next column
-  for (int t = t_begin; t < t_end; ++t) {
-    if (t >= next_switch) {
-      if (c >= 0) commit_column();
-      c = t / tiles_per_col;
-      next_switch = (c + 1) * tiles_per_col;
-      c0 = st->c0[c];
-      r0 = st->r0[c];
-      cd = st->cd[c];
-      rd = st->rd[c];
-      col = cols + static_cast<size_t>(c) * ld;
-      aligned = (reinterpret_cast<uintptr_t>(col) & 15) == 0;
-    }
-    const long long base = static_cast<long long>(t - (next_switch - tiles_per_col)) * kWinTile;
-    if (aligned && base + kWinTile <= n) {
-      const unsigned int first = static_cast<unsigned int>(base) + threadIdx.x * 4;
-      const float* p = col + first;
-      float x[kWinPerThread];
-#pragma unroll
-      for (int q = 0; q < kWinPerThread / 4; ++q) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p + q * kWinThreads * 4));
-        x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
-      }
-      bool any = false;
-      const float nr0 = -r0, nrd = -rd;
-#pragma unroll
-      for (int e = 0; e < kWinPerThread; ++e) {
-        const float t = __fsub_rn(x[e], c0);
-        below0 += (t < nr0) ? 1u : 0u;
-        any |= fabsf(t) <= r0;
-        const float v = __fsub_rn(fabsf(t), cd);
-        belowd += (v < nrd) ? 1u : 0u;
-        any |= fabsf(v) <= rd;
-      }
-      const unsigned int hit = __ballot_sync(0xffffffffu, any);
-      if (hit) {  // warp-uniform: one shared atomic reserves the warp's entries
-        unsigned int slot = 0u;
-        if (lane == 0) slot = atomicAdd(&q_n, static_cast<unsigned int>(__popc(hit)));
-        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(hit & ((1u << lane) - 1u));
-        if (any) {
-          if (slot < kWin2Queue) q_elem[slot] = first;
-          else {  // queue full (cannot happen between two flush checks): expand here
-            for (int e = 0; e < kWinPerThread; ++e) {
-              const float y = p[(e >> 2) * (kWinThreads * 4) + (e & 3)];
-              if (in0(y)) slow_hit(y, false);
-              if (ind(y)) slow_hit(y, true);
-            }
-          }
-        }
-      }
-    } else {  // ragged last tile of a column, or a column that is not 16-byte aligned
-      for (int e = 0; e < kWinPerThread; ++e) {
-        const long long i = base + static_cast<long long>(e >> 2) * kWinThreads * 4 + threadIdx.x * 4 + (e & 3);
-        if (i < n) {
-          const float y = __ldg(col + i);
-          const float t = __fsub_rn(y, c0);
-          below0 += (t < -r0) ? 1u : 0u;
-          if (in0(y)) slow_hit(y, false);
-          belowd += (__fsub_rn(fabsf(t), cd) < -rd) ? 1u : 0u;
-          if (ind(y)) slow_hit(y, true);
-        }
-      }
-    }
-    // every thread may queue one entry per tile: flush while a whole round of tiles still fits
-    if (++since_check == 4) {
-      // (the barrier makes the decision block-uniform although the warps read the fill count at different moments)
-      if (__syncthreads_or(q_n > kWin2Queue - 4 * kWinThreads)) flush(); else since_check = 0;
-    }
-  }
-  if (c >= 0) commit_column();
-}
-
 // The histogram of the window-relative digit over the collected keys (L2-resident), one launch for all columns; the
-// last block of a column picks the target bins (window_pick).  DEV = 1 (one-pass path, MAD): the buffer holds keys of
-// VALUES collected around c0; each is re-keyed as the exact deviation |y - med|, counted as "below" when under the
-// validity window [lo, hi] armed by the median's survivor pass, histogrammed when inside, ignored when above.
+// last block of a column picks the target bins (window_pick).  (Fusing this histogram into the window pass was tried:
+// 483-498 us per pass instead of 445 + 20 -- the extra live state cost the streaming loop more than the launch.)
 constexpr int kWhistThreads = 512;
 
-template <int DEV>
 __global__ void __launch_bounds__(kWhistThreads)
 window_hist_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap, long long n, SelState* st,
                    unsigned int* __restrict__ ghist) {
   __shared__ __align__(8) WinShared ws;
-  __shared__ unsigned int below_s, in_s;
   const int c = blockIdx.y;
-  if (DEV && st->miss[c]) return;   // (uniform over the column's blocks)
   unsigned int* hist = ws.shm + kWinBuf;
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) hist[i] = 0u;
-  if (threadIdx.x == 0) { below_s = 0u; in_s = 0u; }
   __syncthreads();
-  const unsigned int lo = st->lo[c], hi = st->hi[c], span = hi - lo;
+  const unsigned int lo = st->lo[c], span = st->hi[c] - lo;
   const int wshift = st->wshift[c];
-  const float med = DEV ? st->med[c] : 0.f;
-  const unsigned int cnt = min(__ldcg(DEV ? &st->cntd[c] : &st->wcnt[c]), window_cap);
-  unsigned int my_below = 0u, my_in = 0u;
+  const unsigned int cnt = min(__ldcg(&st->wcnt[c]), window_cap);
   const unsigned int* src = wkeys + static_cast<size_t>(c) * window_cap;
   constexpr int kU = 8;   // independent loads in flight per thread (the pass is latency-bound otherwise)
   const unsigned int stride = gridDim.x * blockDim.x * kU;
@@ -966,27 +640,10 @@ window_hist_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_c
       key[u] = i < cnt ? __ldg(src + i) : 0xFFFFFFFFu;
     }
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      if (base + u * blockDim.x + threadIdx.x >= cnt) continue;
-      unsigned int k = key[u];
-      if (DEV) {
-        k = orderable(fabsf(__fsub_rn(key_to_float(k), med)));
-        if (k < lo) { ++my_below; continue; }
-        if (k > hi) continue;
-        ++my_in;
-      }
-      atomicAdd(&hist[window_digit(k, lo, span, wshift)], 1u);
-    }
-  }
-  if (DEV) {
-    if (my_below) atomicAdd(&below_s, my_below);
-    if (my_in) atomicAdd(&in_s, my_in);
+    for (int u = 0; u < kU; ++u)
+      if (base + u * blockDim.x + threadIdx.x < cnt) atomicAdd(&hist[window_digit(key[u], lo, span, wshift)], 1u);
   }
   __syncthreads();
-  if (DEV && threadIdx.x == 0) {   // (before the ticket: the picking block must see every block's counts)
-    if (below_s) atomicAdd(&st->below[c], static_cast<unsigned long long>(below_s));
-    if (in_s) atomicAdd(&st->wcnt[c], in_s);
-  }
   unsigned int* g = ghist + static_cast<size_t>(c) * 2 * kBins;
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
     const unsigned int v = hist[i];
@@ -1009,19 +666,17 @@ window_hist_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_c
 // bin) flags the column `miss` and the caller falls back to the plain radix passes.
 constexpr int kSurvThreads = 512;
 
-template <int DEV>
 __global__ void __launch_bounds__(kSurvThreads)
 survivor_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap, long long n, SelState* st,
-                unsigned int* __restrict__ surv, int final_op, unsigned int capd) {
+                unsigned int* __restrict__ surv, int final_op) {
   __shared__ unsigned int keys[kSurvCap];
   __shared__ unsigned int ticket;
   const int c = blockIdx.y;
   if (st->miss[c]) return;   // (uniform over the column's blocks: set by an earlier kernel)
-  const unsigned int lo = st->lo[c], hi = st->hi[c], span = hi - lo;
+  const unsigned int lo = st->lo[c], span = st->hi[c] - lo;
   const int wshift = st->wshift[c];
-  const float med = DEV ? st->med[c] : 0.f;
   const unsigned int b0 = st->wbin[c][0], b1 = st->wbin[c][1];
-  const unsigned int cnt = min(DEV ? st->cntd[c] : st->wcnt[c], window_cap);
+  const unsigned int cnt = min(st->wcnt[c], window_cap);
   const unsigned int* src = wkeys + static_cast<size_t>(c) * window_cap;
   unsigned int* dst = surv + static_cast<size_t>(c) * kSurvCap;
   constexpr int kU = 8;   // independent loads in flight per thread (the pass is latency-bound otherwise)
@@ -1036,10 +691,6 @@ survivor_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap,
 #pragma unroll
     for (int u = 0; u < kU; ++u) {
       if (base + u * blockDim.x + threadIdx.x >= cnt) continue;
-      if (DEV) {   // exact deviation of the collected value; only the validity window takes part
-        key[u] = orderable(fabsf(__fsub_rn(key_to_float(key[u]), med)));
-        if (key[u] < lo || key[u] > hi) continue;
-      }
       const unsigned int d = window_digit(key[u], lo, span, wshift);
       if (d == b0 || d == b1) {
         const unsigned int slot = atomicAdd(&st->surv_n[c], 1u);
@@ -1082,27 +733,6 @@ survivor_kernel(const unsigned int* __restrict__ wkeys, unsigned int window_cap,
       if (final_op == FINAL_MED) {
         st->med[c] = mid;
         arm_sample(st, c);   // the MAD's sample selection follows
-      } else if (final_op == FINAL_MED_1P) {
-        // One-pass path: the MAD's keys are already collected (values with A <= |y - c0| <= B; `belowd` elements have
-        // |y - c0| < A).  With delta = |c0 - med| every uncollected element has an exact deviation below L = A + delta
-        // or above U = B - delta, so for x in [L, U]: #(deviation < x) = belowd + #(collected with deviation < x) --
-        // the selection among the collected keys inside [L, U] is exact.  (Slack: 2^-18 of the magnitudes involved.)
-        st->med[c] = mid;
-        const float c0 = st->c0[c], a = st->A[c], bb = st->B[c];
-        const float delta = fabsf(c0 - mid) * 1.0000038146972656f + (fabsf(c0) + fabsf(mid) + bb) * 3.814697265625e-06f;
-        const float L = a + delta, U = bb - delta;
-        const unsigned int lk = orderable(L), uk = orderable(U);
-        if (!(U >= L) || !(U < INFINITY) || st->cntd[c] > capd) {
-          st->miss[c] = 1;
-        } else {
-          st->lo[c] = lk;
-          st->hi[c] = uk;
-          const unsigned int sp = uk - lk;
-          const int nbits = sp ? 32 - __clz(static_cast<int>(sp)) : 1;
-          st->wshift[c] = max(nbits - kWindowDigitBits, 0);
-          st->below[c] = st->belowd[c];
-          st->wcnt[c] = 0u;   // recounted by the deviation histogram: keys inside [L, U]
-        }
       } else {
         st->mad[c] = mid;
       }
@@ -1176,8 +806,6 @@ struct FitWork {
   unsigned int* ghist = nullptr;
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
-  unsigned int* wkeysd = nullptr; // one-pass path: keys of the values collected around c0 for the MAD
-  size_t wkeysd_bytes = 0;
   unsigned int* surv = nullptr;   // [columns][kSurvCap] keys of the target bins
   unsigned int* done = nullptr;   // per-column block tickets of hist_kernel / sample_kernel (self-resetting)
   size_t ghist_bytes = 0, skeys_bytes = 0, wkeys_bytes = 0, surv_bytes = 0;
@@ -1270,54 +898,12 @@ void fit_windowed_stat(const float* cols, long long n, int f, long long ld, unsi
                                                                              w.ghist, w.done, OP_WINDOW_BOUNDS);
   }
   g_fit_timer.mark(stream, "hist");
-  if (env_int("DEWI_FIT_FUSED", kFitFusedDefault)) {
-    window_kernel<SRC, 1><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
-    g_fit_timer.mark(stream, "window+hist");
-  } else {
-    window_kernel<SRC, 0><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap, w.ghist);
-    g_fit_timer.mark(stream, "window");
-    window_hist_kernel<0><<<dim3(std::max(1, w.sm_count * 4 / f), f), kWhistThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.ghist);
-    g_fit_timer.mark(stream, "whist");
-  }
-  survivor_kernel<0><<<dim3(std::max(1, w.sm_count * 4 / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op, 0u);
-  g_fit_timer.mark(stream, "survivor");
-}
-
-// Both statistics from ONE pass over the columns (the state must be armed for a sample selection):
-//   sample_kernel           sample keys + first histogram pass
-//   hist_kernel             coarse pass  ->  median window [lo, hi], its centre c0 and half-width w
-//   hist_kernel x 2         the same two passes over the sample's deviations |s - c0|  ->  deviation window [A, B]
-//   window2_kernel          THE pass: median-window keys and deviation-window keys collected together
-//   window_hist + survivor  exact median (as in the two-pass path), then the validity window [L, U] of exact deviations
-//   window_hist + survivor  (DEV) exact MAD among the collected values, re-keyed as |y - med|
-void fit_onepass(const float* cols, long long n, int f, long long ld, unsigned int cap0, unsigned int capd, FitWork& w,
-                 cudaStream_t stream) {
-  const dim3 small(std::max(1, w.sm_count * 4 / f), f);
-  const int threads = 512, per_thread = 8;
-  const int bx = static_cast<int>(std::min<int64_t>(ceil_div(kSample, threads * per_thread), std::max(1, w.sm_count * 4 / f)));
-  const dim3 hgrid(std::max(bx, 1), f);
-  sample_kernel<SRC_RAW><<<dim3(kSampleBlocks, f), 256, 0, stream>>>(cols, n, ld, w.st, w.skeys, w.ghist, w.done,
-                                                                       (n - kSampleRunLen) / (kSampleRuns - 1),
-                                                                       static_cast<int>((n - kSampleRunLen) % (kSampleRuns - 1)));
-  g_fit_timer.mark(stream, "sample");
-  hist_kernel<SRC_KEYS><<<hgrid, threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, kSamplePass1, w.st, w.ghist, w.done,
-                                                       OP_WINDOW_BOUNDS_1P);
-  g_fit_timer.mark(stream, "hist");
-  hist_kernel<SRC_SKEY_DEV><<<hgrid, threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, 0, w.st, w.ghist, w.done, OP_NONE);
-  g_fit_timer.mark(stream, "dev-hist0");
-  hist_kernel<SRC_SKEY_DEV><<<hgrid, threads, 0, stream>>>(w.skeys, kSample, nullptr, kSample, kSamplePass1, w.st, w.ghist, w.done,
-                                                           OP_DEV_BOUNDS);
-  g_fit_timer.mark(stream, "dev-hist1");
-  window2_kernel<0><<<w.sm_count * kWin2BlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap0, w.wkeysd, capd);
-  g_fit_timer.mark(stream, "window2");
-  window_hist_kernel<0><<<small, kWhistThreads, 0, stream>>>(w.wkeys, cap0, n, w.st, w.ghist);
+  window_kernel<SRC><<<w.sm_count * kWinBlocksPerSm, kWinThreads, 0, stream>>>(cols, n, ld, f, w.st, w.wkeys, cap);
+  g_fit_timer.mark(stream, "window");
+  window_hist_kernel<<<dim3(std::max(1, w.sm_count * 4 / f), f), kWhistThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.ghist);
   g_fit_timer.mark(stream, "whist");
-  survivor_kernel<0><<<small, kSurvThreads, 0, stream>>>(w.wkeys, cap0, n, w.st, w.surv, FINAL_MED_1P, capd);
+  survivor_kernel<<<dim3(std::max(1, w.sm_count * 4 / f), f), kSurvThreads, 0, stream>>>(w.wkeys, cap, n, w.st, w.surv, final_op);
   g_fit_timer.mark(stream, "survivor");
-  window_hist_kernel<1><<<small, kWhistThreads, 0, stream>>>(w.wkeysd, capd, n, w.st, w.ghist);
-  g_fit_timer.mark(stream, "dev-whist");
-  survivor_kernel<1><<<small, kSurvThreads, 0, stream>>>(w.wkeysd, capd, n, w.st, w.surv, FINAL_MAD, capd);
-  g_fit_timer.mark(stream, "dev-survivor");
 }
 
 }  // namespace
@@ -1336,12 +922,8 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   DEWI_CUDA(cudaSetDevice(device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool windowed = n >= kWindowMinRows;
-  // expected window population is 2 * margin / sample = 0.5 % of n (+ the outward rounding of its bounds); allow 1.6 %
+  // expected window population is 2 * margin / sample = 0.8 % of n; allow twice that
   const unsigned int cap = windowed ? static_cast<unsigned int>(std::min<int64_t>(n / 64 + 65536, 1ll << 30)) : 0u;
-  // one-pass path: the deviation window holds its own 0.5 % plus 4 half-widths of the median window on either side
-  // (~2.5 % on smooth densities); allow 6.25 %
-  const bool onepass = windowed && env_int("DEWI_FIT_ONEPASS", kFitOnePassDefault) != 0;
-  const unsigned int capd = onepass ? static_cast<unsigned int>(std::min<int64_t>(n / 16 + 65536, 1ll << 30)) : 0u;
   if (device >= 64) return fail("device ordinal out of range");
   std::lock_guard<std::mutex> lock(g_fit_mu);
   FitWork& w = g_fit_work[device];
@@ -1356,7 +938,6 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
     DEWI_TRY(ensure_buf(&w.skeys, &w.skeys_bytes, static_cast<size_t>(f) * kSample * 4));
     DEWI_TRY(ensure_buf(&w.wkeys, &w.wkeys_bytes, static_cast<size_t>(f) * cap * 4));
     DEWI_TRY(ensure_buf(&w.surv, &w.surv_bytes, static_cast<size_t>(kMaxCols) * kSurvCap * 4));
-    if (onepass) DEWI_TRY(ensure_buf(&w.wkeysd, &w.wkeysd_bytes, static_cast<size_t>(f) * capd * 4));
   }
   DEWI_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SelState), stream));
   DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
@@ -1367,12 +948,8 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
     g_fit_timer.mark(stream, "start");
     glue_kernel<<<1, kMaxCols, 0, stream>>>(ARM_SAMPLE, f, n, cap, w.st);
     g_fit_timer.mark(stream, "arm");
-    if (onepass) {
-      fit_onepass(cols, n, f, ld, cap, capd, w, stream);
-    } else {
-      fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
-      fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
-    }
+    fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
+    fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
     DEWI_CUDA(cudaGetLastError());
     DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
