@@ -44,17 +44,18 @@ constexpr int kWindowDigitBits = 11;             // window-relative digit of the
 constexpr int kSurvCap = 8192;                   // keys of the target bins sorted in shared memory (typically a few hundred)
 
 struct SelState {
+  // results first: the host reads back exactly this head (FitResult) into pinned memory
+  float med[kMaxCols];
+  float mad[kMaxCols];
+  int miss[kMaxCols];                       // window overflowed or does not hold the target ranks
   // radix selection, per column, two rank slots
   unsigned int prefix[kMaxCols][2];
   unsigned long long rank[kMaxCols][2];
   int same[kMaxCols];  // both slots still share one prefix -> one histogram serves both
-  float med[kMaxCols];
-  float mad[kMaxCols];
   // windowed path
   unsigned int lo[kMaxCols], hi[kMaxCols];  // inclusive key window
   unsigned long long below[kMaxCols];       // keys < lo
   unsigned int wcnt[kMaxCols];              // keys appended to the window buffer
-  int miss[kMaxCols];                       // window overflowed or does not hold the target ranks
   // in-window selection: digit = (key - lo) >> wshift is the top <= 11 bits of the window's key span
   int wshift[kMaxCols];
   unsigned int wbin[kMaxCols][2];           // digits of the two middle ranks
@@ -801,8 +802,15 @@ score_kernel(const InT* __restrict__ cols, long long n, long long ld, const Scor
 
 // Work buffers are kept per device between calls (grow-only): cudaMalloc / cudaFree would cost more
 // than the kernels.  Calls are serialised by the mutex (the C ABI is one-thread-per-handle anyway).
+struct FitResult {   // == the head of SelState
+  float med[kMaxCols];
+  float mad[kMaxCols];
+  int miss[kMaxCols];
+};
+
 struct FitWork {
   SelState* st = nullptr;
+  FitResult* res_host = nullptr;   // pinned: the read-back is one small asynchronous copy
   unsigned int* ghist = nullptr;
   unsigned int* skeys = nullptr;
   unsigned int* wkeys = nullptr;
@@ -919,7 +927,16 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   if (ld < n) return fail("ld must be >= n");
   int sms = 148;
   DEWI_TRY(dewi_device_check(device, &sms, nullptr, nullptr));
-  DEWI_CUDA(cudaSetDevice(device));
+  struct DeviceGuard {   // the caller's current device is left as it was (the Python wrapper no longer switches it)
+    int prev = -1, want;
+    explicit DeviceGuard(int d) : want(d) {
+      cudaGetDevice(&prev);
+      if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() {
+      if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+  } guard(device);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const bool windowed = n >= kWindowMinRows;
   // expected window population is 2 * margin / sample = 0.8 % of n; allow twice that
@@ -929,6 +946,8 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   FitWork& w = g_fit_work[device];
   w.sm_count = sms;
   if (!w.st) DEWI_CUDA(cudaMalloc(&w.st, sizeof(SelState)));
+  if (!w.res_host) DEWI_CUDA(cudaHostAlloc(&w.res_host, sizeof(FitResult), cudaHostAllocDefault));
+  const bool fresh_hist = w.ghist_bytes == 0;
   if (!w.done) {
     DEWI_CUDA(cudaMalloc(&w.done, kMaxCols * sizeof(unsigned int)));
     DEWI_CUDA(cudaMemsetAsync(w.done, 0, kMaxCols * sizeof(unsigned int), stream));
@@ -940,8 +959,9 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
     DEWI_TRY(ensure_buf(&w.surv, &w.surv_bytes, static_cast<size_t>(kMaxCols) * kSurvCap * 4));
   }
   DEWI_CUDA(cudaMemsetAsync(w.st, 0, sizeof(SelState), stream));
-  DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(f) * 2 * kBins * 4, stream));
-  SelState res;
+  // (the histograms are zeroed once: every pass leaves them clean behind its pick)
+  if (fresh_hist) DEWI_CUDA(cudaMemsetAsync(w.ghist, 0, static_cast<size_t>(kMaxCols) * 2 * kBins * 4, stream));
+  FitResult& res = *w.res_host;
   bool need_full = !windowed;
   if (windowed) {
     g_fit_timer.on = env_set("DEWI_FIT_TIMING");
@@ -951,7 +971,7 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
     fit_windowed_stat<SRC_RAW>(cols, n, f, ld, cap, w, FINAL_MED, stream);
     fit_windowed_stat<SRC_DEV>(cols, n, f, ld, cap, w, FINAL_MAD, stream);
     DEWI_CUDA(cudaGetLastError());
-    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(FitResult), cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
     g_fit_timer.report();
     for (int c = 0; c < f; ++c) need_full = need_full || res.miss[c] != 0;  // e.g. a huge tie group at the median
@@ -960,7 +980,7 @@ extern "C" int dewi_fit_stats(const float* cols, int64_t n, int f, int64_t ld, d
   if (need_full) {
     fit_full(cols, n, f, ld, w, stream);
     DEWI_CUDA(cudaGetLastError());
-    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(res), cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaMemcpyAsync(&res, w.st, sizeof(FitResult), cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
   }
   for (int c = 0; c < f; ++c) {

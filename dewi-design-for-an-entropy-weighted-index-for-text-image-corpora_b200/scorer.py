@@ -40,9 +40,9 @@ def _fit_columns(cols, device: int, zero_mad_as: float = 1e-8):
     f, n = cols.shape
     med = (ctypes.c_double * f)()
     mad = (ctypes.c_double * f)()
-    with torch.cuda.device(device):
-        rc = lib.dewi_fit_stats(ctypes.c_void_p(cols.data_ptr()), n, f, cols.stride(0), med, mad, device,
-                                _native.stream_ptr())
+    # (the library selects the device itself; the stream is the current one of THAT device)
+    rc = lib.dewi_fit_stats(ctypes.c_void_p(cols.data_ptr()), n, f, cols.stride(0), med, mad, device,
+                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
     _native.check(rc)
     mad_arr = np.array(mad[:], dtype=np.float64)
     if zero_mad_as != 1e-8:
