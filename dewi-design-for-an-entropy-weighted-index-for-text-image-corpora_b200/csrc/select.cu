@@ -422,7 +422,8 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
 // per-query independent, so block-level barriers replace the launches; selections are done by RANK COUNTING
 // (every thread counts how many keys beat its own: a few hundred broadcast shared-memory reads) instead of bitonic
 // sorts (dozens of block-wide barrier rounds each), which is what made the separate kernels latency-bound.
-constexpr int kTailThreads = 512;
+constexpr int kTailThreads = 512;      // per block when there are blocks to spare; small batches use kTailThreadsWide
+constexpr int kTailThreadsWide = 1024; // B <= #SMs: one block per SM at most, so the block itself should be wide
 constexpr int kTailWindow = 2048;     // candidate keys gathered between two selections
 constexpr int kTailMaxKc = 512;       // list capacity the fused tail supports (longer lists use the separate kernels)
 
@@ -505,7 +506,7 @@ __device__ __forceinline__ float exact_dot(const RowT* __restrict__ r, const flo
   return acc;
 }
 
-__global__ void __launch_bounds__(kTailThreads)
+__global__ void __launch_bounds__(kTailThreadsWide)
 tail_kernel(const TailArgs a) {
   __shared__ unsigned long long win[kTailWindow];      // keys gathered from the partial lists
   __shared__ unsigned long long best[2][kTailMaxKc];   // running best (sorted), double-buffered
@@ -543,8 +544,12 @@ tail_kernel(const TailArgs a) {
     __syncthreads();
     const int fill = fill_s;
     __syncthreads();   // everybody has read the fill count before the next round's appends move it
-    // (a selection runs while the window still has room for the next round's keys AND the running best behind them)
-    if (fill > kTailWindow - 2 * static_cast<int>(blockDim.x) - kTailMaxKc || base + static_cast<int>(blockDim.x) >= total) {
+    // A selection costs (fill + nb)^2 / blockDim comparisons per thread, so it runs EARLY: as soon as a few hundred keys
+    // are waiting -- after the first one the admission bar is the kc-th best so far and later rounds add a handful
+    // (measured at 12.5M rows, B = 64, ~4600 valid partial entries per query: 54 us with selections of ~1000 keys, see
+    // profiles/).  It must run while the window still has room for the next round's keys and the running best.
+    if (fill >= 256 || fill > kTailWindow - 2 * static_cast<int>(blockDim.x) - kTailMaxKc ||
+        base + static_cast<int>(blockDim.x) >= total) {
       const int nb = nb_s;
       // append the running best to the window, then select into the other buffer
       for (int t = threadIdx.x; t < nb; t += blockDim.x) win[fill + t] = best[cur][t];
@@ -786,7 +791,7 @@ int launch_tail(const Partials& p, int B, const TailCert* cert, const void* rows
   a.fin_id = rr ? reinterpret_cast<long long*>(rr->out_id) : nullptr;
   a.fin_score = rr ? rr->out_score : nullptr;
   if (rows && dim % 8 != 0) return fail("fused tail: the exact re-score needs dim % 8 == 0");
-  tail_kernel<<<B, kTailThreads, 0, stream>>>(a);
+  tail_kernel<<<B, B <= current_sm_count() ? kTailThreadsWide : kTailThreads, 0, stream>>>(a);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
