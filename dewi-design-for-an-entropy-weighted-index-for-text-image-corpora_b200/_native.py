@@ -27,6 +27,7 @@ FLAG_NO_PAIR = 1 << 6
 FLAG_NO_SEED = 1 << 7
 FLAG_NO_M64 = 1 << 8
 FLAG_NO_CERT = 1 << 9
+FLAG_FORCE_CERT = 1 << 10
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2

@@ -489,10 +489,11 @@ class CudaIndex(BaseIndex):
         ids, scores = self._search_host(query.reshape(1, -1), k, float(eta), float(entropy_pref),
                                         _native.FLAG_QUERY_NORMALIZED)
         doc_ids, payloads = self._doc_ids, self._payloads
+        by_row = payloads.at if isinstance(payloads, ColumnPayloads) else None  # (column store: no id -> row search)
         out = []
-        for row, s in zip(ids[0], scores[0]):
-            d = doc_ids[int(row)]
-            out.append((d, float(s), payloads[d]))
+        for row, s in zip(ids[0].tolist(), scores[0].tolist()):
+            d = doc_ids[row]
+            out.append((d, s, by_row(row) if by_row else payloads[d]))
         return out
 
     def _search_host(self, queries: np.ndarray, k: int, eta: float, entropy_pref: float, flags: int = 0):
@@ -502,11 +503,11 @@ class CudaIndex(BaseIndex):
         b = q.shape[0]
         ids = np.empty((b, k), dtype=np.int64)
         scores = np.empty((b, k), dtype=np.float32)
-        with torch.cuda.device(self.device):
-            rc = self._lib.dewi_index_search(self._h, ctypes.c_void_p(q.ctypes.data), b, int(k), float(eta),
-                                             float(entropy_pref), flags | self._flags | _native.FLAG_HOST_IO,
-                                             ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(scores.ctypes.data),
-                                             _native.stream_ptr())
+        # (the library selects the handle's device itself and restores the caller's; the stream is that device's current one)
+        rc = self._lib.dewi_index_search(self._h, ctypes.c_void_p(q.ctypes.data), b, int(k), float(eta),
+                                         float(entropy_pref), flags | self._flags | _native.FLAG_HOST_IO,
+                                         ctypes.c_void_p(ids.ctypes.data), ctypes.c_void_p(scores.ctypes.data),
+                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         _native.check(rc)
         return ids, scores
 

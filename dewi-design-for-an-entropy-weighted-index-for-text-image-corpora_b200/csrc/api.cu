@@ -99,6 +99,13 @@ struct dewi_index {
   int* bad_flag = nullptr;
   // certified single-plane sweep (fp32 corpus): running maxima of ||row - hi|| and ||hi|| (float bits), a fail counter
   unsigned int* plane_max = nullptr;   // [2] plane maxima, [2] = certificate fail counter
+  // host I/O (DEWI_FLAG_HOST_IO): pinned staging so the query upload and the result download are one small truly
+  // asynchronous copy each (pageable copies go through the driver's own staging and cost ~10-20 us apiece -- more than
+  // the kernels of a single-query search over a small corpus)
+  void* pin_q = nullptr;
+  size_t pin_q_bytes = 0;
+  void* pin_out = nullptr;
+  size_t pin_out_bytes = 0;
   long long cert_used = 0, cert_failed = 0;   // searches answered by the certified sweep / re-run with the full product
   bool plane_max_stale = false;               // plane_max changed on the device since plane_hi_max was read
   float plane_hi_max = 0.f;                   // host copy of max_r ||hi_r|| (fp16 planes: range guard)
@@ -273,6 +280,8 @@ int dewi_index_destroy(dewi_index_t* h) {
   cudaFree(h->ent_col);
   cudaFree(h->bad_flag);
   cudaFree(h->plane_max);
+  if (h->pin_q) cudaFreeHost(h->pin_q);
+  if (h->pin_out) cudaFreeHost(h->pin_out);
   for (int i = 0; i < dewi_index::kEvRing; ++i) {
     if (h->ev0[i]) cudaEventDestroy(h->ev0[i]);
     if (h->ev1[i]) cudaEventDestroy(h->ev1[i]);
@@ -584,7 +593,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   // more densely than the bound resolves) the batch is re-run with the full hi/lo product: exact either way.
   int cert_planes = 0;
   if (use_tc && mode == 2 && !(flags & DEWI_FLAG_NO_CERT) && env_int("DEWI_CERT", 1) != 0 &&
-      static_cast<int64_t>(h->n) * dim >= kCertMinElems) {
+      (static_cast<int64_t>(h->n) * dim >= kCertMinElems || (flags & DEWI_FLAG_FORCE_CERT))) {
     const int planes = 1;
     // List capacity.  With fp16 planes the bound is eps ~ 6e-4 at dim 768 (2.1e-4 per rounded operand, 1.8e-4 for the
     // accumulation): ~23 rows are expected inside the proof's margin at k = 10 on 1M Gaussian rows, with a heavier
@@ -820,13 +829,41 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   if (B <= 0 || k <= 0) return fail("B and k must be positive");
   if (k > h->n) return fail("k exceeds the number of indexed rows (ExactIndex raises ValueError, backends.py:468)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  DEWI_TRY(set_device(h));
+  // (the caller's current device is left as it was: the Python wrapper does not switch it around the call)
+  struct DeviceGuard {
+    int prev = -1, want;
+    explicit DeviceGuard(int d) : want(d) {
+      cudaGetDevice(&prev);
+      if (prev != want) cudaSetDevice(want);
+    }
+    ~DeviceGuard() {
+      if (prev >= 0 && prev != want) cudaSetDevice(prev);
+    }
+  } guard(h->device);
   const int kcand = static_cast<int>(std::min<int64_t>(2 * static_cast<int64_t>(k), h->n));  // backends.py:440
   const bool host_io = (flags & DEWI_FLAG_HOST_IO) != 0;
   const float* q_dev = queries;
+  auto pinned = [](void** p, size_t* have, size_t need) -> int {
+    if (need <= *have) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    DEWI_CUDA(cudaHostAlloc(p, need + need / 2, cudaHostAllocDefault));
+    *have = need + need / 2;
+    return 0;
+  };
+  const size_t q_bytes = static_cast<size_t>(B) * h->dim * 4;
+  // small batches go through pinned staging; large ones are copied straight from the caller's memory
+  const bool stage_io = host_io && q_bytes <= (size_t(4) << 20);
   if (host_io) {
-    DEWI_TRY(h->qraw.ensure(static_cast<size_t>(B) * h->dim * 4));
-    DEWI_CUDA(cudaMemcpyAsync(h->qraw.p, queries, static_cast<size_t>(B) * h->dim * 4, cudaMemcpyHostToDevice, stream));
+    DEWI_TRY(h->qraw.ensure(q_bytes));
+    const void* src = queries;
+    if (stage_io) {
+      DEWI_TRY(pinned(&h->pin_q, &h->pin_q_bytes, q_bytes));
+      std::memcpy(h->pin_q, queries, q_bytes);
+      src = h->pin_q;
+    }
+    DEWI_CUDA(cudaMemcpyAsync(h->qraw.p, src, q_bytes, cudaMemcpyHostToDevice, stream));
     q_dev = h->qraw.as<float>();
   }
   const size_t nc = static_cast<size_t>(B) * kcand;
@@ -836,11 +873,11 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   DEWI_TRY(h->loc_ent.ensure(nc * 4));
   int64_t* d_id = out_id;
   float* d_sc = out_score;
-  if (host_io) {
-    DEWI_TRY(h->out_id.ensure(static_cast<size_t>(B) * k * 8));
-    DEWI_TRY(h->out_score.ensure(static_cast<size_t>(B) * k * 4));
+  const size_t id_bytes = static_cast<size_t>(B) * k * 8, sc_bytes = static_cast<size_t>(B) * k * 4;
+  if (host_io) {   // ids and scores share one device buffer, so the download is one copy
+    DEWI_TRY(h->out_id.ensure(id_bytes + sc_bytes));
     d_id = h->out_id.as<int64_t>();
-    d_sc = h->out_score.as<float>();
+    d_sc = reinterpret_cast<float*>(h->out_id.as<char>() + id_bytes);
   }
   // numpy evaluates (1 - eta) in float64 and rounds the weak scalar to float32 (backends.py:461)
   const float w_sim = static_cast<float>(1.0 - eta);
@@ -855,9 +892,15 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
                            B, 1, kcand, 0, kcand, k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc, stream));
     h->last_launches++;
   }
-  if (host_io) {
-    DEWI_CUDA(cudaMemcpyAsync(out_id, d_id, static_cast<size_t>(B) * k * 8, cudaMemcpyDeviceToHost, stream));
-    DEWI_CUDA(cudaMemcpyAsync(out_score, d_sc, static_cast<size_t>(B) * k * 4, cudaMemcpyDeviceToHost, stream));
+  if (host_io && stage_io) {
+    DEWI_TRY(pinned(&h->pin_out, &h->pin_out_bytes, id_bytes + sc_bytes));
+    DEWI_CUDA(cudaMemcpyAsync(h->pin_out, d_id, id_bytes + sc_bytes, cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(out_id, h->pin_out, id_bytes);
+    std::memcpy(out_score, static_cast<char*>(h->pin_out) + id_bytes, sc_bytes);
+  } else if (host_io) {
+    DEWI_CUDA(cudaMemcpyAsync(out_id, d_id, id_bytes, cudaMemcpyDeviceToHost, stream));
+    DEWI_CUDA(cudaMemcpyAsync(out_score, d_sc, sc_bytes, cudaMemcpyDeviceToHost, stream));
     DEWI_CUDA(cudaStreamSynchronize(stream));
   }
   return 0;

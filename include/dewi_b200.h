@@ -55,8 +55,10 @@ enum {
   DEWI_FLAG_NO_PAIR = 1 << 6,          /* B > 128: keep the 1-CTA sweep instead of the CTA-pair one  */
   DEWI_FLAG_NO_SEED = 1 << 7,          /* skip the sample pre-pass that seeds admission thresholds    */
   DEWI_FLAG_NO_M64 = 1 << 8,           /* B <= 64: keep M = 128 MMAs instead of M = 64                */
-  DEWI_FLAG_NO_CERT = 1 << 9           /* fp32 corpus: always sweep the full hi/lo product (3 MMAs, both planes) instead
+  DEWI_FLAG_NO_CERT = 1 << 9,          /* fp32 corpus: always sweep the full hi/lo product (3 MMAs, both planes) instead
                                           of the certified single-plane sweep (hi plane + proof + exact re-score)       */
+  DEWI_FLAG_FORCE_CERT = 1 << 10       /* fp32 corpus: use the certified sweep even on a corpus too small to repay its
+                                          host synchronisation (tests)                                                  */
 };
 
 /* ---- library ------------------------------------------------------------------------------ */

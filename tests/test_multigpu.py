@@ -218,3 +218,86 @@ def test_push_timeout_reports_instead_of_trapping():
         if "unavailable" in ret:
             pytest.skip(f"fused exchange unavailable here: {ret['unavailable']}")
         assert ret["timed_out_ids_are_minus_one"] and ret["raised"] and ret["context_alive"] and ret["late_rank_ok"]
+
+
+def _cert_worker(rank, world, port, exchange, ret):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dewi_b200 import ShardedDewiIndex, _native, shard_range
+
+        emb, pay, queries = _cert_corpus()
+        n, d = emb.shape
+        lo, hi = shard_range(n, world, rank, align=128)
+        ix = ShardedDewiIndex(d, dtype="fp32", device=rank, exchange=exchange)
+        ix.local._flags |= _native.FLAG_FORCE_CERT | _native.FLAG_FORCE_TC
+        ix.add_local(emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        ix.build()
+        q = torch.from_numpy(queries).cuda()
+        try:
+            ids, sc = ix.search_batch(q, k=10, eta=0.0, entropy_pref=0.0)
+        except RuntimeError as exc:
+            if exchange == "push" and ("symmetric memory" in str(exc) or "unavailable" in str(exc)):
+                ret["unavailable"] = str(exc)
+                return
+            raise
+        ids2, sc2 = ix.search_batch(q, k=10, eta=0.0, entropy_pref=0.0)
+        assert torch.equal(ids, ids2) and torch.equal(sc, sc2)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ret[f"cert{rank}"] = ix.local.cert_stats()
+        if rank == 0:
+            ret["ids"], ret["scores"] = ids.cpu().numpy(), sc.cpu().numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def _cert_corpus():
+    """300 rows packed within 2e-4 of each other at the top of query 0's ranking, all inside the FIRST shard: that
+    shard's certificate cannot be given, the others' can."""
+    from _util import make_corpus
+
+    n, d = 48_000, 256
+    rng = np.random.RandomState(55)
+    emb, pay = make_corpus(n, d, seed=56)
+    target = rng.standard_normal(d).astype(np.float32)
+    target /= np.linalg.norm(target)
+    for j, row in enumerate(rng.choice(4000, 300, replace=False)):
+        v = target + (2e-3 + 1e-6 * j) * rng.standard_normal(d).astype(np.float32)
+        emb[row] = v / np.linalg.norm(v)
+    queries = np.stack([target] + [rng.standard_normal(d).astype(np.float32) for _ in range(7)])
+    return emb, pay, queries
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "push"])
+def test_sharded_certified_sweep_with_a_failing_certificate(exchange):
+    """fp32 shards swept through the single fp16 plane: the rank whose certificate fails re-runs its shard with the full
+    hi/lo product -- in the fused exchange its ready flags are withheld until then -- and the global answer is exact."""
+    import torch.multiprocessing as mp
+
+    from oracle import search as osearch
+
+    from _util import check_topk, entropy_column
+
+    world = min(torch.cuda.device_count(), 8)
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_cert_worker, args=(world, port, exchange, ret), nprocs=world, join=True)
+        if "unavailable" in ret:
+            pytest.skip(f"fused exchange unavailable here: {ret['unavailable']}")
+        ids, scores = ret["ids"], ret["scores"]
+        stats = [ret[f"cert{r}"] for r in range(world)]
+    assert stats[0] == (2, 2), stats            # rank 0: certified sweep tried twice, re-run twice
+    assert all(s == (2, 0) for s in stats[1:]), stats
+    emb, pay, queries = _cert_corpus()
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), queries, 10, 0.0, 0.0, True)
+    for i in range(len(queries)):
+        check_topk(rid[i], rsc[i], ids[i], scores[i], what=f"{exchange} q{i}")

@@ -1,5 +1,6 @@
 """Redundancy similarity pass: dense product vs torch's F.normalize + matmul fixtures
-(redundancy.py:36-38); thresholded join vs this repository's CPU restatement (parity unpinned)."""
+(redundancy.py:36-38); thresholded join vs the reductions of the reference's own dense matrix on the fixtures, and vs this
+repository's CPU restatement at larger sizes (the reductions themselves have no reference definition: parity unpinned)."""
 
 import numpy as np
 import pytest
@@ -18,6 +19,31 @@ def test_golden_dense_similarity(name):
     sim = dewi_b200.cross_modal_similarity(g["tfeat"], g["ifeat"])
     assert isinstance(sim, np.ndarray) and sim.shape == g["sim"].shape and sim.dtype == np.float32
     np.testing.assert_allclose(sim, g["sim"], atol=1e-6, rtol=0)
+
+
+@pytest.mark.parametrize("force", ["simt", "tc"])
+@pytest.mark.parametrize("name", ["t37_i53_d512", "t64_i64_d64"])
+def test_join_reductions_of_the_references_own_matrix(name, force):
+    """The thresholded join has no reference definition, but what it reduces does: the dense matrix the reference's
+    `F.normalize(T) @ F.normalize(I).T` produced for the fixture (redundancy.py:36-38, written by make_golden.py from
+    torch).  Row maximum, argmax, count >= tau and the pair list must be exactly the reductions of THAT matrix, up to
+    elements within rounding of the threshold."""
+    g = np.load(GOLD / f"redundancy_{name}.npz")
+    sim, tau = g["sim"], 0.9
+    tol = 2e-6 if force == "simt" else 1e-5
+    out = dewi_b200.redundancy_join(g["tfeat"], g["ifeat"], tau=tau, force=force)
+    t = sim.shape[0]
+    np.testing.assert_allclose(out["max_sim"].cpu().numpy(), sim.max(axis=1), atol=tol)
+    am = out["argmax"].cpu().numpy()
+    assert np.all(sim[np.arange(t), am] >= sim.max(axis=1) - tol)
+    edge = (np.abs(sim - tau) <= tol).sum(axis=1)
+    assert np.all(np.abs(out["count"].cpu().numpy() - (sim >= tau).sum(axis=1)) <= edge)
+    got = set(zip(out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist()))
+    ref = set(zip(*np.nonzero(sim >= tau)))
+    ref = {(int(i), int(j)) for i, j in ref}
+    assert ref and all(abs(sim[i, j] - tau) <= tol for i, j in got ^ ref)
+    for i, j, sv in zip(out["pairs_i"].cpu().tolist(), out["pairs_j"].cpu().tolist(), out["pairs_sim"].cpu().tolist()):
+        assert abs(sv - sim[i, j]) <= tol
 
 
 def planted(n, d, seed, frac=0.02):
