@@ -364,51 +364,56 @@ rerank_kernel(const float* __restrict__ sim, const long long* __restrict__ id, c
       return;
     }
   }
+  // Selections by rank counting (keys are (score, ~id): distinct among valid candidates): a couple of hundred broadcast
+  // shared-memory reads per thread instead of two bitonic sorts of ~40 barrier rounds each.
   const int ncand = n_shards * kcand;
   const int p = next_pow2(ncand);
-  unsigned long long* key = sh;
-  int* val = reinterpret_cast<int*>(sh + p);
+  unsigned long long* key = sh;                                   // [ncand] similarity keys, then adjusted-score keys
+  int* val = reinterpret_cast<int*>(sh + p);                      // [ncand] candidate slot of the entry ranked t-th by similarity
   float* adj = reinterpret_cast<float*>(val + p);
   const int b = blockIdx.x;
   // 1. candidate set: the cand_count best by similarity (backends.py:439-447)
-  for (int t = threadIdx.x; t < p; t += blockDim.x) {
-    unsigned long long kk = 0ull;
-    int vv = -1;
-    if (t < ncand) {
-      const long long g = shard_at(id, t, b, kcand, shard_stride);
-      if (g >= 0) { kk = make_key(shard_at(sim, t, b, kcand, shard_stride), static_cast<uint32_t>(g)); vv = t; }
-    }
-    key[t] = kk;
-    val[t] = vv;
+  for (int t = threadIdx.x; t < ncand; t += blockDim.x) {
+    const long long g = shard_at(id, t, b, kcand, shard_stride);
+    key[t] = (g >= 0) ? make_key(shard_at(sim, t, b, kcand, shard_stride), static_cast<uint32_t>(g)) : 0ull;
+    val[t] = -1;
   }
-  bitonic_sort_desc(key, val, p);
+  __syncthreads();
+  for (int e = threadIdx.x; e < ncand; e += blockDim.x) {
+    const unsigned long long x = key[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < ncand; ++f) rank += (key[f] > x) ? 1 : 0;
+    if (rank < cand_count) val[rank] = e;
+  }
+  __syncthreads();
   // 2. blend in fp32, one rounding per operation as numpy does (backends.py:461-465)
-  for (int t = threadIdx.x; t < p; t += blockDim.x) {
+  for (int t = threadIdx.x; t < ncand; t += blockDim.x) {
     const int slot = (t < cand_count) ? val[t] : -1;
     unsigned long long kk = 0ull;
-    float a = 0.f;
     if (slot >= 0) {
-      a = __fadd_rn(__fmul_rn(w_sim, shard_at(sim, slot, b, kcand, shard_stride)),
-                    __fmul_rn(w_dewi, shard_at(dewi, slot, b, kcand, shard_stride)));
+      float a = __fadd_rn(__fmul_rn(w_sim, shard_at(sim, slot, b, kcand, shard_stride)),
+                          __fmul_rn(w_dewi, shard_at(dewi, slot, b, kcand, shard_stride)));
       if (use_pref) a = __fadd_rn(a, __fmul_rn(pref, shard_at(ent, slot, b, kcand, shard_stride)));
       kk = make_key(a, static_cast<uint32_t>(shard_at(id, slot, b, kcand, shard_stride)));
+      adj[t] = a;
     }
-    // entry t is read and rewritten by the same thread only: no cross-thread hazard
-    key[t] = kk;
-    val[t] = slot;
-    if (slot >= 0) adj[slot] = a;
+    key[t] = kk;   // (the similarity keys are no longer needed: every rank has been taken)
   }
-  // 3. top-k by adjusted score, descending (backends.py:468-471)
-  bitonic_sort_desc(key, val, p);
-  for (int t = threadIdx.x; t < k; t += blockDim.x) {
-    const int slot = (t < p) ? val[t] : -1;
-    const size_t o = static_cast<size_t>(b) * k + t;
-    if (slot >= 0) {
-      out_id[o] = shard_at(id, slot, b, kcand, shard_stride);
-      out_score[o] = adj[slot];
-    } else {
-      out_id[o] = -1;
-      out_score[o] = -INFINITY;
+  for (int t = threadIdx.x; t < k; t += blockDim.x) {   // defaults: fewer than k candidates
+    out_id[static_cast<size_t>(b) * k + t] = -1;
+    out_score[static_cast<size_t>(b) * k + t] = -INFINITY;
+  }
+  __syncthreads();
+  // 3. top-k by adjusted score, descending, ties: lower id first (backends.py:468-471)
+  for (int e = threadIdx.x; e < ncand; e += blockDim.x) {
+    const unsigned long long x = key[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < ncand; ++f) rank += (key[f] > x) ? 1 : 0;
+    if (rank < k) {
+      out_id[static_cast<size_t>(b) * k + rank] = shard_at(id, val[e], b, kcand, shard_stride);
+      out_score[static_cast<size_t>(b) * k + rank] = adj[e];
     }
   }
 }
@@ -532,8 +537,9 @@ tail_kernel(const TailArgs a) {
     if (e < total) {
       const int chunk = e / kc, k = e - chunk * kc;
       const size_t off = ((static_cast<size_t>(chunk) * a.n_qb + qb) * kc + k) * kQueryBlock + ql;
-      const int idx = a.part_i[off];
-      if (idx >= 0) kk = make_key(a.part_s[off], static_cast<uint32_t>(idx));
+      const int idx = __ldg(a.part_i + off);
+      const float sc = __ldg(a.part_s + off);   // (issued with the index, not after it: the round is two L2 latencies otherwise)
+      if (idx >= 0) kk = make_key(sc, static_cast<uint32_t>(idx));
     }
     const bool pass = kk > floor_key;
     const unsigned int m = __ballot_sync(0xffffffffu, pass);
