@@ -28,6 +28,7 @@ FLAG_NO_SEED = 1 << 7
 FLAG_NO_M64 = 1 << 8
 FLAG_NO_CERT = 1 << 9
 FLAG_FORCE_CERT = 1 << 10
+FLAG_NO_ROWS_ON_M = 1 << 11
 JOIN_BF16 = 1 << 0
 JOIN_FORCE_SIMT = 1 << 1
 JOIN_FORCE_TC = 1 << 2

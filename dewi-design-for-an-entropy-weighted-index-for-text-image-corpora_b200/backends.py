@@ -587,10 +587,10 @@ class CudaIndex(BaseIndex):
 
     def sweep_ms(self, back: int = 0) -> Tuple[float, str]:
         """Device time of the sweep kernel of the `back`-th most recent profiled search (0 = last) and
-        which sweep ran ("tcgen05" / "simt")."""
+        which sweep ran ("tcgen05" / "tcgen05-rows" / "tcgen05-pair" / "simt")."""
         ms, kind = ctypes.c_float(0), ctypes.c_int(0)
         _native.check(self._lib.dewi_index_sweep_ms(self._h, int(back), ctypes.byref(ms), ctypes.byref(kind)))
-        return ms.value, {1: "tcgen05", 2: "simt", 3: "tcgen05-pair"}.get(kind.value, "?")
+        return ms.value, {1: "tcgen05", 2: "simt", 3: "tcgen05-pair", 4: "tcgen05-rows"}.get(kind.value, "?")
 
     # ---- stored rows / persistence ---------------------------------------------------------------
     @property

@@ -125,7 +125,7 @@ struct dewi_index {
   bool push_ticket_zeroed = false;
   // optional CUDA-event bracket around the sweep kernel (bench.py's roofline figure)
   int profile = 0;
-  int last_sweep_kind = 0;  // 1 = tcgen05 sweep, 2 = CUDA-core sweep
+  int last_sweep_kind = 0;  // 1 = tcgen05 sweep, 2 = CUDA-core sweep, 3 = CTA-pair sweep, 4 = rows-on-M sweep
   static constexpr int kEvRing = 64;
   cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
   long long searches = 0;  // sweeps bracketed since profiling was enabled
@@ -568,6 +568,9 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   Tc2Plan plan2;
   // at most 64 queries: M = 64 MMAs (half the tensor work / power and half the query re-stream)
   const int q_rows = (B <= 64 && !(flags & DEWI_FLAG_NO_M64)) ? 64 : kQueryBlock;
+  // ... and, where it applies, with the corpus rows on M and the queries on N = 16 / 32 / 64 (search_tcr.cu)
+  const int swap_b = (q_rows == 64 && !(flags & DEWI_FLAG_NO_ROWS_ON_M)) ? B : 0;
+  plan.rows_on_m = 0;
   const int n_qb_in = n_qb;
   // more than one query block: the CTA-pair sweep (two query blocks share every corpus tile)
   bool use_pair = false;
@@ -584,7 +587,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       }
       use_pair = false;
     }
-    return tc_make_plan(mode_, dim, h->n, n_qb, kc_, h->sm_count, &plan, 0, q_rows) == 0;
+    return tc_make_plan(mode_, dim, h->n, n_qb, kc_, h->sm_count, &plan, 0, q_rows, swap_b) == 0;
   };
   // CERTIFIED single-plane sweep (fp32 corpus).  The fp16 hi plane alone -- half the bytes of the hi/lo stream below
   // the ridge, a third of its MMAs above -- is swept with a longer candidate list; a certificate (select.cu) then
@@ -627,7 +630,8 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   const int qnorm = (h->space == DEWI_SPACE_COSINE && !(flags & DEWI_FLAG_QUERY_NORMALIZED)) ? 1 : 0;
   if (cert_planes) DEWI_TRY(h->qstats.ensure(static_cast<size_t>(b_pad) * 16));
   DEWI_TRY(launch_prep_queries(queries, B, b_pad, dim, qnorm, h->qn.as<float>(), h->q0.as<__nv_bfloat16>(),
-                               h->q1.as<__nv_bfloat16>(), stream, /*lane_order=*/(use_tc && !use_pair && q_rows == 64) ? 2 : 1,
+                               h->q1.as<__nv_bfloat16>(), stream,
+                               /*lane_order=*/(use_tc && !use_pair && plan.rows_on_m) ? 0 : ((use_tc && !use_pair && q_rows == 64) ? 2 : 1),
                                cert_planes ? h->qstats.as<float>() : nullptr, fp16_planes));
   h->last_launches++;
 
@@ -636,7 +640,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   Partials parts;
   const int ev_slot = static_cast<int>(h->searches % dewi_index::kEvRing);
   if (h->profile) DEWI_CUDA(cudaEventRecord(h->ev0[ev_slot], stream));
-  h->last_sweep_kind = use_tc ? (use_pair ? 3 : 1) : 2;
+  h->last_sweep_kind = use_tc ? (use_pair ? 3 : (plan.rows_on_m ? 4 : 1)) : 2;
   if (use_tc) {
     DEWI_TRY(ensure_corpus_maps(h, use_pair ? tc2_box_rows() : plan.n_tile));
     CUtensorMap mq0, mq1;
@@ -662,7 +666,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       }
       else
         DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                           h->part_i.as<int>(), sd, stream, fp16_planes));
+                           h->part_i.as<int>(), sd, stream, fp16_planes, B));
       h->last_launches++;
       return 0;
     };
@@ -690,7 +694,8 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
         const bool by_group = sample_tiles * groups <= 2048;
         const int want = by_group ? 0 : static_cast<int>(std::min<int64_t>(std::max<int64_t>(workers, 4 * kc), 2048));
         const int rc = use_pair ? tc2_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s2, want)
-                                : tc_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s1, want, q_rows);
+                                : tc_make_plan(mode, dim, sample_rows, n_qb, kc, h->sm_count, &s1, want, q_rows,
+                                               plan.rows_on_m ? B : 0);
         const int s_chunks = by_group ? static_cast<int>(sample_tiles * groups) : (use_pair ? s2.n_chunks : s1.n_chunks);
         if (rc == 0 && s_chunks >= kc && s_chunks <= 2048) {
           DEWI_TRY(h->seed_max.ensure(static_cast<size_t>(s_chunks) * n_qb * kQueryBlock * 4));

@@ -11,7 +11,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent
 PKG = CSRC.parent
-SOURCES = ["api.cu", "prep.cu", "search_tc.cu", "search_tc2.cu", "search_simt.cu", "select.cu", "scorer.cu", "join.cu", "extras.cu"]
+SOURCES = ["api.cu", "prep.cu", "search_tc.cu", "search_tcr.cu", "search_tc2.cu", "search_simt.cu", "select.cu", "scorer.cu", "join.cu", "extras.cu"]
 HEADERS = ["internal.h", "ptx.cuh", "sweep_epilogue.cuh", "join_epilogue.cuh", "../../include/dewi_b200.h"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -77,17 +77,24 @@ struct TcPlan {
   int n_stages;  // corpus ring depth
   int q_stages;  // query ring depth (or the number of resident query k-blocks)
   int q_resident;  // the single <= 64-query block stays in shared memory for the whole launch
+  int rows_on_m;   // search_tcr.cu: corpus rows on the MMA M dimension, q_rows = queries on N (16 / 32 / 64), natural plane order
   int n_chunks;  // corpus chunks (work items per query block)
   int grid;
   size_t smem_bytes;
 };
 int tc_supported(int dim, int64_t n_rows);
+// swap_queries > 0 (the batch size, at most 64): prefer the rows-on-M sweep (search_tcr.cu) when it applies
 int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks = 0,
-                 int q_rows = 128);
+                 int q_rows = 128, int swap_queries = 0);
 int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream, int fp16_planes = 0);
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes = 0, int n_queries = 0);
+
+// ---- tcgen05 sweep with the corpus rows on M, for at most 64 queries (search_tcr.cu) ------------
+int tcr_make_plan(int dim, int64_t n_rows, int B, int kc, int sm_count, TcPlan* plan, int force_chunks);
+int tcr_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& q0, int64_t n_rows, int dim, int B, int kc,
+               float* part_s, int* part_i, const SweepSeed& seed, cudaStream_t stream, int fp16_planes);
 
 // ---- tcgen05 sweep on CTA pairs, for more than one query block (search_tc2.cu) -----------------
 struct Tc2Plan {

@@ -337,8 +337,12 @@ int tc_supported(int dim, int64_t n_rows) {
 }
 
 int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, TcPlan* plan, int force_chunks,
-                 int q_rows) {
+                 int q_rows, int swap_queries) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
+  if (swap_queries > 0 && mode == 0 && n_qb == 1 &&
+      tcr_make_plan(dim, n_rows, swap_queries, kc, sm_count, plan, force_chunks) == 0)
+    return 0;
+  plan->rows_on_m = 0;
   const size_t smem_max = 227 * 1024;
   int n_tile = (mode == 2) ? 128 : 256;
   const size_t fixed = fixed_bytes(kc, q_rows);
@@ -364,7 +368,9 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
     n_tile = 128;
   }
   if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
-  stages = std::min(stages, kMaxStages);
+  // four 32 KB stages in flight per SM stream fastest (12.5M rows, B = 128: 3.37 / 3.04 / 3.21 ms with 3 / 4 / 5 stages):
+  // a deeper ring only adds concurrent DRAM streams
+  stages = std::min(stages, 4);
   if (env_set("DEWI_TC_STAGES")) stages = std::min(stages, std::max(2, env_int("DEWI_TC_STAGES", stages)));  // experiments
   const int64_t n_tiles = ceil_div(n_rows, n_tile);
   // Work items = chunks x query blocks, dealt round-robin to `grid` persistent CTAs.  Choose the
@@ -406,7 +412,8 @@ int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim
 
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream, int fp16_planes) {
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes, int n_queries) {
+  if (plan.rows_on_m) return tcr_launch(plan, e0, q0, n_rows, dim, n_queries, kc, part_s, part_i, seed, stream, fp16_planes);
   TcArgs a;
   a.fp16 = fp16_planes;
   a.n_rows = static_cast<int>(n_rows);

@@ -393,6 +393,10 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   const size_t smem_max = 227 * 1024;
   const size_t fixed = fixed_bytes(kc) + (a_resident ? a_resident_bytes(mode, dim) : 0);
   int stages = fixed < smem_max ? static_cast<int>((smem_max - fixed) / stage_bytes(mode, a_resident != 0)) : 0;
+  // The search streams the corpus from HBM: four 32 KB stages per CTA are the sweet spot (12.5M rows: B = 256 sweep 4.72 /
+  // 4.19 / 4.26 ms with 3 / 4 / 5 stages, B = 4096 60.6 / 59.5 / 59.6 ms) -- a deeper ring only adds concurrent DRAM
+  // streams.  The join's operands come from L2 and keep the deeper ring.
+  if (!a_resident && kc > 0) stages = std::min(stages, 4);
   if (env_set("DEWI_TC2_STAGES")) stages = std::min(stages, std::max(2, env_int("DEWI_TC2_STAGES", stages)));
   if (stages < 2) return fail("candidate list capacity too large for the CTA-pair sweep's shared memory");
   stages = std::min(stages, kMaxStages);

@@ -65,9 +65,8 @@ __device__ __forceinline__ void lane_prune(LaneList& l, int kc) {
 // score of query b over a sample of the corpus -- a lower bound of its kc-th best over the whole
 // corpus, so nothing at or above it may be dropped: start just below it (admission is strict `>`).
 // TMEM lane L of block qb holds query qb * 128 + (L % 32) * 4 + L / 32 (inverse of query_lane).
-__device__ __forceinline__ float seed_threshold(const float* seed, int stride, int off, int n_queries, int qb, int qlane) {
+__device__ __forceinline__ float seed_threshold_query(const float* seed, int stride, int off, int n_queries, int b) {
   if (!seed) return -INFINITY;
-  const int b = qb * kQueryBlock + (qlane & 31) * 4 + (qlane >> 5);
   if (b >= n_queries) return -INFINITY;
   const float t = seed[static_cast<size_t>(b) * stride + off];
   if (!(t > -INFINITY)) return -INFINITY;  // fewer than kc sample rows (or NaN): no seed
@@ -75,6 +74,9 @@ __device__ __forceinline__ float seed_threshold(const float* seed, int stride, i
   if (t > 0.f) return __uint_as_float(u - 1u);
   if (t < 0.f) return __uint_as_float(u + 1u);
   return __uint_as_float(0x80000001u);  // just below zero
+}
+__device__ __forceinline__ float seed_threshold(const float* seed, int stride, int off, int n_queries, int qb, int qlane) {
+  return seed_threshold_query(seed, stride, off, n_queries, qb * kQueryBlock + (qlane & 31) * 4 + (qlane >> 5));
 }
 
 // Warp-cooperative prune of ONE lane's list (the steady state, where lanes overflow one at a time):

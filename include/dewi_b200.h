@@ -57,8 +57,9 @@ enum {
   DEWI_FLAG_NO_M64 = 1 << 8,           /* B <= 64: keep M = 128 MMAs instead of M = 64                */
   DEWI_FLAG_NO_CERT = 1 << 9,          /* fp32 corpus: always sweep the full hi/lo product (3 MMAs, both planes) instead
                                           of the certified single-plane sweep (hi plane + proof + exact re-score)       */
-  DEWI_FLAG_FORCE_CERT = 1 << 10       /* fp32 corpus: use the certified sweep even on a corpus too small to repay its
+  DEWI_FLAG_FORCE_CERT = 1 << 10,      /* fp32 corpus: use the certified sweep even on a corpus too small to repay its
                                           host synchronisation (tests)                                                  */
+  DEWI_FLAG_NO_ROWS_ON_M = 1 << 11     /* B <= 64: keep the queries on the MMA M dimension instead of the corpus rows    */
 };
 
 /* ---- library ------------------------------------------------------------------------------ */

@@ -386,3 +386,87 @@ def test_certificate_failure_falls_back_to_the_full_product():
     rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), q, k, 0.0, 0.0, True)
     for i in range(2):
         check_topk(rid[i], rsc[i], ids[i], sc[i], what=f"fallback q{i}")
+
+
+def _sweep_kind(ix, queries, k, flags=0):
+    be = ix._backend
+    be.set_profiling(True)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=flags)
+    kind = be.sweep_ms(0)[1]
+    be.set_profiling(False)
+    return ids, sc, kind
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("b", [1, 7, 16, 17, 33, 64])
+def test_rows_on_m_sweep_matches_queries_on_m_and_oracle(dtype, b):
+    """B <= 64 puts the corpus rows on the MMA M dimension and the queries on N = 16 / 32 / 64 (search_tcr.cu);
+    DEWI_FLAG_NO_ROWS_ON_M keeps the queries on M.  Ragged corpus tail (n % 256 != 0), with and without the seeding
+    pre-pass: same results from both kernels, and both match the oracle."""
+    n, d, k = 300_077, 128, 10
+    emb, pay = make_corpus(n, d, seed=161 + b)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    queries = np.random.RandomState(162).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    force = _native.FLAG_FORCE_TC | (_native.FLAG_FORCE_CERT if dtype == "fp32" else 0)   # fp32: certified fp16-plane sweep
+    ids_r, sc_r, kind_r = _sweep_kind(ix, queries, k, force)
+    ids_q, sc_q, kind_q = _sweep_kind(ix, queries, k, force | _native.FLAG_NO_ROWS_ON_M)
+    ids_u, sc_u, kind_u = _sweep_kind(ix, queries, k, force | _native.FLAG_NO_SEED)
+    if dtype == "bf16":   # (an fp32 batch whose certificate fails is re-run with both planes, queries on M)
+        assert kind_r == "tcgen05-rows" and kind_u == "tcgen05-rows"
+    assert kind_q == "tcgen05"
+    np.testing.assert_array_equal(ids_r, ids_q)
+    np.testing.assert_array_equal(sc_r, sc_q)
+    np.testing.assert_array_equal(ids_r, ids_u)
+    np.testing.assert_array_equal(sc_r, sc_u)
+    nq = min(b, 16)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries[:nq], k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for q in range(nq):
+            check_topk(rid[q], rsc[q], ids_r[q], sc_r[q], what=f"rows-on-M B={b} q{q}")
+    else:
+        assert recall_at_k(rid, ids_r[:nq]) >= 0.999
+
+
+@pytest.mark.parametrize("b", [3, 40])
+def test_rows_on_m_certified_sweep_is_exact(b):
+    """fp32 corpus, certified single-plane sweep (48-slot lists) on the rows-on-M kernel."""
+    n, d, k = 150_000, 768, 10
+    emb, pay = make_corpus(n, d, seed=171)
+    ix = bulk_index(emb, pay)
+    queries = np.random.RandomState(172).standard_normal((b, d)).astype(np.float32)
+    flags = _native.FLAG_FORCE_TC | _native.FLAG_FORCE_CERT
+    used0, failed0 = ix._backend.cert_stats()
+    ids, sc, kind = _sweep_kind(ix, queries, k, flags)
+    used1, failed1 = ix._backend.cert_stats()
+    assert kind == "tcgen05-rows" and used1 == used0 + 1 and failed1 == failed0
+    ids_q, sc_q, kind_q = _sweep_kind(ix, queries, k, flags | _native.FLAG_NO_ROWS_ON_M)
+    assert kind_q == "tcgen05"
+    np.testing.assert_array_equal(ids, ids_q)
+    np.testing.assert_array_equal(sc, sc_q)
+    nq = min(b, 12)
+    rid, rsc = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), queries[:nq], k, 0.3, 0.5, True)
+    for q in range(nq):
+        check_topk(rid[q], rsc[q], ids[q], sc[q], what=f"certified rows-on-M B={b} q{q}")
+
+
+@pytest.mark.parametrize("b", [2, 64])
+def test_rows_on_m_sweep_with_lists_overflowing_all_the_time(b):
+    """Worst case for the shared candidate lists: the corpus is sorted by ASCENDING similarity to query 0, so every
+    row beats the running threshold, every list overflows in every half-tile and the prune / retry rounds of the four
+    epilogue warps run continuously (no seed: DEWI_FLAG_NO_SEED).  Results stay exact."""
+    n, d, k = 60_000, 64, 10
+    emb, pay = make_corpus(n, d, seed=181)
+    emb16 = bf16_round(emb)
+    queries = np.random.RandomState(182).standard_normal((b, d)).astype(np.float32)
+    qn = queries[0] / np.linalg.norm(queries[0])
+    order = np.argsort(emb16 @ qn, kind="stable")
+    emb, pay = np.ascontiguousarray(emb[order]), np.ascontiguousarray(pay[order])
+    ix = bulk_index(emb, pay, dtype="bf16")
+    ids, sc, kind = _sweep_kind(ix, queries, k, _native.FLAG_FORCE_TC | _native.FLAG_NO_SEED)
+    assert kind == "tcgen05-rows"
+    ids_q, sc_q, _ = _sweep_kind(ix, queries, k, _native.FLAG_FORCE_TC | _native.FLAG_NO_SEED | _native.FLAG_NO_ROWS_ON_M)
+    np.testing.assert_array_equal(ids, ids_q)
+    np.testing.assert_array_equal(sc, sc_q)
+    rid, rsc = osearch.exact_search_batch(bf16_round(emb), pay[:, 0], entropy_column(pay), queries[:8], k, 0.3, 0.5, True)
+    assert recall_at_k(rid, ids[:8]) >= 0.999
