@@ -205,8 +205,10 @@ class CudaIndex(BaseIndex):
     """
 
     def __init__(self, dim: int, space: str = "cosine", dtype: str = "fp32", device: Optional[int] = None,
-                 precise_query: bool = False, **kwargs: Any):
+                 precise_query: bool = False, rerank_scope: str = "candidates", **kwargs: Any):
         super().__init__(dim, space)
+        if rerank_scope not in ("candidates", "full"):
+            raise ValueError("rerank_scope must be 'candidates' (the reference's two-stage re-rank) or 'full'")
         if space not in _native.SPACE:
             raise ValueError(f"unknown space {space!r}; expected 'cosine' or 'l2'")
         if dtype not in _native.DTYPE:
@@ -227,6 +229,11 @@ class CudaIndex(BaseIndex):
         self._n_device = 0                     # rows resident on the GPU
         self._columns: Optional[ColumnStore] = None  # bulk payload columns (bulk ingest only)
         self._flags = _native.FLAG_PRECISE_QUERY if precise_query else 0
+        # "full": the blend is applied over the WHOLE corpus instead of the top-2k by similarity -- an opt-in that is
+        # NOT the reference's semantics (backends.py:439-481 re-ranks candidates only)
+        self.rerank_scope = rerank_scope
+        if rerank_scope == "full":
+            self._flags |= _native.FLAG_SCOPE_FULL
         self._host_rows: Optional[np.ndarray] = None
         # True once the device payload columns were written without a host mirror (set_payload_columns /
         # set_payload_from_signals(mirror=False)): build() / refresh_payloads() then leave them alone
@@ -568,6 +575,11 @@ class CudaIndex(BaseIndex):
                                                    ctypes.c_void_p(gid.data_ptr()), ctypes.c_void_p(dewi.data_ptr()),
                                                    ctypes.c_void_p(ent.data_ptr()), _native.stream_ptr())
         _native.check(rc)
+
+    def set_blend(self, eta: float, entropy_pref: float) -> None:
+        """Weights of the blended key a `rerank_scope="full"` shard-local search selects by (`search_batch` sets them
+        itself; the sharded index calls this before its local stage)."""
+        _native.check(self._lib.dewi_index_set_blend(self._h, float(eta), float(entropy_pref)))
 
     def cert_stats(self) -> Tuple[int, int]:
         """fp32 index: `(searches answered by the certified single-plane sweep, of which re-run with the full hi/lo

@@ -129,6 +129,9 @@ struct dewi_index {
   static constexpr int kEvRing = 64;
   cudaEvent_t ev0[kEvRing] = {}, ev1[kEvRing] = {};
   long long searches = 0;  // sweeps bracketed since profiling was enabled
+  // rerank_scope = "full" (DEWI_FLAG_SCOPE_FULL): blend weights of the key the sweep selects by (dewi_index_set_blend)
+  SweepBlend blend;
+  bool blend_set = false;
 };
 
 namespace {
@@ -534,11 +537,24 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   if (rerank_done) *rerank_done = false;
   if (B <= 0 || kcand <= 0) return fail("B and kcand must be positive");
   if (h->n <= 0) return fail("index is empty");
-  if (flags & DEWI_FLAG_SCOPE_FULL) return fail("full-corpus blend scope is not implemented (not the reference's semantics)");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DEWI_TRY(set_device(h));
   h->last_launches = 0;
   const int dim = h->dim;
+  // rerank_scope = "full" (opt-in, not the reference's semantics): the sweep selects by the blended key over the whole
+  // corpus -- rows-on-M tensor-core sweep (bf16 corpus; the key is evaluated per row in its epilogue) or the exact
+  // CUDA-core sweep (fp32 corpus, l2 space, odd dims) -- and the kcand best by the exactly re-evaluated blend come back.
+  const bool full = (flags & DEWI_FLAG_SCOPE_FULL) != 0;
+  SweepBlend blend;
+  if (full) {
+    if (!h->blend_set) return fail("full-corpus blend: call dewi_index_set_blend (or dewi_index_search) first");
+    if (push && push->world > 0) return fail("full-corpus blend: use the all-gather exchange, not the fused peer push");
+    if (!h->dewi_col || !h->ent_col) return fail("full-corpus blend: payload columns are not set");
+    blend = h->blend;
+    blend.enabled = 1;
+    blend.dewi = h->dewi_col;
+    blend.ent = h->ent_col;
+  }
   int b_pad = static_cast<int>(round_up(B, kQueryBlock));
   int n_qb = b_pad / kQueryBlock;
   const int kc_valid = static_cast<int>(std::min<int64_t>(kcand, h->n));
@@ -562,6 +578,23 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     }
   }
   int mode = (h->dtype == DEWI_DTYPE_FP32) ? 2 : ((flags & DEWI_FLAG_PRECISE_QUERY) ? 1 : 0);
+  if (full && use_tc) {
+    // only the rows-on-M sweep evaluates the key (one plane, at most 64 queries per launch).  An fp32 corpus goes to the
+    // exact CUDA-core sweep unless the tensor cores are forced (then: fp16 hi plane, over-fetch, exact re-score).
+    if (mode == 2 && (flags & DEWI_FLAG_FORCE_TC)) mode = 0;
+    if (mode != 0 || (flags & (DEWI_FLAG_NO_M64 | DEWI_FLAG_NO_ROWS_ON_M))) {
+      if (flags & DEWI_FLAG_FORCE_TC) return fail("full-corpus blend: the tensor-core path needs the rows-on-M sweep (one plane)");
+      use_tc = false;
+    } else if (B > 64) {
+      for (int b0 = 0; b0 < B; b0 += 64) {
+        const int nb = std::min(64, B - b0);
+        DEWI_TRY(search_local_impl(h, queries + static_cast<size_t>(b0) * dim, nb, kcand, flags, out_sim + static_cast<size_t>(b0) * kcand,
+                                   out_id + static_cast<size_t>(b0) * kcand, out_dewi + static_cast<size_t>(b0) * kcand,
+                                   out_ent + static_cast<size_t>(b0) * kcand, stream_, nullptr, nullptr, nullptr));
+      }
+      return 0;
+    }
+  }
   // list capacity: over-fetch so that rounding in the bf16-plane sweep cannot push a true top-2k row out
   int kc = (mode == 0) ? std::max(32, kc_valid + 16) : kc_valid + 8;
   TcPlan plan;
@@ -595,7 +628,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   // top-2k, and the exact fp32 re-score orders it.  When the certificate cannot be given for some query (scores packed
   // more densely than the bound resolves) the batch is re-run with the full hi/lo product: exact either way.
   int cert_planes = 0;
-  if (use_tc && mode == 2 && !(flags & DEWI_FLAG_NO_CERT) && env_int("DEWI_CERT", 1) != 0 &&
+  if (use_tc && !full && mode == 2 && !(flags & DEWI_FLAG_NO_CERT) && env_int("DEWI_CERT", 1) != 0 &&
       (static_cast<int64_t>(h->n) * dim >= kCertMinElems || (flags & DEWI_FLAG_FORCE_CERT))) {
     const int planes = 1;
     // List capacity.  With fp16 planes the bound is eps ~ 6e-4 at dim 768 (2.1e-4 per rounded operand, 1.8e-4 for the
@@ -621,6 +654,13 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     }
   } else if (!use_tc && (flags & DEWI_FLAG_FORCE_TC)) {
     return fail("tcgen05 sweep not applicable (needs cosine space and dim % 64 == 0)");
+  }
+  if (full && use_tc && !plan.rows_on_m) {   // (query block too large to stay resident, very long lists)
+    if (flags & DEWI_FLAG_FORCE_TC) return fail("full-corpus blend: no rows-on-M plan for this shape");
+    use_tc = false;
+    use_pair = false;
+    n_qb = n_qb_in;
+    b_pad = n_qb * kQueryBlock;
   }
 
   // queries -> normalised fp32 + bf16 planes
@@ -666,7 +706,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       }
       else
         DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                           h->part_i.as<int>(), sd, stream, fp16_planes, B));
+                           h->part_i.as<int>(), sd, stream, fp16_planes, B, full ? &blend : nullptr));
       h->last_launches++;
       return 0;
     };
@@ -719,14 +759,16 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     h->last_launches++;
     parts.n_chunks = n_chunks;
   } else {
-    kc = kc_valid;
+    // (full scope: the sweep's fused-multiply-add key and the re-rank's separately rounded blend can order near-ties
+    // differently; a few extra slots make the kcand best by the exact blend certain to be among the candidates)
+    kc = full ? static_cast<int>(std::min<int64_t>(static_cast<int64_t>(kc_valid) + 8, h->n)) : kc_valid;
     int n_chunks = 1;
     DEWI_TRY(simt_plan(h->n, B, h->sm_count, &n_chunks));
     const size_t items = static_cast<size_t>(n_chunks) * n_qb;
     DEWI_TRY(h->part_s.ensure(items * kc * kQueryBlock * 4));
     DEWI_TRY(h->part_i.ensure(items * kc * kQueryBlock * 4));
     DEWI_TRY(simt_launch(exact_rows, exact_is_bf16, h->n, dim, h->space, h->qn.as<float>(), B, kc, n_chunks,
-                         h->part_s.as<float>(), h->part_i.as<int>(), stream));
+                         h->part_s.as<float>(), h->part_i.as<int>(), stream, full ? &blend : nullptr));
     h->last_launches++;
     parts.n_chunks = n_chunks;
   }
@@ -740,7 +782,7 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   parts.kc = kc;
 
   int* fails_dev = reinterpret_cast<int*>(h->plane_max + 2);
-  if (tail_supported(kc, kcand, rerank ? rerank->k : 1) && env_int("DEWI_FUSED_TAIL", 1) != 0) {
+  if (!full && tail_supported(kc, kcand, rerank ? rerank->k : 1) && env_int("DEWI_FUSED_TAIL", 1) != 0) {
     // ONE launch for everything after the sweep (select.cu: tail_kernel)
     TailCert cert{h->qstats.as<float>(), cert_planes, h->plane_max, kc_valid, fails_dev};
     if (cert_planes) DEWI_CUDA(cudaMemsetAsync(fails_dev, 0, sizeof(int), stream));
@@ -787,9 +829,13 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
     DEWI_TRY(launch_rescore(exact_rows, exact_is_bf16, dim, h->qn.as<float>(), h->cand_idx.as<int>(), B, kc,
                             h->cand_sim.as<float>(), stream, cert_planes ? h->qbar.as<float>() : nullptr));
     h->last_launches++;
+  } else if (full) {   // the CUDA-core sweep's lists hold blended keys: back to the exact scores
+    DEWI_TRY(launch_rescore_any(exact_rows, exact_is_bf16, dim, h->space == DEWI_SPACE_L2 ? 1 : 0, h->qn.as<float>(),
+                                h->cand_idx.as<int>(), B, kc, h->cand_sim.as<float>(), stream));
+    h->last_launches++;
   }
   DEWI_TRY(launch_finalize_local(h->cand_idx.as<int>(), h->cand_sim.as<float>(), B, kc, kcand, h->id_base, h->dewi_col,
-                                 h->ent_col, out_sim, out_id, out_dewi, out_ent, stream, push));
+                                 h->ent_col, out_sim, out_id, out_dewi, out_ent, stream, push, full ? &blend : nullptr));
   h->last_launches++;
   return 0;
 }
@@ -826,6 +872,17 @@ int dewi_rerank(const float* sim, const int64_t* id, const float* dewi_v, const 
   return launch_rerank(sim, id, dewi_v, ent_v, B, n_shards, kcand, shard_stride_bytes, cand_count, k,
                        static_cast<float>(1.0 - eta), static_cast<float>(eta), static_cast<float>(entropy_pref),
                        entropy_pref != 0.0 ? 1 : 0, out_id, out_score, static_cast<cudaStream_t>(stream_));
+}
+
+int dewi_index_set_blend(dewi_index_t* h, double eta, double entropy_pref) {
+  if (!h) return fail("null handle");
+  // the same weak-scalar float32 weights as the re-rank (backends.py:461-465)
+  h->blend.w_sim = static_cast<float>(1.0 - eta);
+  h->blend.w_dewi = static_cast<float>(eta);
+  h->blend.pref = static_cast<float>(entropy_pref);
+  h->blend.use_pref = entropy_pref != 0.0 ? 1 : 0;
+  h->blend_set = true;
+  return 0;
 }
 
 int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref, int flags,
@@ -889,6 +946,7 @@ int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, doubl
   const float w_dewi = static_cast<float>(eta);
   const float pref = static_cast<float>(entropy_pref);
   const TailRerank rr{k, w_sim, w_dewi, pref, entropy_pref != 0.0 ? 1 : 0, d_id, d_sc};
+  if (flags & DEWI_FLAG_SCOPE_FULL) DEWI_TRY(dewi_index_set_blend(h, eta, entropy_pref));
   bool reranked = false;
   DEWI_TRY(search_local_impl(h, q_dev, B, kcand, flags, h->loc_sim.as<float>(), h->loc_id.as<int64_t>(), h->loc_dewi.as<float>(),
                              h->loc_ent.as<float>(), stream_, nullptr, &rr, &reranked));

@@ -68,6 +68,17 @@ struct SweepSeed {
   int max_groups = 0;
 };
 
+// rerank_scope = "full" (opt-in, NOT the reference's semantics -- SURVEY.md section 0.2): the sweep selects by the
+// BLENDED key  w_sim * sim + w_dewi * dewi[row] (+ pref * ent[row])  over the whole corpus instead of by similarity.
+// The key is evaluated in the sweep's epilogue from the two payload columns (8 more bytes per row streamed).
+struct SweepBlend {
+  int enabled = 0;
+  float w_sim = 1.f, w_dewi = 0.f, pref = 0.f;
+  int use_pref = 0;
+  const float* dewi = nullptr;
+  const float* ent = nullptr;
+};
+
 // ---- tcgen05 sweep (search_tc.cu) ------------------------------------------------------------
 // mode 0: S = Q0.E0 ; mode 1: S = (Q0+Q1).E0 ; mode 2: S = Q0.E0 + Q1.E0 + Q0.E1
 struct TcPlan {
@@ -89,12 +100,14 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
 int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim, int box_rows);
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream, int fp16_planes = 0, int n_queries = 0);
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes = 0, int n_queries = 0,
+              const SweepBlend* blend = nullptr);
 
 // ---- tcgen05 sweep with the corpus rows on M, for at most 64 queries (search_tcr.cu) ------------
 int tcr_make_plan(int dim, int64_t n_rows, int B, int kc, int sm_count, TcPlan* plan, int force_chunks);
 int tcr_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& q0, int64_t n_rows, int dim, int B, int kc,
-               float* part_s, int* part_i, const SweepSeed& seed, cudaStream_t stream, int fp16_planes);
+               float* part_s, int* part_i, const SweepSeed& seed, cudaStream_t stream, int fp16_planes,
+               const SweepBlend* blend = nullptr);
 
 // ---- tcgen05 sweep on CTA pairs, for more than one query block (search_tc2.cu) -----------------
 struct Tc2Plan {
@@ -121,7 +134,7 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
 // ---- CUDA-core exact sweep (search_simt.cu) --------------------------------------------------
 int simt_plan(int64_t n_rows, int B, int sm_count, int* n_chunks);
 int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, int space, const float* qn, int B, int kc,
-                int n_chunks, float* part_s, int* part_i, cudaStream_t stream);
+                int n_chunks, float* part_s, int* part_i, cudaStream_t stream, const SweepBlend* blend = nullptr);
 
 // ---- selection / re-rank (select.cu) ---------------------------------------------------------
 // seed[b] = the kc-th largest of query b's per-item maxima [n_chunks][n_qb][128] (-inf when n_chunks < kc)
@@ -129,6 +142,9 @@ int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, 
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
 int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, int* cand_idx, int B, int kc,
                    float* cand_sim, cudaStream_t stream, const float* bar = nullptr);
+// any dim / cosine or l2: exact scores of the candidates a blended-key sweep selected (rerank_scope = "full")
+int launch_rescore_any(const void* rows, int rows_are_bf16, int dim, int is_l2, const float* qn, const int* cand_idx, int B, int kc,
+                       float* cand_sim, cudaStream_t stream);
 // Certified single-plane sweep (fp32 corpus swept through its bf16 hi plane): counts in *fails the queries whose list
 // of the kc best swept scores cannot be PROVEN to contain the exact top-`need` (see select.cu).
 int launch_certificate(const float* cand_sim, const int* cand_idx, int B, int kc, int need, const float* q_stats, int q_planes,
@@ -149,7 +165,7 @@ struct PeerPush {
 };
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
-                          float* out_ent, cudaStream_t stream, const PeerPush* push = nullptr);
+                          float* out_ent, cudaStream_t stream, const PeerPush* push = nullptr, const SweepBlend* blend = nullptr);
 // Fused tail (select.cu: tail_kernel): merge -> [certificate] -> exact re-score -> order + payload (+ peer push) -> [blend +
 // top-k on a single shard] in ONE launch, one block per query.
 struct TailCert {          // certificate of the single-plane sweep

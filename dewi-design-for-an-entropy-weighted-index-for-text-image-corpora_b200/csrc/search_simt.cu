@@ -93,7 +93,7 @@ __device__ __forceinline__ void list_insert(float* ls, int* li, int kc, int lane
 template <typename RowT, int VEC, bool IS_L2, int QB>
 __global__ void __launch_bounds__(kSimtThreads)
 search_simt_kernel(const RowT* __restrict__ rows, long long n_rows, int dim, const float* __restrict__ qn, int B,
-                   int kc, int n_qb, float* __restrict__ part_s, int* __restrict__ part_i) {
+                   int kc, int n_qb, float* __restrict__ part_s, int* __restrict__ part_i, const SweepBlend blend) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* ls_all = sm;                                                   // [warps][QB][kc]
@@ -121,6 +121,16 @@ search_simt_kernel(const RowT* __restrict__ rows, long long n_rows, int dim, con
       float acc_a[QB], acc_b[QB];
 #pragma unroll
       for (int q = 0; q < QB; ++q) { acc_a[q] = 0.f; acc_b[q] = 0.f; }
+      // rerank_scope = "full": the lists are kept by the blended key w_sim * sim + w_dewi * dewi (+ pref * ent)
+      float bias_a = 0.f, bias_b = 0.f;
+      if (blend.enabled) {
+        bias_a = blend.w_dewi * __ldg(blend.dewi + r);
+        bias_b = blend.w_dewi * __ldg(blend.dewi + (two ? r + 1 : r));
+        if (blend.use_pref) {
+          bias_a = fmaf(blend.pref, __ldg(blend.ent + r), bias_a);
+          bias_b = fmaf(blend.pref, __ldg(blend.ent + (two ? r + 1 : r)), bias_b);
+        }
+      }
       for (int d = lane * VEC; d < dim; d += 32 * VEC) {
         float xa[VEC], xb[VEC];
         RowLoad<RowT, VEC>::ld(pa + d, xa);
@@ -149,6 +159,7 @@ search_simt_kernel(const RowT* __restrict__ rows, long long n_rows, int dim, con
         if (q < nq) {
           float va = warp_sum(acc_a[q]), vb = warp_sum(acc_b[q]);
           if (IS_L2) { va = -va; vb = -vb; }
+          if (blend.enabled) { va = fmaf(blend.w_sim, va, bias_a); vb = fmaf(blend.w_sim, vb, bias_b); }
           if (va > thr[q]) list_insert(ls + q * kc, li + q * kc, kc, lane, va, static_cast<int>(r), thr[q]);
           if (two && vb > thr[q]) list_insert(ls + q * kc, li + q * kc, kc, lane, vb, static_cast<int>(r + 1), thr[q]);
         }
@@ -197,19 +208,19 @@ search_simt_kernel(const RowT* __restrict__ rows, long long n_rows, int dim, con
 
 template <typename RowT, int VEC, bool IS_L2>
 int launch_t(const RowT* rows, int64_t n_rows, int dim, const float* qn, int B, int kc, int n_chunks, int n_qb,
-             float* part_s, int* part_i, cudaStream_t stream) {
+             float* part_s, int* part_i, cudaStream_t stream, const SweepBlend& blend) {
   if (B >= 4) {
     constexpr int QB = 4;
     const size_t smem = static_cast<size_t>(kSimtWarps) * QB * kc * 8;
     auto kern = search_simt_kernel<RowT, VEC, IS_L2, QB>;
     DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<n_chunks, kSimtThreads, smem, stream>>>(rows, n_rows, dim, qn, B, kc, n_qb, part_s, part_i);
+    kern<<<n_chunks, kSimtThreads, smem, stream>>>(rows, n_rows, dim, qn, B, kc, n_qb, part_s, part_i, blend);
   } else {
     constexpr int QB = 1;
     const size_t smem = static_cast<size_t>(kSimtWarps) * QB * kc * 8;
     auto kern = search_simt_kernel<RowT, VEC, IS_L2, QB>;
     DEWI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<n_chunks, kSimtThreads, smem, stream>>>(rows, n_rows, dim, qn, B, kc, n_qb, part_s, part_i);
+    kern<<<n_chunks, kSimtThreads, smem, stream>>>(rows, n_rows, dim, qn, B, kc, n_qb, part_s, part_i, blend);
   }
   DEWI_CUDA(cudaGetLastError());
   return 0;
@@ -226,24 +237,25 @@ int simt_plan(int64_t n_rows, int B, int sm_count, int* n_chunks) {
 }
 
 int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, int space, const float* qn, int B, int kc,
-                int n_chunks, float* part_s, int* part_i, cudaStream_t stream) {
+                int n_chunks, float* part_s, int* part_i, cudaStream_t stream, const SweepBlend* blend_) {
   if (static_cast<size_t>(kSimtWarps) * 4 * kc * 8 > 200 * 1024) return fail("k too large for the exact sweep");
+  const SweepBlend blend = blend_ ? *blend_ : SweepBlend();
   const int n_qb = static_cast<int>(ceil_div(B, kQueryBlock));
   const bool l2 = (space == DEWI_SPACE_L2);
   if (rows_are_bf16) {
     const auto* r = static_cast<const __nv_bfloat16*>(rows);
     if (dim % 8 == 0)
-      return l2 ? launch_t<__nv_bfloat16, 8, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream)
-                : launch_t<__nv_bfloat16, 8, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream);
-    return l2 ? launch_t<__nv_bfloat16, 1, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream)
-              : launch_t<__nv_bfloat16, 1, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream);
+      return l2 ? launch_t<__nv_bfloat16, 8, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend)
+                : launch_t<__nv_bfloat16, 8, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend);
+    return l2 ? launch_t<__nv_bfloat16, 1, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend)
+              : launch_t<__nv_bfloat16, 1, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend);
   }
   const auto* r = static_cast<const float*>(rows);
   if (dim % 4 == 0)
-    return l2 ? launch_t<float, 4, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream)
-              : launch_t<float, 4, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream);
-  return l2 ? launch_t<float, 1, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream)
-            : launch_t<float, 1, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream);
+    return l2 ? launch_t<float, 4, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend)
+              : launch_t<float, 4, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend);
+  return l2 ? launch_t<float, 1, true>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend)
+            : launch_t<float, 1, false>(r, n_rows, dim, qn, B, kc, n_chunks, n_qb, part_s, part_i, stream, blend);
 }
 
 }  // namespace dewi

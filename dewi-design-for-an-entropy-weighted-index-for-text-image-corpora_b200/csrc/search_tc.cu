@@ -412,8 +412,9 @@ int tc_encode_rows_map(CUtensorMap* map, const void* base, int64_t rows, int dim
 
 int tc_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
               const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-              const SweepSeed& seed, cudaStream_t stream, int fp16_planes, int n_queries) {
-  if (plan.rows_on_m) return tcr_launch(plan, e0, q0, n_rows, dim, n_queries, kc, part_s, part_i, seed, stream, fp16_planes);
+              const SweepSeed& seed, cudaStream_t stream, int fp16_planes, int n_queries, const SweepBlend* blend) {
+  if (plan.rows_on_m) return tcr_launch(plan, e0, q0, n_rows, dim, n_queries, kc, part_s, part_i, seed, stream, fp16_planes, blend);
+  if (blend && blend->enabled) return fail("the full-corpus blend needs the rows-on-M or the CUDA-core sweep");
   TcArgs a;
   a.fp16 = fp16_planes;
   a.n_rows = static_cast<int>(n_rows);

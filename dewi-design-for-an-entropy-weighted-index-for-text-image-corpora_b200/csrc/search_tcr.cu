@@ -53,6 +53,7 @@ struct TcrArgs {
   float* max_out;     // pre-pass mode: maxima instead of candidate lists (internal.h: SweepSeed)
   int max_groups;
   int fp16;
+  SweepBlend blend;   // rerank_scope = "full": select by the blended key instead of by similarity
 };
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -122,14 +123,38 @@ __device__ __forceinline__ void load_thr(const float* thr, float (&t)[CH]) {
 // Thresholds only rise and admission is strict, so a stale threshold merely admits a row that the next prune drops.
 // The flag of half-tile p is zero again when its loop ends, and is next written after the first barrier of half-tile
 // p + 1 -- which every warp reaches only after its last read of it: two flags used alternately suffice.
+// Scores of one chunk of queries for this thread's row; with `key.on` they become the blended keys
+// key.w * sim + key.bias (rerank_scope = "full": key.bias = w_dewi * dewi[row] + pref * ent[row]).
+struct RowKey {
+  bool on;
+  float w, bias;
+};
+__device__ __forceinline__ RowKey row_key(const SweepBlend& b, int row, bool valid) {
+  RowKey k{b.enabled != 0, b.w_sim, 0.f};
+  if (k.on && valid) {
+    k.bias = b.w_dewi * __ldg(b.dewi + row);
+    if (b.use_pref) k.bias = fmaf(b.pref, __ldg(b.ent + row), k.bias);
+  }
+  return k;
+}
+template <int CH>
+__device__ __forceinline__ void load_scores(uint32_t taddr, const RowKey& key, float (&v)[CH]) {
+  load_cols<CH>(taddr, v);
+  if (key.on) {
+#pragma unroll
+    for (int j = 0; j < CH; ++j) v[j] = fmaf(key.w, v[j], key.bias);
+  }
+}
+
 template <int QN, int CH>
-__device__ __forceinline__ void scan_half(const RowLists<QN>& L, uint32_t tc, int row, bool valid, int e, int lane, uint32_t& par) {
+__device__ __forceinline__ void scan_half(const RowLists<QN>& L, uint32_t tc, int row, bool valid, int e, int lane, uint32_t& par,
+                                          const RowKey& key) {
   constexpr int NCH = QN / CH;
   uint32_t pend[NCH];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     float v[CH], t[CH];
-    load_cols<CH>(tc + c * CH, v);
+    load_scores<CH>(tc + c * CH, key, v);
     load_thr<CH>(L.thr + c * CH, t);
     bool hit = false;
 #pragma unroll
@@ -160,7 +185,7 @@ __device__ __forceinline__ void scan_half(const RowLists<QN>& L, uint32_t tc, in
     for (int c = 0; c < NCH; ++c) {
       if (__any_sync(0xffffffffu, pend[c] != 0)) {
         float v[CH], t[CH];
-        load_cols<CH>(tc + c * CH, v);
+        load_scores<CH>(tc + c * CH, key, v);
         load_thr<CH>(L.thr + c * CH, t);
         pend[c] = pend[c] ? append_chunk<QN, CH>(L, v, t, pend[c], c * CH, row) : 0u;
         any_pend |= pend[c] != 0;
@@ -173,11 +198,11 @@ __device__ __forceinline__ void scan_half(const RowLists<QN>& L, uint32_t tc, in
 
 // Pre-pass half-tile: this warp's 32 rows are one 32-row group; lane j ends up with query (q0 + j)'s maximum over them.
 template <int QN, int CH>
-__device__ __forceinline__ void max_half(const TcrArgs& a, int* imax, uint32_t tc, bool valid, int group, int lane) {
+__device__ __forceinline__ void max_half(const TcrArgs& a, int* imax, uint32_t tc, bool valid, int group, int lane, const RowKey& key) {
 #pragma unroll
   for (int c = 0; c < QN / CH; ++c) {
     float v[CH];
-    load_cols<CH>(tc + c * CH, v);
+    load_scores<CH>(tc + c * CH, key, v);
     int mine = f2key(-INFINITY);
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -338,8 +363,9 @@ search_tcr_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
           const uint32_t tc = tmem_lane + static_cast<uint32_t>(acc * 2 * QN + h * QN);
           const int row = t * kRowTile + h * 128 + quarter * 32 + lane;
           const bool valid = row < a.n_rows;
-          if (a.max_out) max_half<QN, CH>(a, imax, tc, valid, t * (kRowTile / 32) + h * 4 + quarter, lane);
-          else scan_half<QN, CH>(L, tc, row, valid, e, lane, par);
+          const RowKey key = row_key(a.blend, row, valid);
+          if (a.max_out) max_half<QN, CH>(a, imax, tc, valid, t * (kRowTile / 32) + h * 4 + quarter, lane, key);
+          else scan_half<QN, CH>(L, tc, row, valid, e, lane, par, key);
         }
         ptx::tc_fence_before();
         __syncwarp();
@@ -430,8 +456,9 @@ int tcr_make_plan(int dim, int64_t n_rows, int B, int kc, int sm_count, TcPlan* 
 }
 
 int tcr_launch(const TcPlan& plan, const CUtensorMap& e0, const CUtensorMap& q0, int64_t n_rows, int dim, int B, int kc,
-               float* part_s, int* part_i, const SweepSeed& seed, cudaStream_t stream, int fp16_planes) {
+               float* part_s, int* part_i, const SweepSeed& seed, cudaStream_t stream, int fp16_planes, const SweepBlend* blend) {
   TcrArgs a;
+  if (blend) a.blend = *blend;
   a.n_rows = static_cast<int>(n_rows);
   a.n_tiles = static_cast<int>(ceil_div(n_rows, kRowTile));
   a.n_kb = dim / kKBlock;

@@ -232,6 +232,37 @@ __global__ void rescore_kernel(const RowT* __restrict__ rows, int dim, const flo
   if (lane == 0) cand_sim[w] = acc;
 }
 
+// General form (any dim, cosine or l2 space; scalar loads): re-derives the exact scores of candidates that the
+// CUDA-core sweep selected by a blended key (rerank_scope = "full"), in the sweep's own arithmetic (fmaf chains over
+// d = lane, lane + 32, ... are NOT reproduced -- the re-rank only needs the exact similarity to within rounding).
+template <typename RowT>
+__global__ void rescore_any_kernel(const RowT* __restrict__ rows, int dim, const float* __restrict__ qn, const int* __restrict__ cand_idx,
+                                   int total, int kc, float* __restrict__ cand_sim, int is_l2) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= total) return;
+  const int idx = cand_idx[w];
+  if (idx < 0) {
+    if (lane == 0) cand_sim[w] = -INFINITY;
+    return;
+  }
+  const RowT* r = rows + static_cast<size_t>(idx) * dim;
+  const float* q = qn + static_cast<size_t>(w / kc) * dim;
+  float acc = 0.f;
+  for (int d = lane; d < dim; d += 32) {
+    const float x = sizeof(RowT) == 2 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(r)[d]) : static_cast<float>(r[d]);
+    if (is_l2) {
+      const float t = x - q[d];
+      acc = fmaf(t, t, acc);
+    } else {
+      acc = fmaf(x, q[d], acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) cand_sim[w] = is_l2 ? -acc : acc;
+}
+
 // ---- finalize_local -----------------------------------------------------------------------------
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -249,7 +280,7 @@ __global__ void __launch_bounds__(kSelThreads)
 finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict__ cand_sim, int kc_in, int kcand,
                       long long id_base, const float* __restrict__ dewi, const float* __restrict__ ent,
                       float* __restrict__ out_sim, long long* __restrict__ out_id, float* __restrict__ out_dewi,
-                      float* __restrict__ out_ent, const PeerPush push) {
+                      float* __restrict__ out_ent, const PeerPush push, const SweepBlend blend) {
   extern __shared__ unsigned long long sh[];
   __shared__ unsigned int ticket;
   const int p = next_pow2(kc_in);
@@ -261,7 +292,15 @@ finalize_local_kernel(const int* __restrict__ cand_idx, const float* __restrict_
     int vv = -1;
     if (t < kc_in) {
       const int idx = cand_idx[static_cast<size_t>(b) * kc_in + t];
-      if (idx >= 0) { kk = make_key(cand_sim[static_cast<size_t>(b) * kc_in + t], static_cast<uint32_t>(idx)); vv = t; }
+      if (idx >= 0) {
+        float score = cand_sim[static_cast<size_t>(b) * kc_in + t];
+        if (blend.enabled) {   // rerank_scope = "full": keep the kcand best by the blended score, evaluated as the re-rank does
+          score = __fadd_rn(__fmul_rn(blend.w_sim, score), __fmul_rn(blend.w_dewi, dewi[idx]));
+          if (blend.use_pref) score = __fadd_rn(score, __fmul_rn(blend.pref, ent[idx]));
+        }
+        kk = make_key(score, static_cast<uint32_t>(idx));
+        vv = t;
+      }
     }
     key[t] = kk;
     val[t] = vv;
@@ -739,19 +778,35 @@ int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn
   return 0;
 }
 
+int launch_rescore_any(const void* rows, int rows_are_bf16, int dim, int is_l2, const float* qn, const int* cand_idx, int B, int kc,
+                       float* cand_sim, cudaStream_t stream) {
+  const int total = B * kc;
+  const int threads = 256;
+  const int blocks = static_cast<int>(ceil_div(static_cast<int64_t>(total) * 32, threads));
+  if (rows_are_bf16)
+    rescore_any_kernel<__nv_bfloat16><<<blocks, threads, 0, stream>>>(static_cast<const __nv_bfloat16*>(rows), dim, qn, cand_idx, total,
+                                                                       kc, cand_sim, is_l2);
+  else
+    rescore_any_kernel<float><<<blocks, threads, 0, stream>>>(static_cast<const float*>(rows), dim, qn, cand_idx, total, kc, cand_sim,
+                                                               is_l2);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_finalize_local(const int* cand_idx, const float* cand_sim, int B, int kc_in, int kcand, int64_t id_base,
                           const float* dewi, const float* ent, float* out_sim, int64_t* out_id, float* out_dewi,
-                          float* out_ent, cudaStream_t stream, const PeerPush* push) {
+                          float* out_ent, cudaStream_t stream, const PeerPush* push, const SweepBlend* blend_) {
+  const SweepBlend blend = blend_ ? *blend_ : SweepBlend();
   const int p = next_pow2(kc_in);
   if (p > 4096) return fail("too many candidates per query");
   const size_t smem = static_cast<size_t>(p) * 12;
   if (push && push->world > 0) {
     if (push->world > kMaxPeers || !push->ticket) return fail("invalid peer-push descriptor");
     finalize_local_kernel<1><<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, nullptr,
-                                                               nullptr, nullptr, nullptr, *push);
+                                                               nullptr, nullptr, nullptr, *push, blend);
   } else {
     finalize_local_kernel<0><<<B, kSelThreads, smem, stream>>>(cand_idx, cand_sim, kc_in, kcand, id_base, dewi, ent, out_sim,
-                                                               reinterpret_cast<long long*>(out_id), out_dewi, out_ent, PeerPush());
+                                                               reinterpret_cast<long long*>(out_id), out_dewi, out_ent, PeerPush(), blend);
   }
   DEWI_CUDA(cudaGetLastError());
   return 0;

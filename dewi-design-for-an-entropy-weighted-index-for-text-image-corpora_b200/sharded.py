@@ -247,7 +247,14 @@ class ShardedDewiIndex:
         b = queries.shape[0]
         kcand = min(2 * k, self.n_total)  # backends.py:440
         self._check_status()
-        if self._push_ready(b, kcand, queries, exchange or self._exchange_want):
+        full = getattr(self.local, "rerank_scope", "candidates") == "full"
+        if full:
+            # opt-in full-corpus blend: every shard selects by the blended key (its global top-k lies in the union of the
+            # shards' local ones), exchanged with the all-gather -- the fused push lives in the candidate-scope tail kernel
+            if exchange == "push":
+                raise ValueError("rerank_scope='full' uses the all-gather exchange")
+            self.local.set_blend(eta, entropy_pref)
+        if not full and self._push_ready(b, kcand, queries, exchange or self._exchange_want):
             return self._search_batch_push(queries, b, kcand, k, eta, entropy_pref)
         self.exchange = "nccl"
         pk = self._packed

@@ -51,7 +51,7 @@ enum {
   DEWI_FLAG_FORCE_TC = 1 << 2,         /* fail instead of falling back to the CUDA-core sweep      */
   DEWI_FLAG_HOST_IO = 1 << 3,          /* queries / outputs are HOST pointers (copies inside call) */
   DEWI_FLAG_PRECISE_QUERY = 1 << 4,    /* bf16 corpus: hi+lo query planes (2 MMAs) not 1 + rescore */
-  DEWI_FLAG_SCOPE_FULL = 1 << 5,       /* (non-reference) blend over the whole corpus; unsupported */
+  DEWI_FLAG_SCOPE_FULL = 1 << 5,       /* (non-reference, opt-in) blend over the WHOLE corpus       */
   DEWI_FLAG_NO_PAIR = 1 << 6,          /* B > 128: keep the 1-CTA sweep instead of the CTA-pair one  */
   DEWI_FLAG_NO_SEED = 1 << 7,          /* skip the sample pre-pass that seeds admission thresholds    */
   DEWI_FLAG_NO_M64 = 1 << 8,           /* B <= 64: keep M = 128 MMAs instead of M = 64                */
@@ -139,6 +139,12 @@ DEWI_API int dewi_rerank_gathered(const float* sim, const int64_t* id, const flo
                 int n_shards, int kcand, int64_t shard_stride_bytes, int cand_count, int k, double eta, double entropy_pref,
                 int64_t* out_id, float* out_score, const uint32_t* ready_flags, uint32_t seq, uint32_t* status_word,
                 double timeout_s, int device, void* stream);
+/* rerank_scope = "full" (DEWI_FLAG_SCOPE_FULL; opt-in, NOT the reference's two-stage semantics of backends.py:439-481,
+ * see SURVEY.md section 0.2): the sweep selects by the blended score  (1 - eta) * sim + eta * dewi (+ entropy_pref * ent)
+ * over the WHOLE corpus, search_local returns the kcand best rows by that score (still as sim / id / dewi / ent, so the
+ * same dewi_rerank finishes the job -- also across shards: the global top-k by the blend is in the union of the local
+ * ones).  The weights are per handle: set them before dewi_index_search_local; dewi_index_search sets them itself. */
+DEWI_API int dewi_index_set_blend(dewi_index_t* h, double eta, double entropy_pref);
 /* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,

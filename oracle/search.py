@@ -90,6 +90,30 @@ def exact_search_batch(embeddings, dewi, entropy, queries, k=10, eta=0.5, entrop
     return np.stack(ids), np.stack(scs)
 
 
+def full_scope_search(embeddings, dewi, entropy, query, k=10, eta=0.5, entropy_pref=0.0, normalize=True):
+    """`rerank_scope="full"` -- NOT a reference code path (parity unpinned by definition): the
+    reference's own blend statements (backends.py:461-465, float32 arrays, weak Python-float scalars) applied to EVERY
+    row instead of to the top-2k by similarity, then its final select / sort (backends.py:468-471)."""
+    query = np.asarray(query, dtype=np.float32)
+    if normalize:
+        query_norm = np.linalg.norm(query)
+        if query_norm > 0:
+            query = query / query_norm
+    query = query.reshape(1, -1)
+    if normalize:
+        scores = np.dot(embeddings, query.T).flatten()
+    else:
+        scores = -np.sum((embeddings - query) ** 2, axis=1)
+    dewi_scores = np.asarray(dewi).astype(np.float32)
+    entropies = np.asarray(entropy).astype(np.float32)
+    adjusted_scores = (1 - eta) * scores + eta * dewi_scores
+    if entropy_pref != 0:
+        adjusted_scores += entropy_pref * entropies
+    top_k_indices = np.argpartition(adjusted_scores, -k)[-k:]
+    sorted_indices = top_k_indices[np.argsort(-adjusted_scores[top_k_indices])]
+    return sorted_indices.astype(np.int64), adjusted_scores[sorted_indices]
+
+
 def candidate_sims(embeddings, query, k, normalize=True):
     """Raw similarities and the 2k candidate set of backends.py:431-447 (for tie-window checks)."""
     query = np.asarray(query, dtype=np.float32)

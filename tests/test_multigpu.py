@@ -96,6 +96,59 @@ def test_nccl_sharded_search_matches_oracle(dtype, exchange):
         assert recall_at_k(rid, ids) >= 0.999
 
 
+def _full_scope_worker(rank, world, port, n, d, b, k, ret):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from dewi_b200 import ShardedDewiIndex, shard_range
+        from _util import make_corpus
+
+        emb, pay = make_corpus(n, d, seed=51, style="readme")
+        queries = np.random.RandomState(52).standard_normal((b, d)).astype(np.float32)
+        lo, hi = shard_range(n, world, rank, align=128)
+        ix = ShardedDewiIndex(d, dtype="bf16", device=rank, rerank_scope="full")
+        ix.add_local(emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        ix.build()
+        ids, sc = ix.search_batch(torch.from_numpy(queries).cuda(), k=k, eta=0.3, entropy_pref=0.5)
+        torch.cuda.synchronize()
+        assert ix.exchange == "nccl"
+        if rank == 0:
+            ret["ids"], ret["scores"] = ids.cpu().numpy(), sc.cpu().numpy()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_full_scope_matches_the_blend_over_every_row():
+    """rerank_scope="full" across real GPUs: every shard selects by the blended key, one all-gather, one re-rank."""
+    import torch.multiprocessing as mp
+
+    from oracle import search as osearch
+
+    from _util import bf16_round, entropy_column, make_corpus, recall_at_k
+
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least two GPUs")
+    world = min(world, 8)
+    n, d, b, k = 300_000, 128, 20, 10
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_full_scope_worker, args=(world, port, n, d, b, k, ret), nprocs=world, join=True)
+        ids, scores = ret["ids"], ret["scores"]
+    emb, pay = make_corpus(n, d, seed=51, style="readme")
+    queries = np.random.RandomState(52).standard_normal((b, d)).astype(np.float32)
+    rows, ent = bf16_round(emb), entropy_column(pay)
+    ref = [osearch.full_scope_search(rows, pay[:, 0], ent, q, k, 0.3, 0.5, True) for q in queries]
+    assert recall_at_k(np.stack([r[0] for r in ref]), ids) >= 0.999
+    np.testing.assert_allclose(scores, np.stack([r[1] for r in ref]), rtol=2e-5, atol=2e-6)
+
+
 def _join_worker(rank, world, port, n, d, tau, align, ret):
     import torch.distributed as dist
 

@@ -470,3 +470,116 @@ def test_rows_on_m_sweep_with_lists_overflowing_all_the_time(b):
     np.testing.assert_array_equal(sc, sc_q)
     rid, rsc = osearch.exact_search_batch(bf16_round(emb), pay[:, 0], entropy_column(pay), queries[:8], k, 0.3, 0.5, True)
     assert recall_at_k(rid, ids[:8]) >= 0.999
+
+
+# ---- rerank_scope="full": the blend applied over the whole corpus (opt-in, not the reference's semantics) ----------
+def _full_oracle(rows, pay, queries, k, eta, pref, normalize=True):
+    ent = entropy_column(pay)
+    out = [osearch.full_scope_search(rows, pay[:, 0], ent, q, k, eta, pref, normalize) for q in queries]
+    return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+@pytest.mark.parametrize("b", [3, 70])
+def test_full_scope_fp32_matches_the_blend_over_every_row(b):
+    """fp32 corpus -> exact CUDA-core sweep selecting by the blended key; compared with the reference's blend
+    statements applied to every row (oracle.search.full_scope_search).  The answer differs from the two-stage one."""
+    n, d, k = 40_000, 96, 10
+    emb, pay = make_corpus(n, d, seed=201, style="readme")
+    queries = np.random.RandomState(202).standard_normal((b, d)).astype(np.float32)
+    ix = dewi_b200.DewiIndex(dim=d, backend="cuda", rerank_scope="full")
+    ix.add_batch(None, emb, payload_columns=pay.astype(np.float32), normalized=True)
+    ix.build()
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    rid, rsc = _full_oracle(emb, pay, queries[:16], k, 0.3, 0.5)
+    for q in range(min(b, 16)):
+        check_topk(rid[q], rsc[q], ids[q], sc[q], what=f"full scope q{q}")
+    two_stage, _ = osearch.exact_search_batch(emb, pay[:, 0], entropy_column(pay), queries[:4], k, 0.3, 0.5, True)
+    assert (two_stage != rid[:4]).any(), "the two scopes should not coincide on this corpus"
+    # single-query facade and eta = 1 / pref = 0 (pure dewi ranking: the same ids for every query)
+    res = ix.search(queries[0], k=k, eta=0.3, entropy_pref=0.5)
+    assert [int(r[0].split("_")[1]) for r in res] == ids[0].tolist()
+    ids1, _ = ix.search_batch(queries[:2], k=k, eta=1.0, entropy_pref=0.0)
+    dewi32 = pay[:, 0].astype(np.float32)
+    np.testing.assert_array_equal(np.sort(dewi32[ids1[0]]), np.sort(dewi32)[-k:])
+    np.testing.assert_array_equal(ids1[0], ids1[1])
+
+
+def test_full_scope_l2_space_and_odd_dim():
+    n, d, k, b = 9_000, 50, 7, 5
+    rng = np.random.RandomState(211)
+    emb = (0.25 * rng.standard_normal((n, d))).astype(np.float32)
+    _, pay = make_corpus(n, 8, seed=212, style="readme")
+    queries = (0.25 * rng.standard_normal((b, d))).astype(np.float32)
+    ix = dewi_b200.DewiIndex(dim=d, space="l2", backend="cuda", rerank_scope="full")
+    ix.add_batch(None, emb, payload_columns=pay.astype(np.float32))
+    ix.build()
+    ids, sc = ix.search_batch(queries, k=k, eta=0.25, entropy_pref=-0.5)
+    rid, rsc = _full_oracle(emb, pay, queries, k, 0.25, -0.5, normalize=False)
+    for q in range(b):
+        check_topk(rid[q], rsc[q], ids[q], sc[q], what=f"full scope l2 q{q}")
+
+
+@pytest.mark.parametrize("b", [1, 64, 150])
+def test_full_scope_bf16_runs_on_the_tensor_cores(b):
+    """bf16 corpus -> rows-on-M sweep with the blended key evaluated per row in its epilogue (batches above 64 in
+    groups of 64); recall against the blend over every (bf16-representable) row."""
+    n, d, k = 400_123, 128, 10
+    emb, pay = make_corpus(n, d, seed=221, style="profile")
+    rows = bf16_round(emb)
+    queries = np.random.RandomState(222).standard_normal((b, d)).astype(np.float32)
+    ix = dewi_b200.DewiIndex(dim=d, backend="cuda", dtype="bf16", rerank_scope="full")
+    ix.add_batch(None, emb, payload_columns=pay.astype(np.float32), normalized=True)
+    ix.build()
+    be = ix._backend
+    be.set_profiling(True)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    assert be.sweep_ms(0)[1] == "tcgen05-rows"
+    be.set_profiling(False)
+    nq = min(b, 24)
+    sel = np.linspace(0, b - 1, nq).astype(int)
+    rid, rsc = _full_oracle(rows, pay, queries[sel], k, 0.3, 0.5)
+    assert recall_at_k(rid, ids[sel]) >= 0.999
+    np.testing.assert_allclose(sc[sel], rsc, rtol=2e-5, atol=2e-6)
+    # similarity only (eta = 0, no entropy term): the full scope then IS the top-k by similarity
+    ids0, sc0 = ix.search_batch(queries[:4], k=k, eta=0.0, entropy_pref=0.0)
+    be._flags &= ~_native.FLAG_SCOPE_FULL   # the same index in the reference's candidate scope
+    ids_c, sc_c = ix.search_batch(queries[:4], k=k, eta=0.0, entropy_pref=0.0)
+    np.testing.assert_array_equal(ids0, ids_c)
+    np.testing.assert_array_equal(sc0, sc_c)
+
+
+@pytest.mark.parametrize("n_shards", [3])
+def test_full_scope_virtual_shards_merge_equals_single_index(n_shards):
+    """The global top-k by the blend lies in the union of the shards' local ones: per-shard search_local (blended
+    key) + one dewi_rerank over the concatenated blocks == the single-index full-scope answer."""
+    import torch
+    n, d, k, b = 90_000, 64, 10, 9
+    emb, pay = make_corpus(n, d, seed=231, style="readme")
+    queries = np.random.RandomState(232).standard_normal((b, d)).astype(np.float32)
+    single = dewi_b200.DewiIndex(dim=d, backend="cuda", dtype="bf16", rerank_scope="full")
+    single.add_batch(None, emb, payload_columns=pay.astype(np.float32), normalized=True)
+    single.build()
+    ids1, sc1 = single.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    bounds = np.linspace(0, n, n_shards + 1).astype(int)
+    q_dev = torch.from_numpy(queries).cuda()
+    kcand = 2 * k
+    blocks = []
+    for g in range(n_shards):
+        lo, hi = bounds[g], bounds[g + 1]
+        sh = dewi_b200.CudaIndex(d, dtype="bf16", rerank_scope="full")
+        sh.set_id_base(int(lo))
+        sh.add_batch(None, emb[lo:hi], payload_columns=pay[lo:hi].astype(np.float32), normalized=True)
+        sh.build()
+        sh.set_blend(0.3, 0.5)
+        blocks.append(sh.search_local(q_dev, kcand))
+    sim, gid, dewi, ent = (torch.cat([blk[i] for blk in blocks], dim=1).contiguous() for i in range(4))
+    lib = _native.load_library()
+    out_ids = torch.empty((b, k), dtype=torch.int64, device="cuda")
+    out_sc = torch.empty((b, k), dtype=torch.float32, device="cuda")
+    import ctypes
+    _native.check(lib.dewi_rerank(ctypes.c_void_p(sim.data_ptr()), ctypes.c_void_p(gid.data_ptr()), ctypes.c_void_p(dewi.data_ptr()),
+                                  ctypes.c_void_p(ent.data_ptr()), b, 1, kcand * n_shards, 0, kcand * n_shards, k, 0.3, 0.5,
+                                  ctypes.c_void_p(out_ids.data_ptr()), ctypes.c_void_p(out_sc.data_ptr()), 0, _native.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out_ids.cpu().numpy(), ids1)
+    np.testing.assert_array_equal(out_sc.cpu().numpy(), sc1)
