@@ -454,9 +454,10 @@ def main():
 
     roofline = roofline_for(args.batch, sweep, flops)
     # dram__bytes_read+write of the main sweep launch from the committed `ncu --set full` capture
-    # (profiles/r2_o_prof_b64_12M5rows_raw.csv: 19.2006 GB read + 5.4 MB written for a 19.2 GB shard),
+    # (rows-on-M sweep, profiles/r2_t_prof_rows_on_m_b64_12M5rows_raw.csv: 19.2021 GB read + 4.7 MB written for a 19.2 GB
+    # shard; the queries-on-M sweep it replaced for B <= 64, profiles/r2_o_prof_b64_12M5rows_raw.csv: 19.2006 GB + 5.4 MB),
     # scaled to this shard; only the single-query-block kernel (B <= 128) was captured at that ratio
-    traffic = shard_bytes * 1.00031 if (args.batch <= 128 and kind.startswith("tcgen05")) else None
+    traffic = shard_bytes * 1.00036 if (args.batch <= 128 and kind.startswith("tcgen05")) else None
     roofline.update({"traffic": traffic, "traffic_source": "ncu capture of the same kernel at 12.5M rows, scaled by shard size"
                      if traffic else None, "kernel": f"similarity sweep ({kind}) incl. its sample pre-pass", "kernel_ms": sweep,
                      "algorithmic_bytes_per_launch": shard_bytes, "peak_source": peaks["source"],

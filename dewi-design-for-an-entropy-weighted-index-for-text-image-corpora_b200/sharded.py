@@ -270,7 +270,9 @@ class ShardedDewiIndex:
             self.dist.all_gather_into_tensor(pk.gathered, pk.local, group=self.group)
         out_ids = torch.empty((b, k), dtype=torch.int64, device=queries.device)
         out_scores = torch.empty((b, k), dtype=torch.float32, device=queries.device)
-        self._rerank_stage(pk, kcand, k, eta, entropy_pref, out_ids, out_scores)
+        # candidate scope: the global top-2k by similarity are blended (backends.py:439-481); full scope: every gathered
+        # candidate is (each shard already selected by the blended key)
+        self._rerank_stage(pk, kcand * self.world if full else kcand, k, eta, entropy_pref, out_ids, out_scores)
         return out_ids, out_scores
 
     def _check_status(self) -> None:
