@@ -722,7 +722,14 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       const int64_t tiles_total = ceil_div(h->n, n_tile);
       const int64_t workers = use_pair ? std::max(1, h->sm_count / 2) : h->sm_count;
       if (!(flags & DEWI_FLAG_NO_SEED) && tiles_total >= 16 * workers) {
-        const int64_t sample_tiles = std::max<int64_t>(workers, tiles_total / 128);
+        int64_t sample_tiles = std::max<int64_t>(workers, tiles_total / 128);
+        // Many query blocks over a SMALL corpus: every (chunk, query pair) work item restarts its lists at the seed, and a
+        // seed drawn from 2 % of 1M rows leaves ~70 rows per query above it in every item -- the epilogue then walks its
+        // slow path in 92 % of the 32-column groups and sets the pace (ncu: tensor pipe 43 % active at 1M rows, B = 4096).
+        // 128 sample tiles (3 % of 1M rows) halve that: B = 4096 sweep 6.91 -> 6.22 ms, B = 1024 1.77 -> 1.65 ms; 256
+        // tiles cost more than they return (7.70 ms).
+        if (use_pair && n_qb >= 8) sample_tiles = std::max<int64_t>(sample_tiles, std::min<int64_t>(128, tiles_total / 16));
+        if (env_set("DEWI_SEED_TILES")) sample_tiles = std::min<int64_t>(tiles_total / 2, std::max<int64_t>(workers, env_int("DEWI_SEED_TILES", 0)));  // experiments
         const int64_t sample_rows = sample_tiles * n_tile;
         TcPlan s1{};
         Tc2Plan s2{};

@@ -124,12 +124,22 @@ __device__ __forceinline__ void scan_tile(LaneList& l, int kc, uint32_t tcol, in
       for (int j = 0; j < 32; ++j)
         if (r0 + j >= n_rows) v[j] = -INFINITY;
     }
-    float mx = v[0];
+    // maxima of the four 8-column groups first: when hits are frequent but sparse (many query blocks over a small corpus:
+    // a couple per warp and 32 columns) only the groups that hold one are walked
+    float gm[32 / kGroup];
 #pragma unroll
-    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+    for (int g = 0; g < 32 / kGroup; ++g) {
+      gm[g] = v[g * kGroup];
+#pragma unroll
+      for (int jj = 1; jj < kGroup; ++jj) gm[g] = fmaxf(gm[g], v[g * kGroup + jj]);
+    }
+    float mx = gm[0];
+#pragma unroll
+    for (int g = 1; g < 32 / kGroup; ++g) mx = fmaxf(mx, gm[g]);
     if (__any_sync(0xffffffffu, mx > l.thr)) {
 #pragma unroll
       for (int g = 0; g < 32 / kGroup; ++g) {
+        if (!__any_sync(0xffffffffu, gm[g] > l.thr)) continue;
 #pragma unroll
         for (int jj = 0; jj < kGroup; ++jj) {
           const int j = g * kGroup + jj;
