@@ -356,6 +356,14 @@ search_tcr_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
       }
       epi_bar();
       for (int t = t0; t < t1; ++t) {
+        // (full scope: the two payload loads of both halves are issued BEFORE the wait for the accumulator, so their
+        // DRAM latency overlaps the MMAs instead of sitting in front of every half-tile)
+        RowKey keys[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int row = t * kRowTile + h * 128 + quarter * 32 + lane;
+          keys[h] = row_key(a.blend, row, row < a.n_rows);
+        }
         ptx::mbar_wait(&bar_acc_full[acc], acc_phase);
         ptx::tc_fence_after();
 #pragma unroll 1
@@ -363,7 +371,7 @@ search_tcr_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_consta
           const uint32_t tc = tmem_lane + static_cast<uint32_t>(acc * 2 * QN + h * QN);
           const int row = t * kRowTile + h * 128 + quarter * 32 + lane;
           const bool valid = row < a.n_rows;
-          const RowKey key = row_key(a.blend, row, valid);
+          const RowKey key = h ? keys[1] : keys[0];
           if (a.max_out) max_half<QN, CH>(a, imax, tc, valid, t * (kRowTile / 32) + h * 4 + quarter, lane, key);
           else scan_half<QN, CH>(L, tc, row, valid, e, lane, par, key);
         }
