@@ -607,13 +607,26 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
   const int n_qb_in = n_qb;
   // more than one query block: the CTA-pair sweep (two query blocks share every corpus tile)
   bool use_pair = false;
+  // rows the seeding pre-pass of the CTA-pair sweep samples, in tiles of 256 (see the seeding block below)
+  auto pair_sample_tiles = [&](int n_qb_) -> int64_t {
+    const int64_t tiles_total = ceil_div(h->n, 2 * tc2_box_rows());
+    int64_t t = std::max<int64_t>(std::max(1, h->sm_count / 2), tiles_total / 128);
+    if (n_qb_ >= 8) t = std::max<int64_t>(t, std::min<int64_t>(128, tiles_total / 16));
+    return t;
+  };
   auto make_plans = [&](int mode_, int kc_) -> bool {   // false: no tensor-core plan for this (mode, list capacity)
     n_qb = n_qb_in;
     b_pad = n_qb * kQueryBlock;
     use_pair = n_qb >= 2 && !(flags & DEWI_FLAG_NO_PAIR);
     if (use_pair) {
       const int n_qb2 = static_cast<int>(round_up(n_qb, 2));
-      if (tc2_make_plan(mode_, dim, h->n, n_qb2, kc_, h->sm_count, &plan2) == 0) {
+      // Many query pairs over a small corpus: the pre-pass sample is too small for a tight seed (see the seeding block
+      // below: ~1024 kc / sample_rows hits per warp and 32-column group), so the sweep is STAGED -- the first round of
+      // chunks runs as a launch of its own and its finished lists seed the rest (search_tc2.cu: tc2_make_plan).
+      const int64_t sample_rows = pair_sample_tiles(n_qb2) * 2 * tc2_box_rows();
+      const int staged = (n_qb2 >= 8 && !(flags & DEWI_FLAG_NO_SEED) && sample_rows * 3 < static_cast<int64_t>(4096) * kc_ &&
+                          env_int("DEWI_TC2_STAGED", 1) != 0) ? 1 : 0;
+      if (tc2_make_plan(mode_, dim, h->n, n_qb2, kc_, h->sm_count, &plan2, 0, 0, 0, staged) == 0) {
         n_qb = n_qb2;
         b_pad = n_qb * kQueryBlock;
         return true;
@@ -701,8 +714,26 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       if (use_pair) {
         const int64_t sync_words = tc2_sync_words(p2, rows, n_qb);
         if (sync_words > 0) DEWI_TRY(h->sync_cnt.ensure(static_cast<size_t>(sync_words) * 4));
-        DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
-                            h->part_i.as<int>(), sd, stream, sync_words > 0 ? h->sync_cnt.as<unsigned int>() : nullptr, fp16_planes));
+        unsigned int* sc = sync_words > 0 ? h->sync_cnt.as<unsigned int>() : nullptr;
+        if (p2.first_items > 0 && !sd.max_out) {
+          // staged: the first round of chunks, then the kc-th best of every query's finished lists as the seed of the rest
+          DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(), h->part_i.as<int>(), sd,
+                              stream, sc, fp16_planes, 0, p2.first_items));
+          DEWI_TRY(h->seed_sim.ensure(static_cast<size_t>(B) * 4));
+          DEWI_TRY(launch_seed_from_partials(h->part_s.as<float>(), p2.first_items / (n_qb / 2), n_qb, B, kc, sd.values,
+                                             h->seed_sim.as<float>(), stream));
+          SweepSeed sd2;
+          sd2.values = h->seed_sim.as<float>();
+          sd2.stride = 1;
+          sd2.off = 0;
+          sd2.n_queries = B;
+          DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(), h->part_i.as<int>(), sd2,
+                              stream, sc, fp16_planes, p2.first_items, -1));
+          h->last_launches += 2;
+        } else {
+          DEWI_TRY(tc2_launch(p2, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
+                              h->part_i.as<int>(), sd, stream, sc, fp16_planes));
+        }
       }
       else
         DEWI_TRY(tc_launch(p1, h->map_e0, h->map_e1, mq0, mq1, rows, dim, n_qb, kc, h->part_s.as<float>(),
@@ -722,13 +753,12 @@ static int search_local_impl(dewi_index_t* h, const float* queries, int B, int k
       const int64_t tiles_total = ceil_div(h->n, n_tile);
       const int64_t workers = use_pair ? std::max(1, h->sm_count / 2) : h->sm_count;
       if (!(flags & DEWI_FLAG_NO_SEED) && tiles_total >= 16 * workers) {
-        int64_t sample_tiles = std::max<int64_t>(workers, tiles_total / 128);
-        // Many query blocks over a SMALL corpus: every (chunk, query pair) work item restarts its lists at the seed, and a
+        int64_t sample_tiles = use_pair ? pair_sample_tiles(n_qb) : std::max<int64_t>(workers, tiles_total / 128);
+        // (many query blocks over a SMALL corpus: every (chunk, query pair) work item restarts its lists at the seed, and a
         // seed drawn from 2 % of 1M rows leaves ~70 rows per query above it in every item -- the epilogue then walks its
         // slow path in 92 % of the 32-column groups and sets the pace (ncu: tensor pipe 43 % active at 1M rows, B = 4096).
-        // 128 sample tiles (3 % of 1M rows) halve that: B = 4096 sweep 6.91 -> 6.22 ms, B = 1024 1.77 -> 1.65 ms; 256
-        // tiles cost more than they return (7.70 ms).
-        if (use_pair && n_qb >= 8) sample_tiles = std::max<int64_t>(sample_tiles, std::min<int64_t>(128, tiles_total / 16));
+        // pair_sample_tiles takes 128 tiles (3 % of 1M rows) there: B = 4096 sweep 6.91 -> 6.22 ms, B = 1024 1.77 -> 1.65 ms;
+        // 256 tiles cost more than they return (7.70 ms).  The staged sweep then tightens the seed further.)
         if (env_set("DEWI_SEED_TILES")) sample_tiles = std::min<int64_t>(tiles_total / 2, std::max<int64_t>(workers, env_int("DEWI_SEED_TILES", 0)));  // experiments
         const int64_t sample_rows = sample_tiles * n_tile;
         TcPlan s1{};

@@ -116,15 +116,17 @@ struct Tc2Plan {
   int q_stages;
   int n_chunks;
   int grid;
+  int first_items;   // staged sweep: items [0, first_items) run in a first launch whose lists seed the second (0: one launch)
   size_t smem_bytes;
 };
 int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks = 0,
-                  int64_t tiles_per_item = 0, int a_resident = 0);
+                  int64_t tiles_per_item = 0, int a_resident = 0, int stage_first = 0);
 int tc2_box_rows();
 int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb);
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt = nullptr, int fp16_planes = 0);
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt = nullptr, int fp16_planes = 0, int item0 = 0,
+               int item1 = -1);
 
 int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, const CUtensorMap& a0, const CUtensorMap& a1,
                     int64_t m_rows, int64_t m_pad, int64_t n_rows, int dim, int sm_count, float tau, int self_join, int64_t a_offset,
@@ -139,6 +141,10 @@ int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, in
 // ---- selection / re-rank (select.cu) ---------------------------------------------------------
 // seed[b] = the kc-th largest of query b's per-item maxima [n_chunks][n_qb][128] (-inf when n_chunks < kc)
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream);
+// Staged sweep: seed_out[b] = max(seed_in[b] (optional), the kc-th largest entry of query b's partial lists of chunks
+// [0, n_chunks_done)) -- kc distinct rows score at least that much, so it bounds the query's kc-th best from below.
+int launch_seed_from_partials(const float* part_s, int n_chunks_done, int n_qb, int B, int kc, const float* seed_in, float* seed_out,
+                              cudaStream_t stream);
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);
 int launch_rescore(const void* rows, int rows_are_bf16, int dim, const float* qn, int* cand_idx, int B, int kc,
                    float* cand_sim, cudaStream_t stream, const float* bar = nullptr);

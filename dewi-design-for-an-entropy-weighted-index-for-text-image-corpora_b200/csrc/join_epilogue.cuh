@@ -17,6 +17,7 @@ struct Tc2Args {
   int n_qpairs;   // query-block pairs
   int n_chunks;
   int n_items;    // n_chunks * n_qpairs, dealt to clusters
+  int item0, item1;  // the items this launch walks (a staged sweep runs the first chunks in a launch of their own)
   int kc;
   int e_stages;
   int q_stages;

@@ -161,7 +161,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     // chunk: leave it in L2 at normal priority unless this is the only pair
     const uint64_t e_policy = a.n_qpairs > 1 ? ptx::kEvictNormal : ptx::kEvictFirst;
     uint32_t a_ph = 0;
-    for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+    for (int item = a.item0 + cluster_id; item < a.item1; item += n_clusters) {
       const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
       const int qrow = (sp.qpair * 2 + static_cast<int>(rank)) * kQueryBlock + (a.sym ? static_cast<int>(a.a_offset) : 0);
       if (ARES && sp.len > 0) {
@@ -182,11 +182,12 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       int sync_expect = 0;
       unsigned int* sync_row = nullptr;
       if (a.sync_cnt && rank == 0) {
-        const int chunk = item / a.n_qpairs, round = item / n_clusters;
+        // (rounds are counted from the launch's first item; item0 is a multiple of n_qpairs, so first >= item0)
+        const int chunk = item / a.n_qpairs, round = (item - a.item0) / n_clusters;
         const int first = chunk * a.n_qpairs, last = first + a.n_qpairs;                 // the chunk's items
-        const int lo = max(first, round * n_clusters), hi = min(min(last, (round + 1) * n_clusters), a.n_items);
+        const int lo = max(first, a.item0 + round * n_clusters), hi = min(min(last, a.item0 + (round + 1) * n_clusters), a.item1);
         sync_expect = hi - lo;
-        sync_row = a.sync_cnt + (static_cast<size_t>(chunk) * 2 + (round - first / n_clusters)) * a.sync_blocks;
+        sync_row = a.sync_cnt + (static_cast<size_t>(chunk) * 2 + (round - (first - a.item0) / n_clusters)) * a.sync_blocks;
       }
       for (int step = 0; step < sp.len; ++step) {
         if (sync_expect > 1 && (step % a.sync_every) == 0 && step / a.sync_every < a.sync_blocks) {
@@ -230,7 +231,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
       const uint32_t ring_addr = ptx::smem_u32(ring);
       const uint32_t a_addr = ptx::smem_u32(a_buf);
       uint32_t a_full_ph = 0;
-      for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+      for (int item = a.item0 + cluster_id; item < a.item1; item += n_clusters) {
         const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
         if (ARES && sp.len > 0) {
           ptx::mbar_wait(bar_a_full, a_full_ph);   // the item's row block (both CTAs' halves of M) has landed
@@ -287,7 +288,7 @@ search_tc2_kernel(const __grid_constant__ CUtensorMap map_e0, const __grid_const
     l.stride = kQueryBlock;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = cluster_id; item < a.n_items; item += n_clusters) {
+    for (int item = a.item0 + cluster_id; item < a.item1; item += n_clusters) {
       const int chunk = item / a.n_qpairs;
       const ItemSpan sp = item_span(a, item, cluster_id, n_clusters);
       const int qb = sp.qpair * 2 + static_cast<int>(rank);
@@ -387,7 +388,7 @@ int launch_one(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
 }  // namespace
 
 int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, Tc2Plan* plan, int force_chunks,
-                  int64_t tiles_per_item, int a_resident) {
+                  int64_t tiles_per_item, int a_resident, int stage_first) {
   if (!tc_supported(dim, n_rows)) return fail("tcgen05 sweep needs dim % 64 == 0 and rows < 2^31");
   if (n_qb < 2 || (n_qb & 1)) return fail("the CTA-pair sweep needs an even number of query blocks");
   const size_t smem_max = 227 * 1024;
@@ -411,6 +412,23 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   int64_t chunks = want;
   for (int64_t c = want; c <= want + clusters && c <= n_tiles; ++c) {
     if ((c * n_qpairs) % clusters == 0) { chunks = c; break; }
+  }
+  // STAGED sweep (many query pairs over a small corpus; api.cu): the first `a` chunks -- as many as one round of
+  // clusters holds -- run in a launch of their own, and the kc-th best of each query's finished lists seeds the rest:
+  // a bound drawn from a / chunks of the corpus instead of the pre-pass's 2-3 %, at no extra MMA work.  Chunks are
+  // chosen so that the second launch is a whole number of rounds.
+  plan->first_items = 0;
+  if (stage_first && force_chunks <= 0 && tiles_per_item <= 0 && !a_resident) {
+    const int64_t a = clusters / n_qpairs;
+    if (a >= 1) {
+      for (int64_t c = std::max<int64_t>(chunks, a + 1); c <= chunks + 2 * clusters && c <= n_tiles; ++c) {
+        if (((c - a) * n_qpairs) % clusters == 0) {
+          chunks = c;
+          plan->first_items = static_cast<int>(a * n_qpairs);
+          break;
+        }
+      }
+    }
   }
   if (force_chunks > 0) chunks = force_chunks;
   chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n_tiles));
@@ -443,7 +461,7 @@ int64_t tc2_sync_words(const Tc2Plan& plan, int64_t n_rows, int n_qb) {
 
 int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1, const CUtensorMap& q0,
                const CUtensorMap& q1, int64_t n_rows, int dim, int n_qb, int kc, float* part_s, int* part_i,
-               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt, int fp16_planes) {
+               const SweepSeed& seed, cudaStream_t stream, unsigned int* sync_cnt, int fp16_planes, int item0, int item1) {
   Tc2Args a;
   a.fp16 = fp16_planes;
   a.n_rows = static_cast<int>(n_rows);
@@ -452,6 +470,8 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   a.n_qpairs = n_qb / 2;
   a.n_chunks = plan.n_chunks;
   a.n_items = plan.n_chunks * a.n_qpairs;
+  a.item0 = item0;
+  a.item1 = item1 < 0 ? a.n_items : std::min(item1, a.n_items);
   a.kc = kc;
   a.e_stages = plan.n_stages;
   a.q_stages = plan.q_stages;
@@ -476,7 +496,7 @@ int tc2_launch(const Tc2Plan& plan, const CUtensorMap& e0, const CUtensorMap& e1
   if (sync_cnt && a.n_qpairs > 1 && a.n_qpairs <= plan.grid / 2) {
     const int64_t words = tc2_sync_words(plan, n_rows, n_qb);
     if (words > 0) {
-      DEWI_CUDA(cudaMemsetAsync(sync_cnt, 0, static_cast<size_t>(words) * 4, stream));
+      if (item0 == 0) DEWI_CUDA(cudaMemsetAsync(sync_cnt, 0, static_cast<size_t>(words) * 4, stream));  // (rows are per chunk)
       a.sync_cnt = sync_cnt;
       a.sync_blocks = static_cast<int>(words / (2 * plan.n_chunks));
     }
@@ -536,6 +556,8 @@ int tc2_join_launch(int mode, const CUtensorMap& b0, const CUtensorMap& b1, cons
   a.n_qpairs = n_qb / 2;
   a.n_chunks = plan.n_chunks;
   a.n_items = plan.n_chunks * a.n_qpairs;
+  a.item0 = 0;
+  a.item1 = a.n_items;
   a.kc = 0;
   a.e_stages = plan.n_stages;
   a.q_stages = plan.q_stages;

@@ -159,6 +159,38 @@ seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb
   }
 }
 
+// Staged sweep (api.cu): the same selection over the finished partial lists [chunk][n_qb][kc][128] of the first chunks.
+__global__ void __launch_bounds__(512)
+seed_from_partials_kernel(const float* __restrict__ part_s, int n_vals, int n_qb, int kc, const float* __restrict__ seed_in,
+                          float* __restrict__ seed_out) {
+  __shared__ unsigned long long key[kWindow];
+  __shared__ float found;
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
+  for (int t = threadIdx.x; t < n_vals; t += blockDim.x) {
+    const int chunk = t / kc, k = t - chunk * kc;
+    const float v = part_s[((static_cast<size_t>(chunk) * n_qb + qb) * kc + k) * kQueryBlock + ql];
+    key[t] = (v > -INFINITY) ? make_key(v, static_cast<uint32_t>(t)) : 0ull;
+  }
+  if (threadIdx.x == 0) found = -INFINITY;
+  __syncthreads();
+  for (int e = threadIdx.x; e < n_vals; e += blockDim.x) {
+    const unsigned long long x = key[e];
+    if (x == 0ull) continue;
+    int rank = 0;
+    for (int f = 0; f < n_vals; ++f) rank += (key[f] > x) ? 1 : 0;
+    if (rank == kc - 1) {
+      const uint32_t o = static_cast<uint32_t>(x >> 32);
+      found = __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float prev = seed_in ? seed_in[b] : -INFINITY;
+    seed_out[b] = (prev > found) ? prev : found;   // (a NaN or missing earlier seed compares false: `found` stands)
+  }
+}
+
 // ---- certificate of the single-plane sweep ----------------------------------------------------------------
 // fp32 corpus, swept through its bf16 hi plane only (api.cu: certified mode).  With s = q . e the exact similarity
 // and S the swept one (bf16 products are exact, fp32 accumulation),
@@ -741,6 +773,15 @@ tail_kernel(const TailArgs a) {
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream) {
   if (n_chunks < kc || n_chunks > kWindow) return fail("seed_from_maxima: item count outside [kc, 2048]");
   seed_from_maxima_kernel<<<B, 512, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
+  DEWI_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_seed_from_partials(const float* part_s, int n_chunks_done, int n_qb, int B, int kc, const float* seed_in, float* seed_out,
+                              cudaStream_t stream) {
+  const int n_vals = n_chunks_done * kc;
+  if (n_vals < kc || n_vals > kWindow) return fail("seed_from_partials: list count out of range");
+  seed_from_partials_kernel<<<B, 512, 0, stream>>>(part_s, n_vals, n_qb, kc, seed_in, seed_out);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }

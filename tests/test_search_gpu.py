@@ -583,3 +583,38 @@ def test_full_scope_virtual_shards_merge_equals_single_index(n_shards):
     torch.cuda.synchronize()
     np.testing.assert_array_equal(out_ids.cpu().numpy(), ids1)
     np.testing.assert_array_equal(out_sc.cpu().numpy(), sc1)
+
+
+@pytest.mark.parametrize("dtype,b", [("bf16", 1024), ("fp32", 1500)])
+def test_staged_pair_sweep_equals_unseeded_and_oracle(dtype, b):
+    """Many query pairs over a small corpus: the CTA-pair sweep runs its first round of chunks as a launch of its own and
+    seeds the rest from the finished lists (tc2_make_plan: first_items).  Same answers as the unseeded single launch
+    (DEWI_FLAG_NO_SEED), exact ties at the seed included, and the oracle's."""
+    n, d, k = 700_000, 64, 10
+    emb, pay = make_corpus(n, d, seed=241)
+    emb[3000:3030] = emb[77]            # 31 identical rows inside the first chunks ...
+    emb[650_000:650_025] = emb[77]      # ... and in the last ones
+    queries = np.random.RandomState(242).standard_normal((b, d)).astype(np.float32)
+    queries[5] = emb[77] + 0.01 * queries[5]
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    force = _native.FLAG_FORCE_TC | (_native.FLAG_FORCE_CERT if dtype == "fp32" else 0)
+    n0 = ix._backend.last_launches()
+    ids_s, sc_s = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=force)
+    launches_staged = ix._backend.last_launches()
+    ids_u, sc_u = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=force | _native.FLAG_NO_SEED)
+    launches_plain = ix._backend.last_launches()
+    assert launches_staged >= launches_plain + 3, "pre-pass + seed + a second sweep launch were expected"
+    sel = [q for q in range(b) if q != 5]
+    np.testing.assert_array_equal(ids_s[sel], ids_u[sel])
+    np.testing.assert_array_equal(sc_s[sel], sc_u[sel])
+    tied = {77, *range(3000, 3030), *range(650_000, 650_025)}
+    assert set(ids_s[5].tolist()) <= tied and set(ids_u[5].tolist()) <= tied
+    pick = np.linspace(0, b - 1, 12).astype(int)
+    pick = pick[pick != 5]
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries[pick], k, 0.3, 0.5, True)
+    if dtype == "fp32":
+        for i, q in enumerate(pick):
+            check_topk(rid[i], rsc[i], ids_s[q], sc_s[q], what=f"staged q{q}")
+    else:
+        assert recall_at_k(rid, ids_s[pick]) >= 0.999
