@@ -228,7 +228,9 @@ def run_c5(rows, torch, dewi_b200, peaks, dist_ready=False):
         alg = float(nrows) * (nrows - 1) * d
         tiles = -(-nrows // 256)
         executed = 2.0 * 256 * 256 * d * tiles * (1 + (tiles - 1) / 2 + (0.5 if tiles % 2 == 0 else 0.0))
-        runs.append({"precision": precision, "rows": nrows, "ms": ms, "pairs_found": n_found, "pairs_planted": (nrows // 100) if world == 1 else n // 100,
+        # planted pairs whose two rows both lie inside the rows this run joins (the fp32 run takes a prefix)
+        planted = int(((dup < nrows) & (src < nrows)).sum().item()) if world == 1 else n // 100
+        runs.append({"precision": precision, "rows": nrows, "ms": ms, "pairs_found": n_found, "pairs_planted": planted,
                      "pair_dots_per_s": nrows * (nrows - 1) / 2 / (ms / 1e3), "algorithmic_tflops": alg / (ms / 1e3) / 1e12,
                      "executed_tflops": executed * (3 if precision == "fp32" else 1) / (ms / 1e3) / 1e12})
         res.clear()
