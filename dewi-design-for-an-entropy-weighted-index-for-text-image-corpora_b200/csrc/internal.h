@@ -143,6 +143,7 @@ int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, in
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream);
 // Staged sweep: seed_out[b] = max(seed_in[b] (optional), the kc-th largest entry of query b's partial lists of chunks
 // [0, n_chunks_done)) -- kc distinct rows score at least that much, so it bounds the query's kc-th best from below.
+constexpr int kSeedWindow = 2048;   // list entries per query the selection ranks in shared memory (select.cu: kWindow)
 int launch_seed_from_partials(const float* part_s, int n_chunks_done, int n_qb, int B, int kc, const float* seed_in, float* seed_out,
                               cudaStream_t stream);
 int launch_merge_select(const Partials& p, int B, int kc_out, int* cand_idx, float* cand_sim, cudaStream_t stream);

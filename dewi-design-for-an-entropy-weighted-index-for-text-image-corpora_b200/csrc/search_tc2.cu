@@ -420,7 +420,9 @@ int tc2_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_co
   plan->first_items = 0;
   if (stage_first && force_chunks <= 0 && tiles_per_item <= 0 && !a_resident) {
     const int64_t a = clusters / n_qpairs;
-    if (a >= 1) {
+    // (the seed is the kc-th best of a * kc list entries per query, ranked in shared memory: long lists -- k above ~50 --
+    // stay with the single launch)
+    if (a >= 1 && a * kc <= kSeedWindow) {
       for (int64_t c = std::max<int64_t>(chunks, a + 1); c <= chunks + 2 * clusters && c <= n_tiles; ++c) {
         if (((c - a) * n_qpairs) % clusters == 0) {
           chunks = c;

@@ -59,6 +59,7 @@ __host__ __device__ inline int next_pow2(int v) {
 // sorted, later candidates trickle in and the number of bitonic sorts stays at one or two -- and a
 // sweep that ran with seeded thresholds, whose partial lists are mostly empty, needs a single small one.
 constexpr int kWindow = 2048;
+static_assert(kWindow == kSeedWindow, "tc2_make_plan sizes the staged sweep's first round by this window");
 constexpr int kMergeThreads = 1024;  // one compare-exchange per thread per bitonic stage
 
 __global__ void __launch_bounds__(kMergeThreads)

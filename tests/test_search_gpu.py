@@ -618,3 +618,20 @@ def test_staged_pair_sweep_equals_unseeded_and_oracle(dtype, b):
             check_topk(rid[i], rsc[i], ids_s[q], sc_s[q], what=f"staged q{q}")
     else:
         assert recall_at_k(rid, ids_s[pick]) >= 0.999
+
+
+def test_many_query_pairs_with_long_lists_skip_the_staged_sweep():
+    """k = 60 makes the candidate lists of one staged first round (18 chunks x 136 entries at B = 1024) longer than the
+    2048-entry window the seed selection ranks in shared memory: tc2_make_plan must keep the single launch instead of
+    planning a first round launch_seed_from_partials would refuse (the search used to fail with an error)."""
+    n, d, k, b = 120_000, 64, 60, 1024
+    emb, pay = make_corpus(n, d, seed=251)
+    queries = np.random.RandomState(252).standard_normal((b, d)).astype(np.float32)
+    ix = bulk_index(emb, pay, dtype="bf16")
+    ix._backend.set_profiling(True)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5, flags=_native.FLAG_FORCE_TC)
+    assert ix._backend.sweep_ms()[1] == "tcgen05-pair"
+    pick = np.linspace(0, b - 1, 8).astype(int)
+    rid, _ = osearch.exact_search_batch(bf16_round(emb), pay[:, 0], entropy_column(pay), queries[pick], k, 0.3, 0.5, True)
+    assert recall_at_k(rid, ids[pick]) >= 0.995   # (480 ids: bf16 query rounding may swap a pair at the 2k-th boundary)
+    assert np.all(np.diff(sc, axis=1) <= 0)
