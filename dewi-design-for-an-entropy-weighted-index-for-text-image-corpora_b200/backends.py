@@ -193,6 +193,10 @@ def _torch():
     return torch
 
 
+# candidates (min(2k, N), backends.py:440) one search keeps per query: the exact sweep's shared-memory lists hold 400
+MAX_CANDIDATES = 400
+
+
 class CudaIndex(BaseIndex):
     """Exact DEWI-re-ranked search on a B200 -- the drop-in for `ExactIndex` (backends.py:386-481).
 
@@ -473,6 +477,12 @@ class CudaIndex(BaseIndex):
         return self._n_device + len(self._pending)
 
     # ---- search --------------------------------------------------------------------------------
+    def _check_candidate_limit(self, k: int) -> None:
+        """Documented limit: the candidate lists live in shared memory."""
+        if min(2 * k, self._n_device) > MAX_CANDIDATES:
+            raise ValueError(f"k={k}: this backend re-ranks at most {MAX_CANDIDATES} candidates (min(2k, N)) per query, "
+                             f"i.e. k <= {MAX_CANDIDATES // 2} on a corpus of more than {MAX_CANDIDATES} rows")
+
     def search(self, query: np.ndarray, k: int = 10, eta: float = 0.5, entropy_pref: float = 0.0
                ) -> List[Tuple[str, float, Payload]]:
         """One query -> `[(doc_id, score, payload)]` sorted by score, descending (backends.py:414-481)."""
@@ -489,6 +499,7 @@ class CudaIndex(BaseIndex):
         if k > n:
             # np.argpartition(adjusted_scores, -k) raises for k > N (backends.py:468)
             raise ValueError(f"kth(=-{k}) out of bounds ({min(2 * k, n)})")
+        self._check_candidate_limit(k)
         if self._normalize:  # backends.py:420-424, same numpy expression -> same bits
             qn = np.linalg.norm(query)
             if qn > 0:
@@ -527,6 +538,7 @@ class CudaIndex(BaseIndex):
             self.build()
         if k > self._n_device:
             raise ValueError(f"k={k} exceeds the number of indexed rows ({self._n_device})")
+        self._check_candidate_limit(k)
         if isinstance(queries, np.ndarray):
             if queries.ndim != 2 or queries.shape[1] != self.dim:
                 raise ValueError(f"Expected queries of shape (B, {self.dim}), got {queries.shape}")

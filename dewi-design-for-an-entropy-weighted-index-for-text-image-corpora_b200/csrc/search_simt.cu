@@ -238,7 +238,9 @@ int simt_plan(int64_t n_rows, int B, int sm_count, int* n_chunks) {
 
 int simt_launch(const void* rows, int rows_are_bf16, int64_t n_rows, int dim, int space, const float* qn, int B, int kc,
                 int n_chunks, float* part_s, int* part_i, cudaStream_t stream, const SweepBlend* blend_) {
-  if (static_cast<size_t>(kSimtWarps) * 4 * kc * 8 > 200 * 1024) return fail("k too large for the exact sweep");
+  if (static_cast<size_t>(kSimtWarps) * 4 * kc * 8 > 200 * 1024)
+    return fail("k too large: a search keeps at most 400 candidates (min(2k, N), backends.py:440) per query, i.e. k <= 200 on "
+                "a corpus of more than 400 rows (documented limit; the reference accepts any k <= N)");
   const SweepBlend blend = blend_ ? *blend_ : SweepBlend();
   const int n_qb = static_cast<int>(ceil_div(B, kQueryBlock));
   const bool l2 = (space == DEWI_SPACE_L2);

@@ -35,7 +35,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 from . import _native
-from .backends import CudaIndex
+from .backends import MAX_CANDIDATES, CudaIndex
 
 
 def _torch():
@@ -246,6 +246,8 @@ class ShardedDewiIndex:
             raise ValueError("exchange must be 'auto', 'push' or 'nccl'")
         b = queries.shape[0]
         kcand = min(2 * k, self.n_total)  # backends.py:440
+        if kcand > MAX_CANDIDATES:
+            raise ValueError(f"k={k}: at most {MAX_CANDIDATES} candidates (min(2k, N)) are re-ranked per query")
         self._check_status()
         full = getattr(self.local, "rerank_scope", "candidates") == "full"
         if full:

@@ -145,7 +145,9 @@ DEWI_API int dewi_rerank_gathered(const float* sim, const int64_t* id, const flo
  * same dewi_rerank finishes the job -- also across shards: the global top-k by the blend is in the union of the local
  * ones).  The weights are per handle: set them before dewi_index_search_local; dewi_index_search sets them itself. */
 DEWI_API int dewi_index_set_blend(dewi_index_t* h, double eta, double entropy_pref);
-/* Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
+/* Limit: min(kcand, N) <= 400 candidates per query (k <= 200 for dewi_index_search on more than 400 rows); beyond it the
+ * calls fail with a message instead of truncating (the reference accepts any k <= N).
+ * Whole single-shard search = search_local + rerank.  With DEWI_FLAG_HOST_IO `queries`,
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,
                       int flags, int64_t* out_id, float* out_score, void* stream);

@@ -635,3 +635,34 @@ def test_many_query_pairs_with_long_lists_skip_the_staged_sweep():
     rid, _ = osearch.exact_search_batch(bf16_round(emb), pay[:, 0], entropy_column(pay), queries[pick], k, 0.3, 0.5, True)
     assert recall_at_k(rid, ids[pick]) >= 0.995   # (480 ids: bf16 query rounding may swap a pair at the 2k-th boundary)
     assert np.all(np.diff(sc, axis=1) <= 0)
+
+
+@pytest.mark.parametrize("dtype,n,d,k", [("fp32", 5000, 128, 100), ("fp32", 5000, 128, 200), ("bf16", 9000, 64, 200),
+                                          ("fp32", 300, 100, 150)])
+def test_large_k_up_to_the_documented_limit(dtype, n, d, k):
+    """Up to 400 candidates (min(2k, N)) per query: long lists take the exact CUDA-core sweep (the tensor-core sweeps'
+    shared memory holds ~150) and the fused tail; checked against the oracle like every other search."""
+    emb, pay = make_corpus(n, d, seed=261)
+    queries = np.random.RandomState(262).standard_normal((3, d)).astype(np.float32)
+    rows = emb if dtype == "fp32" else bf16_round(emb)
+    ix = bulk_index(emb, pay, dtype=dtype)
+    ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+    rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries, k, 0.3, 0.5, True)
+    for i in range(len(queries)):
+        check_topk(rid[i], rsc[i], ids[i], sc[i], what=f"k={k} q{i}")
+    res = ix.search(queries[0], k=k, eta=0.3, entropy_pref=0.5)
+    assert len(res) == k and [int(r[0][4:]) for r in res] == ids[0].tolist()
+
+
+def test_k_above_the_candidate_limit_raises():
+    emb, pay = make_corpus(3000, 64, seed=263)
+    ix = bulk_index(emb, pay, dtype="fp32")
+    q = np.random.RandomState(264).standard_normal((2, 64)).astype(np.float32)
+    with pytest.raises(ValueError, match="400 candidates"):
+        ix.search_batch(q, k=201)
+    with pytest.raises(ValueError, match="400 candidates"):
+        ix.search(q[0], k=201)
+    # the library refuses as well (a caller that binds the C ABI directly, INTEGRATION.md)
+    be = ix._backend
+    with pytest.raises(_native.NativeError, match="at most 400 candidates"):
+        be._search_host(q, 201, 0.3, 0.5)
