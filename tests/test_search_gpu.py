@@ -666,3 +666,41 @@ def test_k_above_the_candidate_limit_raises():
     be = ix._backend
     with pytest.raises(_native.NativeError, match="at most 400 candidates"):
         be._search_host(q, 201, 0.3, 0.5)
+
+
+def _shape_sweep():
+    """Edge shapes of the plan selection (tile / query-block / minimum-row boundaries) + seeded random ones."""
+    shapes = [(2047, 64, 1, 10), (2048, 64, 1, 10), (2049, 128, 64, 10), (4097, 64, 65, 3), (16385, 128, 128, 10),
+              (8191, 192, 129, 7), (33000, 64, 256, 10), (12345, 256, 257, 10), (70001, 64, 513, 5), (1, 64, 3, 1),
+              (31, 128, 2, 20), (5000, 1024, 9, 10), (40000, 320, 31, 40), (9000, 64, 1025, 2), (2500, 448, 700, 10)]
+    rng = np.random.RandomState(271)
+    for _ in range(14):
+        shapes.append((int(rng.randint(1, 60000)), int(rng.choice([64, 128, 192, 256, 384, 100, 72])), int(rng.randint(1, 600)),
+                       int(rng.randint(1, 48))))
+    return shapes
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_shape_sweep_default_path_selection_vs_oracle(dtype):
+    """No forcing flags: whatever sweep the planner picks for the shape (rows-on-M, queries-on-M, CTA pairs, staged,
+    certified, CUDA cores) must reproduce the oracle -- shapes sit on the planner's boundaries (2048 rows, 64 / 128 /
+    256 queries, ragged tiles, dims that are not a multiple of 64, one-row corpora)."""
+    for si, (n, d, b, k) in enumerate(_shape_sweep()):
+        k = min(k, n)
+        emb, pay = make_corpus(n, d, seed=300 + si)
+        queries = np.random.RandomState(400 + si).standard_normal((b, d)).astype(np.float32)
+        rows = emb if dtype == "fp32" else bf16_round(emb)
+        ix = bulk_index(emb, pay, dtype=dtype)
+        ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
+        assert ids.shape == (b, k)
+        pick = np.unique(np.linspace(0, b - 1, min(b, 24)).astype(int))
+        rid, rsc = osearch.exact_search_batch(rows, pay[:, 0], entropy_column(pay), queries[pick], k, 0.3, 0.5, True)
+        what = f"shape {si}: n={n} d={d} B={b} k={k} {dtype}"
+        if dtype == "fp32":
+            for i, q in enumerate(pick):
+                check_topk(rid[i], rsc[i], ids[q], sc[q], what=f"{what} q{q}")
+        else:
+            # bf16 rows: the tensor-core sweeps round the query too (one bf16 plane + exact re-score of the candidates)
+            assert recall_at_k(rid, ids[pick]) >= 0.995, what
+            assert np.max(np.abs(np.sort(sc[pick], axis=1) - np.sort(rsc, axis=1))) <= 2e-3, what
+        del ix
