@@ -108,3 +108,31 @@ def test_nan_signals_and_extreme_deltas_follow_numpy():
             np.testing.assert_allclose(out[ok], want, rtol=SCORE_RTOL, atol=1e-300 if dt == "float64" else 1e-45)
     w = dewi_b200.local_weights_from_surprisal(np.array([0.5, np.nan, 2.0, 1.0, 3.0], np.float32))
     assert np.isnan(w[1]) and not np.isnan(w[[0, 2, 3, 4]]).any()
+
+
+@pytest.mark.parametrize("n", [(1 << 22) - 1, 5_000_002])
+def test_adversarial_columns_keep_fit_stats_exact(n):
+    """Columns built to defeat the sampled window of the large-n selection (scorer.cu): sorted and periodic data (a
+    strided sample is then biased), a constant column, two values, a heavy tail, values one ulp apart, denormals and
+    infinities.  Whatever path the kernel takes (window hit, window miss -> plain radix passes) the medians / MADs must
+    equal np.median's bit for bit (scorer.py:18-26)."""
+    rng = np.random.RandomState(n % 977)
+    base = rng.standard_normal(n).astype(np.float32)
+    one = np.float32(1.0)
+    cols = [
+        np.sort(base),                                                     # ascending
+        (np.arange(n) % 4096).astype(np.float32),                          # sawtooth, period = a power of two
+        np.full(n, 0.375, np.float32),                                     # constant: MAD = 0 -> 1e-8
+        np.where(rng.rand(n) < 0.5, np.float32(-2.0), np.float32(7.0)),    # two values
+        rng.standard_cauchy(n).astype(np.float32),                         # heavy tail
+        np.where(rng.rand(n) < 0.5, one, np.nextafter(one, np.float32(2.0), dtype=np.float32)),   # 1 or 1 + one ulp
+        base * np.float32(1e-41),                                          # denormals around zero
+    ]
+    cols[4][:3] = [np.inf, -np.inf, np.inf]
+    sig = np.stack(cols).astype(np.float32)
+    named = {k: sig[i] for i, k in enumerate(SIGNAL_FIELDS)}
+    med, mad = oscorer.robust_fit(named)
+    s = dewi_b200.DewiScorer()
+    s.fit_stats_columns(sig)
+    assert s.stats.medians == med, (s.stats.medians, med)
+    assert s.stats.mads == mad, (s.stats.mads, mad)
