@@ -368,6 +368,10 @@ int tc_make_plan(int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_cou
     n_tile = 128;
   }
   if (stages < 2) return fail("candidate list capacity too large for the tcgen05 sweep's shared memory");
+  // M = 64 sweeps of one or two planes exist for 256-row tiles only (tc_launch): lists long enough to force 128-row
+  // tiles there (k above ~105 with at most 64 queries) have no plan -- the caller takes the CUDA-core sweep
+  if (q_rows == 64 && mode != 2 && n_tile != 256)
+    return fail("candidate list capacity too large for the M = 64 tcgen05 sweep's shared memory");
   // four 32 KB stages in flight per SM stream fastest (12.5M rows, B = 128: 3.37 / 3.04 / 3.21 ms with 3 / 4 / 5 stages):
   // a deeper ring only adds concurrent DRAM streams
   stages = std::min(stages, 4);
