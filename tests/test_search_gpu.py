@@ -637,13 +637,16 @@ def test_many_query_pairs_with_long_lists_skip_the_staged_sweep():
     assert np.all(np.diff(sc, axis=1) <= 0)
 
 
-@pytest.mark.parametrize("dtype,n,d,k", [("fp32", 5000, 128, 100), ("fp32", 5000, 128, 200), ("bf16", 9000, 64, 200),
-                                          ("fp32", 300, 100, 150)])
-def test_large_k_up_to_the_documented_limit(dtype, n, d, k):
+@pytest.mark.parametrize("dtype,n,d,k,b", [("fp32", 5000, 128, 100, 3), ("fp32", 5000, 128, 200, 3), ("bf16", 9000, 64, 200, 3),
+                                            ("fp32", 300, 100, 150, 3), ("fp32", 5000, 128, 150, 8), ("bf16", 9000, 64, 120, 40),
+                                            ("bf16", 6000, 128, 110, 100), ("fp32", 6000, 64, 160, 300)])
+def test_large_k_up_to_the_documented_limit(dtype, n, d, k, b):
     """Up to 400 candidates (min(2k, N)) per query: long lists take the exact CUDA-core sweep (the tensor-core sweeps'
-    shared memory holds ~150) and the fused tail; checked against the oracle like every other search."""
+    shared memory holds ~150-220) and the fused tail; checked against the oracle like every other search.  k = 110-160
+    used to plan an M = 64 sweep on 128-row tiles that has no kernel (tc_make_plan) -- with few queries, with one
+    query block and with CTA pairs."""
     emb, pay = make_corpus(n, d, seed=261)
-    queries = np.random.RandomState(262).standard_normal((3, d)).astype(np.float32)
+    queries = np.random.RandomState(262).standard_normal((b, d)).astype(np.float32)
     rows = emb if dtype == "fp32" else bf16_round(emb)
     ix = bulk_index(emb, pay, dtype=dtype)
     ids, sc = ix.search_batch(queries, k=k, eta=0.3, entropy_pref=0.5)
