@@ -61,6 +61,7 @@ __host__ __device__ inline int next_pow2(int v) {
 constexpr int kWindow = 2048;
 static_assert(kWindow == kSeedWindow, "tc2_make_plan sizes the staged sweep's first round by this window");
 constexpr int kMergeThreads = 1024;  // one compare-exchange per thread per bitonic stage
+static_assert(kWindow <= 2 * kMergeThreads, "the seed selections hold the window two keys per thread");
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ part_i, int n_chunks, int n_qb, int kc,
@@ -136,9 +137,45 @@ merge_select_kernel(const float* __restrict__ part_s, const int* __restrict__ pa
 // Pre-pass result -> admission thresholds.  Every work item of the pre-pass reported the best score it
 // saw for the query; those maxima belong to distinct corpus rows, so the kc-th largest of them is a
 // lower bound of the query's kc-th best score over the corpus.
+//
+// The kc-th largest of up to 2 * blockDim values (each thread holds two order-preserving 32-bit keys, 0 = absent) by
+// bisection on the key: 32 rounds, each one or two barrier-popcounts (__syncthreads_count), no shared memory and no
+// n^2 work.  (Rank counting -- every key against every other -- took 684 us for 4096 queries x 1024 maxima, 14 % of
+// the C2 B = 4096 search: profiles/r2_zy_launches_c2_b4096_1Mrows.csv.)  Returns 0 when fewer than kc keys are present.
+__device__ __forceinline__ uint32_t kth_largest_key(uint32_t k0, uint32_t k1, bool two, int kc) {
+  uint32_t prefix = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = prefix | (1u << bit);
+    int c = __syncthreads_count(k0 >= cand);
+    if (two) c += __syncthreads_count(k1 >= cand);   // (`two` is uniform over the block)
+    if (c >= kc) prefix = cand;                      // at least kc keys are >= cand: the kc-th largest is too
+  }
+  return prefix;
+}
+__device__ __forceinline__ float key_to_float(uint32_t o) {
+  return o ? __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o) : -INFINITY;   // 0: fewer than kc values -> no seed
+}
+
 __global__ void __launch_bounds__(kMergeThreads)
 seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb, int kc, float* __restrict__ seed) {
-  // rank counting instead of a sort: the key beaten by exactly kc - 1 others is the kc-th largest (keys are distinct)
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
+  uint32_t k[2] = {0u, 0u};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int t = static_cast<int>(threadIdx.x) + s * static_cast<int>(blockDim.x);
+    if (t < n_chunks) {
+      const float v = maxima[(static_cast<size_t>(t) * n_qb + qb) * kQueryBlock + ql];
+      if (v > -INFINITY) k[s] = orderable(v);   // (every finite score maps to a non-zero key; NaN is dropped)
+    }
+  }
+  const uint32_t kth = kth_largest_key(k[0], k[1], n_chunks > static_cast<int>(blockDim.x), kc);
+  if (threadIdx.x == 0) seed[b] = key_to_float(kth);
+}
+
+// The same selection by rank counting (the key beaten by exactly kc - 1 others): kept for A/B runs (DEWI_SEED_RANKCOUNT=1).
+__global__ void __launch_bounds__(kMergeThreads)
+seed_from_maxima_rank_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb, int kc, float* __restrict__ seed) {
   __shared__ unsigned long long key[kWindow];
   const int b = blockIdx.x;
   const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
@@ -161,9 +198,32 @@ seed_from_maxima_kernel(const float* __restrict__ maxima, int n_chunks, int n_qb
 }
 
 // Staged sweep (api.cu): the same selection over the finished partial lists [chunk][n_qb][kc][128] of the first chunks.
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kMergeThreads)
 seed_from_partials_kernel(const float* __restrict__ part_s, int n_vals, int n_qb, int kc, const float* __restrict__ seed_in,
                           float* __restrict__ seed_out) {
+  const int b = blockIdx.x;
+  const int qb = b / kQueryBlock, ql = query_lane(b % kQueryBlock);
+  uint32_t k[2] = {0u, 0u};
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int t = static_cast<int>(threadIdx.x) + s * static_cast<int>(blockDim.x);
+    if (t < n_vals) {
+      const int chunk = t / kc, e = t - chunk * kc;
+      const float v = part_s[((static_cast<size_t>(chunk) * n_qb + qb) * kc + e) * kQueryBlock + ql];
+      if (v > -INFINITY) k[s] = orderable(v);
+    }
+  }
+  const float found = key_to_float(kth_largest_key(k[0], k[1], n_vals > static_cast<int>(blockDim.x), kc));
+  if (threadIdx.x == 0) {
+    const float prev = seed_in ? seed_in[b] : -INFINITY;
+    seed_out[b] = (prev > found) ? prev : found;   // (a NaN or missing earlier seed compares false: `found` stands)
+  }
+}
+
+// (rank-counting form, DEWI_SEED_RANKCOUNT=1)
+__global__ void __launch_bounds__(512)
+seed_from_partials_rank_kernel(const float* __restrict__ part_s, int n_vals, int n_qb, int kc, const float* __restrict__ seed_in,
+                               float* __restrict__ seed_out) {
   __shared__ unsigned long long key[kWindow];
   __shared__ float found;
   const int b = blockIdx.x;
@@ -188,7 +248,7 @@ seed_from_partials_kernel(const float* __restrict__ part_s, int n_vals, int n_qb
   __syncthreads();
   if (threadIdx.x == 0) {
     const float prev = seed_in ? seed_in[b] : -INFINITY;
-    seed_out[b] = (prev > found) ? prev : found;   // (a NaN or missing earlier seed compares false: `found` stands)
+    seed_out[b] = (prev > found) ? prev : found;
   }
 }
 
@@ -773,7 +833,9 @@ tail_kernel(const TailArgs a) {
 
 int launch_seed_from_maxima(const float* maxima, int n_chunks, int n_qb, int B, int kc, float* seed, cudaStream_t stream) {
   if (n_chunks < kc || n_chunks > kWindow) return fail("seed_from_maxima: item count outside [kc, 2048]");
-  seed_from_maxima_kernel<<<B, 512, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
+  // 1024 threads hold the (at most 2048) maxima two per thread
+  if (env_int("DEWI_SEED_RANKCOUNT", 0) != 0) seed_from_maxima_rank_kernel<<<B, 512, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);  // experiments
+  else seed_from_maxima_kernel<<<B, kMergeThreads, 0, stream>>>(maxima, n_chunks, n_qb, kc, seed);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
@@ -782,7 +844,10 @@ int launch_seed_from_partials(const float* part_s, int n_chunks_done, int n_qb, 
                               cudaStream_t stream) {
   const int n_vals = n_chunks_done * kc;
   if (n_vals < kc || n_vals > kWindow) return fail("seed_from_partials: list count out of range");
-  seed_from_partials_kernel<<<B, 512, 0, stream>>>(part_s, n_vals, n_qb, kc, seed_in, seed_out);
+  if (env_int("DEWI_SEED_RANKCOUNT", 0) != 0)
+    seed_from_partials_rank_kernel<<<B, 512, 0, stream>>>(part_s, n_vals, n_qb, kc, seed_in, seed_out);  // experiments
+  else
+    seed_from_partials_kernel<<<B, kMergeThreads, 0, stream>>>(part_s, n_vals, n_qb, kc, seed_in, seed_out);
   DEWI_CUDA(cudaGetLastError());
   return 0;
 }
