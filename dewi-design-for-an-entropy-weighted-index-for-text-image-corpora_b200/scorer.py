@@ -31,6 +31,9 @@ def _device_index(device: Optional[int]) -> int:
     return torch.cuda.current_device() if torch.cuda.is_available() else 0
 
 
+MAX_FIT_COLUMNS = 32  # columns one dewi_fit_stats call accepts (csrc/scorer.cu: kMaxCols)
+
+
 def _fit_columns(cols, device: int, zero_mad_as: float = 1e-8):
     """cols: CUDA float32 tensor [F, N] (row c = one signal column).  Returns (med[F], mad[F]) as float64
     arrays.  The library reports a zero MAD as 1e-8 (scorer.py:24); `zero_mad_as` maps it back for callers
@@ -38,16 +41,24 @@ def _fit_columns(cols, device: int, zero_mad_as: float = 1e-8):
     torch = _torch()
     lib = _native.load_library()
     f, n = cols.shape
-    med = (ctypes.c_double * f)()
-    mad = (ctypes.c_double * f)()
-    # (the library selects the device itself; the stream is the current one of THAT device)
-    rc = lib.dewi_fit_stats(ctypes.c_void_p(cols.data_ptr()), n, f, cols.stride(0), med, mad, device,
-                            ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
-    _native.check(rc)
-    mad_arr = np.array(mad[:], dtype=np.float64)
+    med_arr = np.empty(f, dtype=np.float64)
+    mad_arr = np.empty(f, dtype=np.float64)
+    # (the library selects the device itself; the stream is the current one of THAT device.)  One call fits up to
+    # MAX_FIT_COLUMNS columns; the reference fits however many keys a row has (scorer.py:19-25), so wider inputs take
+    # several calls -- the seven DEWI signals take one.
+    for c0 in range(0, f, MAX_FIT_COLUMNS):
+        fc = min(MAX_FIT_COLUMNS, f - c0)
+        med = (ctypes.c_double * fc)()
+        mad = (ctypes.c_double * fc)()
+        rc = lib.dewi_fit_stats(ctypes.c_void_p(cols.data_ptr() + c0 * cols.stride(0) * cols.element_size()), n, fc,
+                                cols.stride(0), med, mad, device,
+                                ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream))
+        _native.check(rc)
+        med_arr[c0:c0 + fc] = med[:]
+        mad_arr[c0:c0 + fc] = mad[:]
     if zero_mad_as != 1e-8:
         mad_arr[mad_arr == 1e-8] = zero_mad_as  # a float32 MAD is never 1e-8 exactly unless it was zero
-    return np.array(med[:], dtype=np.float64), mad_arr
+    return med_arr, mad_arr
 
 
 @dataclass

@@ -136,3 +136,14 @@ def test_adversarial_columns_keep_fit_stats_exact(n):
     s.fit_stats_columns(sig)
     assert s.stats.medians == med, (s.stats.medians, med)
     assert s.stats.mads == mad, (s.stats.mads, mad)
+
+
+def test_more_columns_than_one_library_call_fits():
+    """`RobustStats.fit` fits every key a row has (scorer.py:19-25); one dewi_fit_stats call takes 32 columns, so the
+    wrapper splits wider inputs -- 40 columns here, medians / MADs bit-equal to numpy's."""
+    rng = np.random.RandomState(17)
+    n, f = 3001, 40
+    cols = {f"s{j:02d}": (rng.standard_normal(n) * (j + 1)).astype(np.float32) for j in range(f)}
+    got = dewi_b200.RobustStats.fit_columns(cols)
+    med, mad = oscorer.robust_fit(cols)
+    assert got.medians == med and got.mads == mad
