@@ -115,3 +115,66 @@ def test_cluster_metrics_like_the_reference():
     labels = np.array([0, 1, 1, 3, 0, 5])
     assert dewi_b200.clusters_from_labels(labels) == [[0, 4], [1, 2], [3], [5]]
     assert dewi_b200.clusters_from_labels(labels, doc_ids=list("abcdef")) == [["a", "e"], ["b", "c"], ["d"], ["f"]]
+
+
+def test_candidate_limit_of_the_wrappers():
+    """At most 400 candidates (min(2k, N), backends.py:440) per query -- 392 when `rerank_scope="full"` over-fetches
+    eight slots; small corpora are bounded by N, not by k (documented divergence)."""
+    from types import SimpleNamespace
+
+    from dewi_b200.backends import MAX_CANDIDATES, CudaIndex
+
+    check = CudaIndex._check_candidate_limit
+    assert MAX_CANDIDATES == 400
+    big = SimpleNamespace(_n_device=1_000_000, rerank_scope="candidates")
+    check(big, 10)
+    check(big, 200)
+    with pytest.raises(ValueError, match="400 candidates"):
+        check(big, 201)
+    check(SimpleNamespace(_n_device=300, rerank_scope="candidates"), 300)      # k = N = 300: every row is a candidate
+    full = SimpleNamespace(_n_device=1_000_000, rerank_scope="full")
+    check(full, 196)
+    with pytest.raises(ValueError, match="392 candidates"):
+        check(full, 197)
+    check(SimpleNamespace(_n_device=350, rerank_scope="full"), 350)
+
+
+def test_fit_columns_splits_wide_inputs_over_several_library_calls(monkeypatch):
+    """`RobustStats.fit` fits every key a row has (scorer.py:19-25); one dewi_fit_stats call takes 32 columns.  The
+    wrapper's splitting (pointer offsets, result assembly) is checked against a stand-in for the library call that
+    reads the very pointers it is handed -- the kernel itself is covered by the GPU tests."""
+    import ctypes
+    from types import SimpleNamespace
+
+    import torch
+
+    from dewi_b200 import _native, scorer
+
+    calls = []
+
+    def fake_fit_stats(ptr, n, f, ld, med, mad, device, stream):
+        assert 1 <= f <= scorer.MAX_FIT_COLUMNS
+        calls.append(f)
+        flat = np.ctypeslib.as_array((ctypes.c_float * ((f - 1) * ld + n)).from_address(ptr.value))
+        for c in range(f):
+            v = flat[c * ld: c * ld + n]
+            med[c] = float(np.median(v))
+            mad[c] = float(np.median(np.abs(v - np.float32(med[c])))) or 1e-8
+        return 0
+
+    monkeypatch.setattr(_native, "load_library", lambda: SimpleNamespace(dewi_fit_stats=fake_fit_stats))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: SimpleNamespace(cuda_stream=0))
+    rng = np.random.RandomState(3)
+    for f, n in ((7, 101), (32, 50), (33, 64), (70, 33)):
+        calls.clear()
+        host = (rng.standard_normal((f, n)) * np.arange(1, f + 1)[:, None]).astype(np.float32)
+        host[min(3, f - 1)] = 2.5                                  # a constant column: MAD 0 -> 1e-8 (scorer.py:24)
+        wide = torch.from_numpy(np.ascontiguousarray(np.pad(host, ((0, 0), (0, 5)))))[:, :n]   # row pitch n + 5
+        med, mad = scorer._fit_columns(wide, 0)
+        assert calls == [32] * (f // 32) + ([f % 32] if f % 32 else [])
+        assert np.array_equal(med, np.median(host, axis=1).astype(np.float64))
+        want_mad = np.median(np.abs(host - np.median(host, axis=1, keepdims=True)), axis=1).astype(np.float64)
+        want_mad[want_mad == 0] = 1e-8
+        assert np.array_equal(mad, want_mad)
+        med0, mad0 = scorer._fit_columns(wide, 0, zero_mad_as=0.0)  # robust.py:8-10 adds its own epsilon instead
+        assert mad0[min(3, f - 1)] == 0.0 and np.array_equal(med0, med)
