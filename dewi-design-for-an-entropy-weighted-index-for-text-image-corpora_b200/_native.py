@@ -67,6 +67,7 @@ SIGNATURES = {
     "dewi_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_double, c_int, c_void_p, c_void_p, c_void_p]),
     "dewi_index_set_blend": (c_int, [c_void_p, c_double, c_double]),
     "dewi_index_last_launches": (c_int, [c_void_p, POINTER(c_int)]),
+    "dewi_plan_probe": (c_int, [c_int, c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_int, POINTER(c_int)]),
     "dewi_index_cert_stats": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "dewi_index_set_profiling": (c_int, [c_void_p, c_int]),
     "dewi_index_sweep_ms": (c_int, [c_void_p, c_int, POINTER(c_float), POINTER(c_int)]),

@@ -1039,6 +1039,31 @@ int dewi_index_cert_stats(const dewi_index_t* h, int64_t* used, int64_t* failed)
   return 0;
 }
 
+int dewi_plan_probe(int which, int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, int q_rows, int opt,
+                    int* out) {
+  if (!out) return fail("null argument");
+  for (int i = 0; i < 10; ++i) out[i] = 0;
+  if (which == 0) {   // single-CTA sweeps: queries on M (search_tc.cu) or, with opt = batch size <= 64, rows on M (search_tcr.cu)
+    TcPlan p{};
+    const int rc = tc_make_plan(mode, dim, n_rows, n_qb, kc, sm_count, &p, 0, q_rows, opt);
+    if (rc != 0) return rc;
+    const int v[10] = {p.rows_on_m, p.q_rows, p.n_tile, p.n_stages, p.q_stages, p.q_resident, p.n_chunks, p.grid,
+                       static_cast<int>(p.smem_bytes), p.mode};
+    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    return 0;
+  }
+  if (which == 1) {   // CTA-pair sweep (search_tc2.cu); opt = 1 asks for the staged form
+    Tc2Plan p{};
+    const int rc = tc2_make_plan(mode, dim, n_rows, n_qb, kc, sm_count, &p, 0, 0, 0, opt);
+    if (rc != 0) return rc;
+    const int v[10] = {p.mode, p.n_stages, p.q_stages, p.n_chunks, p.grid, p.first_items, static_cast<int>(p.smem_bytes),
+                       2 * tc2_box_rows(), 0, 0};
+    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    return 0;
+  }
+  return fail("plan probe: which must be 0 (single-CTA sweeps) or 1 (CTA-pair sweep)");
+}
+
 int dewi_index_last_launches(const dewi_index_t* h, int* launches) {
   if (!h || !launches) return fail("null argument");
   *launches = h->last_launches;

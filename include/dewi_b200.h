@@ -151,6 +151,16 @@ DEWI_API int dewi_index_set_blend(dewi_index_t* h, double eta, double entropy_pr
  * `out_id`, `out_score` are host pointers and the call returns after the results have landed. */
 DEWI_API int dewi_index_search(dewi_index_t* h, const float* queries, int B, int k, double eta, double entropy_pref,
                       int flags, int64_t* out_id, float* out_score, void* stream);
+/* Test aid (no GPU needed): the launch plan the host-side planners choose for a sweep shape, so that CPU tests can
+ * walk the shape space and check every plan against the kernels the library instantiates (tests/test_planner_cpu.py).
+ * which = 0: single-CTA sweeps (mode 0 = one plane, 1 = two query planes, 2 = hi/lo; q_rows = 64 | 128 query rows on
+ *   MMA M; opt = batch size <= 64 to prefer the rows-on-M sweep, else 0) ->
+ *   out = { rows_on_m, q_rows, n_tile, n_stages, q_stages, q_resident, n_chunks, grid, smem_bytes, mode }.
+ * which = 1: CTA-pair sweep (n_qb even; opt = 1 asks for the staged form) ->
+ *   out = { mode, n_stages, q_stages, n_chunks, grid, first_items, smem_bytes, rows_per_tile, 0, 0 }.
+ * Non-zero when the planner has no plan for the shape (the search then falls back, see dewi_index_search_local). */
+DEWI_API int dewi_plan_probe(int which, int mode, int dim, int64_t n_rows, int n_qb, int kc, int sm_count, int q_rows,
+                    int opt, int* out);
 /* Kernel launches issued by the last search on this handle (bench.py's `gpu_launches`). */
 DEWI_API int dewi_index_last_launches(const dewi_index_t* h, int* launches);
 /* fp32 corpus: searches answered by the certified single-plane sweep so far, and how many of those had to be re-run
