@@ -159,12 +159,21 @@ class ColumnPayloads:
     def __init__(self, ids: Sequence[str], store: ColumnStore):
         self._ids = ids
         self._store = store
+        self._lookup: Optional[Dict[str, int]] = None
 
     def _row(self, doc_id: str) -> Optional[int]:
-        try:
-            return self._ids.index(doc_id)
-        except ValueError:
-            return None
+        ids = self._ids
+        if isinstance(ids, LazyIds):  # the row is parsed out of the id
+            try:
+                return ids.index(doc_id)
+            except ValueError:
+                return None
+        # explicit ids: one dict built on first use instead of an O(n) `list.index` per lookup (a `save()` of n documents
+        # would otherwise cost n^2 / 2 string comparisons).  A duplicated id resolves to its LAST row, which is the
+        # payload the reference's `_payloads[doc_id] = payload` keeps (backends.py:400).
+        if self._lookup is None:   # (the id list never changes under a view: every bulk ingest builds a new one)
+            self._lookup = {d: i for i, d in enumerate(ids)}
+        return self._lookup.get(doc_id)
 
     def get(self, doc_id: str, default=None):
         r = self._row(doc_id)
@@ -711,9 +720,11 @@ class CudaIndex(BaseIndex):
                 shards.append({"file": name, "row0": lo, "rows": m})
             meta["bf16_sidecar"] = shards
         (path / "metadata.json").write_text(json.dumps(meta))
+        by_row = self._payloads.at if isinstance(self._payloads, ColumnPayloads) else None  # (column store: no id -> row search)
         with open(path / "payloads.jsonl", "w") as f:
-            for d in self._doc_ids:
-                f.write(json.dumps({"doc_id": d, "payload": self._payloads[d].to_dict()}) + "\n")
+            for i, d in enumerate(self._doc_ids):
+                p = by_row(i) if by_row else self._payloads[d]
+                f.write(json.dumps({"doc_id": d, "payload": p.to_dict()}) + "\n")
 
     @classmethod
     def load(cls, path: Union[str, Path], **kwargs: Any) -> "CudaIndex":

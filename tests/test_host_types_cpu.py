@@ -178,3 +178,23 @@ def test_fit_columns_splits_wide_inputs_over_several_library_calls(monkeypatch):
         assert np.array_equal(mad, want_mad)
         med0, mad0 = scorer._fit_columns(wide, 0, zero_mad_as=0.0)  # robust.py:8-10 adds its own epsilon instead
         assert mad0[min(3, f - 1)] == 0.0 and np.array_equal(med0, med)
+
+
+def test_column_payload_lookup_by_explicit_ids_is_indexed():
+    """Explicit ids over a column store: lookups go through one dict (not `list.index` per call), a duplicated id
+    resolves to its last row -- the payload the reference's `_payloads[doc_id] = payload` keeps (backends.py:400)."""
+    store = ColumnStore()
+    cols = np.arange(6 * len(PAYLOAD_FIELDS), dtype=np.float32).reshape(6, -1)
+    store.append(6, cols)
+    ids = ["a", "b", "c", "b", "d", "e"]
+    view = ColumnPayloads(ids, store)
+    assert view["a"].dewi == cols[0, 0] and view["e"].dewi == cols[5, 0]
+    assert view["b"].dewi == cols[3, 0]                      # the later "b"
+    assert view.get("zz") is None and "zz" not in view and "c" in view and len(view) == 6
+    with pytest.raises(KeyError):
+        view["zz"]
+    n = 200_000                                               # 2e5 lookups: seconds with a dict, hours with list.index
+    big = ColumnStore()
+    big.append(n, None)
+    bv = ColumnPayloads([f"id{i}" for i in range(n)], big)
+    assert all(bv.get(f"id{i}") is not None for i in range(0, n, 1))
