@@ -134,3 +134,23 @@ def test_staged_first_round_respects_the_seed_window(lib):
     assert rc == 0 and plan[5] == 0, plan
     rc, plan = probe(lib, 1, 0, 64, 700_000, 8, 36, 148, 128, 1)      # k = 10: staged, 18 chunks in the first round
     assert rc == 0 and plan[5] == 18 * 4, plan
+
+
+def test_plans_of_the_benchmark_configurations(lib):
+    """The launch geometry the measured numbers in DESIGN.md section 6 were taken with (148 SMs): a regression here
+    changes what `bench.py` times."""
+    # C3 100M x 768 bf16, k = 10 (kc = 36): B <= 64 -> rows on M, one CTA per SM, resident queries (12 k-blocks)
+    rc, p = probe(lib, 0, 0, 768, 100_000_000, 1, 36, 148, 64, 64)
+    assert rc == 0 and p[:8] == [1, 64, 256, 3, 12, 1, 148, 148], p          # QN = 64: three ring stages beside the queries
+    rc, p = probe(lib, 0, 0, 768, 100_000_000, 1, 36, 148, 64, 1)
+    assert rc == 0 and p[:8] == [1, 16, 256, 4, 12, 1, 148, 148], p          # QN = 16: four
+    rc, p = probe(lib, 0, 0, 768, 100_000_000, 1, 36, 148, 128, 0)
+    assert rc == 0 and p[:8] == [0, 128, 256, 4, 2, 0, 148, 148], p          # one block of 65..128 queries: queries on M
+    # B = 4096 (32 query blocks): CTA pairs, four ring stages, items a multiple of the 74 clusters
+    rc, p = probe(lib, 1, 0, 768, 100_000_000, 32, 36, 148, 128, 0)
+    assert rc == 0 and p[1] == 4 and p[4] == 148 and (p[3] * 16) % 74 == 0 and p[5] == 0, p
+    # C2 1M x 768 fp32, certified single-plane sweep (kc = 48), staged: 4 of 41 chunks first at B = 4096, 18 of 55 at B = 1024
+    rc, p = probe(lib, 1, 0, 768, 1_000_000, 32, 48, 148, 128, 1)
+    assert rc == 0 and (p[3], p[5]) == (41, 4 * 16), p
+    rc, p = probe(lib, 1, 0, 768, 1_000_000, 8, 48, 148, 128, 1)
+    assert rc == 0 and (p[3], p[5]) == (55, 18 * 4), p
