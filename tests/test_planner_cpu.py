@@ -77,7 +77,7 @@ def test_single_cta_plans_are_launchable(lib, kernels):
                          f"mode={mode} dim={dim} n={n_rows} n_qb={n_qb} kc={kc} q_rows={q_rows} opt={opt}: {plan}")
             seen.add((plan[0], plan[9], plan[2], plan[1], plan[5]))
     # the walk reached every family: rows-on-M at each width, M = 64 resident and streamed, M = 128 on both tile sizes
-    assert {(1, 0, 128, 16, 1), (1, 0, 128, 32, 1), (1, 0, 128, 64, 1)} <= seen or any(s[0] == 1 for s in seen)
+    assert {(1, 0, 256, 16, 1), (1, 0, 256, 32, 1), (1, 0, 256, 64, 1)} <= seen
     assert any(s[0] == 0 and s[3] == 64 and s[4] == 1 for s in seen) and any(s[0] == 0 and s[3] == 64 and s[4] == 0 for s in seen)
     assert any(s[0] == 0 and s[3] == 128 and s[2] == 128 for s in seen) and any(s[0] == 0 and s[3] == 128 and s[2] == 256 for s in seen)
 
